@@ -1,0 +1,676 @@
+// rt_b200.cu -- librt_b200.so: contexts, scene upload, frame orchestration and the C ABI of
+// include/rt_b200.h.  One RtDevice per GPU this process drives; rt_init(n) drives n GPUs from one process
+// (the C++ drop-in, ncclCommInitAll), rt_init_rank() drives one GPU as a rank of a torchrun job.
+// No CPU fallback: without a CUDA device every entry point fails with RT_ERR_NO_DEVICE.
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_kernels.cuh"
+
+namespace {
+
+using namespace rt;
+
+// ---- tunables -------------------------------------------------------------------------------------
+constexpr int kRP = 2;   // ray pairs per thread (R = 4 rays)
+constexpr int kJ = 8;    // triangles per filter block (R*J = 32 candidate bits)
+constexpr uint32_t kMaxChunkSamples = 1u << 23;  // 8 Mi samples per wavefront chunk (84 B of state each)
+
+// ---- NCCL through dlopen (no link-time dependency; inside python the already-loaded torch copy is reused)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) return false;
+#define RT_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(handle, name)); if (!field) return false;
+        RT_SYM(GetUniqueId, "ncclGetUniqueId")
+        RT_SYM(CommInitRank, "ncclCommInitRank")
+        RT_SYM(CommInitAll, "ncclCommInitAll")
+        RT_SYM(CommDestroy, "ncclCommDestroy")
+        RT_SYM(AllGather, "ncclAllGather")
+        RT_SYM(GroupStart, "ncclGroupStart")
+        RT_SYM(GroupEnd, "ncclGroupEnd")
+        RT_SYM(GetErrorString, "ncclGetErrorString")
+#undef RT_SYM
+        return true;
+    }
+};
+constexpr int kNcclFloat = 7;  // ncclFloat32
+
+// ---- state ------------------------------------------------------------------------------------------
+struct RtDevice {
+    int device = 0, rank = 0;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    // scene
+    float4 *rec = nullptr, *triv = nullptr, *normal_mat = nullptr, *materials = nullptr, *spheres = nullptr;
+    int ntri = 0, ntiles = 0, nmat = 0, nspheres = 0;
+    float M_built = 0.f;
+    // per-chunk state
+    size_t cap_samples = 0;
+    float4 *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *acc = nullptr, *hit = nullptr;
+    uint32_t *lit = nullptr, *q_ray = nullptr, *q_hit = nullptr;
+    uint32_t* counters = nullptr;      // kCntWords per chunk slot
+    int counters_slots = 0;
+    int32_t* prim = nullptr; size_t cap_prim = 0;
+    // framebuffers
+    float *fb_local = nullptr, *fb_gather = nullptr, *fb_final = nullptr;
+    size_t cap_local = 0, cap_gather = 0, cap_final = 0;
+    uint8_t* fb_u8 = nullptr; size_t cap_u8 = 0;
+    cudaEvent_t ev[16] = {};
+    cudaEvent_t ev_phase[8] = {};
+    int num_sms = 148;
+};
+
+struct Global {
+    std::vector<RtDevice> devs;
+    int world = 0;          // total ranks (== devs.size() in single-process mode)
+    bool single_process = true;
+    bool scene_ready = false, frame_ready = false;
+    NcclApi nccl;
+    float scene_extent = 0.f;   // max |coordinate| over the scene
+    bool any_transparent = false;
+    rt_params last;             // params of the last frame
+    uint32_t rows_per_rank = 0;
+    rt_stats stats = {};
+    std::vector<uint32_t> host_counters;
+    std::string error;
+} g;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g.error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define NC(call)                                                                                                 \
+    do {                                                                                                         \
+        ncclResult_t r_ = (call);                                                                                \
+        if (r_ != 0) return fail(RT_ERR_NCCL, "%s failed: %s", #call, g.nccl.GetErrorString ? g.nccl.GetErrorString(r_) : "?"); \
+    } while (0)
+
+template <class T>
+int ensure(T*& ptr, size_t& cap, size_t need) {
+    if (need <= cap && ptr) return RT_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    CU(cudaMalloc(&ptr, need * sizeof(T)));
+    cap = need;
+    return RT_OK;
+}
+
+int create_device(RtDevice& d, int device, int rank) {
+    d.device = device; d.rank = rank;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    for (auto& e : d.ev) CU(cudaEventCreate(&e));
+    for (auto& e : d.ev_phase) CU(cudaEventCreate(&e));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(RT_ERR_NO_DEVICE, "device %d is sm_%d%d; librt_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    d.num_sms = prop.multiProcessorCount;
+    return RT_OK;
+}
+
+void destroy_device(RtDevice& d) {
+    cudaSetDevice(d.device);
+    if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
+    void* ptrs[] = {d.rec, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+                    d.q_hit, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& e : d.ev) if (e) cudaEventDestroy(e);
+    for (auto& e : d.ev_phase) if (e) cudaEventDestroy(e);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    d = RtDevice();
+}
+
+int check_ready() {
+    if (g.devs.empty()) return fail(RT_ERR_STATE, "rt_init has not been called (or failed): there is no CPU fallback");
+    return RT_OK;
+}
+
+float pow2_ceil(float v) {
+    float m = 1.0f / 1024.0f;
+    while (m < v) m *= 2.0f;
+    return m;
+}
+
+// (Re)build the filter records when the magnitude bound M grows.
+int build_records(RtDevice& d, float M) {
+    if (d.M_built >= M && d.rec) return RT_OK;
+    CU(cudaSetDevice(d.device));
+    const int npad = d.ntiles * kTile;
+    k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.ntri, npad, M, d.rec);
+    CU(cudaGetLastError());
+    d.M_built = M;
+    return RT_OK;
+}
+
+int ensure_chunk_state(RtDevice& d, size_t nsamples, bool want_prim, size_t prim_total) {
+    CU(cudaSetDevice(d.device));
+    if (nsamples > d.cap_samples) {
+        void** ptrs[] = {(void**)&d.ray_o, (void**)&d.ray_d, (void**)&d.thr, (void**)&d.acc, (void**)&d.hit, (void**)&d.lit, (void**)&d.q_ray, (void**)&d.q_hit};
+        const size_t sizes[] = {16, 16, 16, 16, 16, 4, 4, 4};
+        for (int i = 0; i < 8; ++i) {
+            if (*ptrs[i]) cudaFree(*ptrs[i]);
+            *ptrs[i] = nullptr;
+            CU(cudaMalloc(ptrs[i], sizes[i] * nsamples));
+        }
+        d.cap_samples = nsamples;
+    }
+    if (want_prim) { int rc = ensure(d.prim, d.cap_prim, prim_total); if (rc) return rc; }
+    return RT_OK;
+}
+
+int ensure_counters(RtDevice& d, int slots) {
+    if (slots <= d.counters_slots && d.counters) return RT_OK;
+    if (d.counters) cudaFree(d.counters);
+    d.counters = nullptr;
+    CU(cudaMalloc(&d.counters, sizeof(uint32_t) * kCntWords * slots));
+    d.counters_slots = slots;
+    return RT_OK;
+}
+
+void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float eps_r, uint32_t* counters) {
+    memset(&P, 0, sizeof(P));
+    P.rec = d.rec; P.triv = d.triv; P.normal_mat = d.normal_mat; P.materials = d.materials; P.spheres = d.spheres;
+    P.ntri = d.ntri; P.ntiles = d.ntiles; P.nspheres = d.nspheres;
+    P.ray_o = d.ray_o; P.ray_d = d.ray_d; P.thr = d.thr; P.acc = d.acc; P.hit = d.hit; P.lit = d.lit;
+    P.q_ray = d.q_ray; P.q_hit = d.q_hit; P.counters = counters;
+    P.eps_r = eps_r;
+    memcpy(P.camera, rp.camera, sizeof(P.camera));
+    P.nlights = (int)rp.n_lights;
+    memcpy(P.lights, rp.lights, sizeof(P.lights));
+    P.features = rp.features;
+    P.max_lvl = rp.max_lvl;
+}
+
+// Wavefront for one chunk whose rays are either generated (primary) or already in ray_o/ray_d (trace API).
+int run_wavefront(RtDevice& d, const FrameParams& P, int grid_scan) {
+    const bool shadows = (P.features & RT_SHADOWS) && P.nlights > 0;
+    const bool bounces = (P.features & (RT_REFLECTION | RT_REFRACTION)) != 0;
+    const int levels = bounces ? std::min(P.max_lvl + 1, kMaxLevels - 2) : 1;
+    const int grid_shade = d.num_sms * 4;
+    for (int level = 0; level < levels; ++level) {
+        if (level == 0) k_trace<kRP, kJ, true><<<grid_scan, kThreads, 0, d.stream>>>(P, 0);
+        else k_trace<kRP, kJ, false><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
+        if (shadows) {
+            if (g.any_transparent) k_shadow<kRP, kJ, true><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
+            else k_shadow<kRP, kJ, false><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
+        }
+        k_shade<<<grid_shade, 256, 0, d.stream>>>(P, level);
+    }
+    CU(cudaGetLastError());
+    return levels;
+}
+
+float magnitude_bound(const rt_params& rp, const float* extra, int n_extra) {
+    float m = g.scene_extent + 0.5f;
+    for (int c = 0; c < 4; ++c)
+        for (int k = 0; k < 3; ++k) m = std::max(m, std::fabs(rp.corners[c * 6 + k]));  // ray origins on the near plane
+    for (int i = 0; i < n_extra; ++i) m = std::max(m, std::fabs(extra[i]));
+    return pow2_ceil(m);
+}
+
+float eps_r_for(float M) { return M * (24.0f * kU32 / kCosMin + 64.0f * kU32); }
+
+int validate_params(const rt_params* p, bool need_frame) {
+    if (!p) return fail(RT_ERR_INVALID, "params is NULL");
+    if (need_frame && (p->width == 0 || p->height == 0 || p->pixelfactor_x == 0 || p->pixelfactor_y == 0))
+        return fail(RT_ERR_INVALID, "width/height/pixelfactor must be >= 1");
+    if (p->n_lights > RT_MAX_LIGHTS) return fail(RT_ERR_INVALID, "at most %d lights", RT_MAX_LIGHTS);
+    if (p->max_lvl < 0 || p->max_lvl > kMaxLevels - 3) return fail(RT_ERR_INVALID, "max_lvl must be in [0, %d]", kMaxLevels - 3);
+    return RT_OK;
+}
+
+int render_enqueue(const rt_params* rp) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (!g.scene_ready) return fail(RT_ERR_STATE, "rt_render before rt_upload_scene");
+    rc = validate_params(rp, true);
+    if (rc) return rc;
+    const uint32_t W = rp->width, H = rp->height, G = (uint32_t)g.world;
+    const uint32_t spp = rp->pixelfactor_x * rp->pixelfactor_y;
+    const uint32_t rows_per_rank = (H + G - 1) / G;
+    const float M = magnitude_bound(*rp, nullptr, 0);
+    const float eps_r = eps_r_for(M);
+    const size_t row_samples = (size_t)W * spp;
+    if (row_samples > kMaxChunkSamples * 4ull) return fail(RT_ERR_INVALID, "one row of samples (%zu) is too large", row_samples);
+    const uint32_t rows_per_chunk = (uint32_t)std::max<size_t>(1, kMaxChunkSamples / row_samples);
+
+    for (RtDevice& d : g.devs) {
+        CU(cudaSetDevice(d.device));
+        const uint32_t my_rows = (H > (uint32_t)d.rank) ? (H - d.rank + G - 1) / G : 0;
+        const uint32_t nchunks = (my_rows + rows_per_chunk - 1) / rows_per_chunk;
+        const size_t chunk_cap = (size_t)std::min(rows_per_chunk, std::max(my_rows, 1u)) * row_samples;
+        rc = build_records(d, M); if (rc) return rc;
+        rc = ensure_chunk_state(d, chunk_cap, rp->want_prim_id != 0, (size_t)rows_per_rank * row_samples); if (rc) return rc;
+        rc = ensure_counters(d, std::max(1u, nchunks)); if (rc) return rc;
+        size_t need_local = (size_t)rows_per_rank * W * 3;
+        rc = ensure(d.fb_local, d.cap_local, need_local); if (rc) return rc;
+        if (G > 1) {
+            rc = ensure(d.fb_gather, d.cap_gather, need_local * G); if (rc) return rc;
+            rc = ensure(d.fb_final, d.cap_final, (size_t)W * H * 3); if (rc) return rc;
+        }
+        CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords * std::max(1u, nchunks), d.stream));
+        if (my_rows < rows_per_rank) CU(cudaMemsetAsync(d.fb_local, 0, need_local * sizeof(float), d.stream));
+        if (rp->want_prim_id) CU(cudaMemsetAsync(d.prim, 0xff, sizeof(int32_t) * rows_per_rank * row_samples, d.stream));
+        CU(cudaEventRecord(d.ev_phase[0], d.stream));
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            FrameParams P;
+            fill_common(P, d, *rp, eps_r, d.counters + (size_t)c * kCntWords);
+            memcpy(P.corners, rp->corners, sizeof(P.corners));
+            P.divX = (float)(W * rp->pixelfactor_x - 1);   // main.cpp:360 (unsigned arithmetic, then float)
+            P.divY = (float)(H * rp->pixelfactor_y - 1);   // main.cpp:361
+            P.W = W; P.H = H; P.pfx = rp->pixelfactor_x; P.pfy = rp->pixelfactor_y;
+            P.row0 = c * rows_per_chunk;
+            P.nrows = std::min(rows_per_chunk, my_rows - P.row0);
+            P.G = G; P.rank = (uint32_t)d.rank;
+            P.nsamples = (uint32_t)(P.nrows * row_samples);
+            P.sample_base = (uint32_t)(P.row0 * row_samples);
+            P.prim_out = rp->want_prim_id ? d.prim : nullptr;
+            const int grid_scan = d.num_sms * 2;
+            int levels = run_wavefront(d, P, grid_scan);
+            if (levels < 0) return levels;
+            g.stats.n_levels = (uint32_t)levels;
+            k_resolve<<<d.num_sms * 4, 256, 0, d.stream>>>(P, d.fb_local);
+            CU(cudaGetLastError());
+        }
+        CU(cudaEventRecord(d.ev_phase[1], d.stream));
+    }
+    // one all-gather per frame (rank-major slabs), then de-interleave rows
+    if (G > 1) {
+        const size_t count = (size_t)rows_per_rank * W * 3;
+        if (g.single_process) NC(g.nccl.GroupStart());
+        for (RtDevice& d : g.devs) {
+            CU(cudaSetDevice(d.device));
+            NC(g.nccl.AllGather(d.fb_local, d.fb_gather, count, kNcclFloat, d.comm, d.stream));
+        }
+        if (g.single_process) NC(g.nccl.GroupEnd());
+        for (RtDevice& d : g.devs) {
+            CU(cudaSetDevice(d.device));
+            k_deinterleave<<<d.num_sms * 4, 256, 0, d.stream>>>(d.fb_gather, d.fb_final, W, H, G, rows_per_rank);
+            CU(cudaGetLastError());
+        }
+    }
+    for (RtDevice& d : g.devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaEventRecord(d.ev_phase[2], d.stream));
+    }
+    g.last = *rp;
+    g.rows_per_rank = rows_per_rank;
+    g.frame_ready = true;
+    return RT_OK;
+}
+
+int sync_all() {
+    for (RtDevice& d : g.devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaStreamSynchronize(d.stream));
+    }
+    return RT_OK;
+}
+
+// Gather ray counters of the last frame from device 0..n (this process's share).
+int collect_stats() {
+    rt_stats& st = g.stats;
+    const uint32_t levels = st.n_levels;
+    st = rt_stats();
+    st.n_levels = levels;
+    st.n_gpus = (uint32_t)g.world;
+    st.rank = g.devs.empty() ? 0 : (uint32_t)g.devs[0].rank;
+    const rt_params& rp = g.last;
+    const bool shadows = (rp.features & RT_SHADOWS) && rp.n_lights > 0;
+    for (RtDevice& d : g.devs) {
+        CU(cudaSetDevice(d.device));
+        st.n_triangles = (uint32_t)d.ntri;
+        g.host_counters.resize((size_t)kCntWords * d.counters_slots);
+        CU(cudaMemcpy(g.host_counters.data(), d.counters, sizeof(uint32_t) * g.host_counters.size(), cudaMemcpyDeviceToHost));
+        const uint32_t H = rp.height, G = (uint32_t)g.world;
+        const uint32_t my_rows = (H > (uint32_t)d.rank) ? (H - d.rank + G - 1) / G : 0;
+        st.primary_rays += (uint64_t)my_rows * rp.width * rp.pixelfactor_x * rp.pixelfactor_y;
+        for (int c = 0; c < d.counters_slots; ++c) {
+            const uint32_t* cw = &g.host_counters[(size_t)c * kCntWords];
+            for (int l = 0; l < kMaxLevels; ++l) {
+                if (shadows) st.shadow_rays += (uint64_t)cw[kCntHit + l] * rp.n_lights;
+                if (l > 0) st.bounce_rays += cw[kCntRay + l];
+            }
+            st.exact_evals += (uint64_t)cw[kCntExact] | ((uint64_t)cw[kCntExact + 1] << 32);
+        }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, d.ev_phase[0], d.ev_phase[1]) == cudaSuccess) st.ms_intersect = std::max(st.ms_intersect, ms);
+        if (cudaEventElapsedTime(&ms, d.ev_phase[1], d.ev_phase[2]) == cudaSuccess) st.ms_gather = std::max(st.ms_gather, ms);
+        if (cudaEventElapsedTime(&ms, d.ev_phase[0], d.ev_phase[2]) == cudaSuccess) st.ms_total = std::max(st.ms_total, ms);
+    }
+    st.tri_tests = (st.primary_rays + st.shadow_rays + st.bounce_rays) * (uint64_t)st.n_triangles;
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rt_last_error(void) { return g.error.c_str(); }
+
+void rt_shutdown(void) {
+    for (RtDevice& d : g.devs) destroy_device(d);
+    g.devs.clear();
+    g.world = 0;
+    g.scene_ready = g.frame_ready = false;
+}
+
+int rt_init(int n_gpus) {
+    rt_shutdown();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(RT_ERR_NO_DEVICE, "no CUDA device (%s); librt_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count == 0");
+    if (n_gpus < 1 || n_gpus > count) return fail(RT_ERR_INVALID, "n_gpus=%d but %d device(s) are visible", n_gpus, count);
+    g.devs.resize(n_gpus);
+    g.world = n_gpus;
+    g.single_process = true;
+    for (int i = 0; i < n_gpus; ++i) {
+        int rc = create_device(g.devs[i], i, i);
+        if (rc) { rt_shutdown(); return rc; }
+    }
+    if (n_gpus > 1) {
+        if (!g.nccl.load()) { rt_shutdown(); return fail(RT_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror()); }
+        std::vector<ncclComm_t> comms(n_gpus);
+        std::vector<int> ids(n_gpus);
+        for (int i = 0; i < n_gpus; ++i) ids[i] = i;
+        ncclResult_t r = g.nccl.CommInitAll(comms.data(), n_gpus, ids.data());
+        if (r != 0) { rt_shutdown(); return fail(RT_ERR_NCCL, "ncclCommInitAll failed: %s", g.nccl.GetErrorString(r)); }
+        for (int i = 0; i < n_gpus; ++i) g.devs[i].comm = comms[i];
+    }
+    return RT_OK;
+}
+
+int rt_nccl_unique_id(void* out, size_t cap, size_t* bytes) {
+    if (!g.nccl.load()) return fail(RT_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    if (cap < sizeof(ncclUniqueId)) return fail(RT_ERR_INVALID, "need %zu bytes for an ncclUniqueId", sizeof(ncclUniqueId));
+    ncclUniqueId id;
+    NC(g.nccl.GetUniqueId(&id));
+    memcpy(out, &id, sizeof(id));
+    if (bytes) *bytes = sizeof(id);
+    return RT_OK;
+}
+
+int rt_init_rank(int device, int rank, int world, const void* nccl_id, size_t nccl_id_bytes) {
+    rt_shutdown();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(RT_ERR_NO_DEVICE, "no CUDA device (%s); librt_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count == 0");
+    if (device < 0 || device >= count || world < 1 || rank < 0 || rank >= world) return fail(RT_ERR_INVALID, "bad device/rank/world %d/%d/%d", device, rank, world);
+    g.devs.resize(1);
+    g.world = world;
+    g.single_process = false;
+    int rc = create_device(g.devs[0], device, rank);
+    if (rc) { rt_shutdown(); return rc; }
+    if (world > 1) {
+        if (!g.nccl.load()) { rt_shutdown(); return fail(RT_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror()); }
+        if (!nccl_id || nccl_id_bytes < sizeof(ncclUniqueId)) { rt_shutdown(); return fail(RT_ERR_INVALID, "world > 1 needs an ncclUniqueId"); }
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof(id));
+        ncclResult_t r = g.nccl.CommInitRank(&g.devs[0].comm, world, id, rank);
+        if (r != 0) { rt_shutdown(); return fail(RT_ERR_NCCL, "ncclCommInitRank failed: %s", g.nccl.GetErrorString(r)); }
+    }
+    return RT_OK;
+}
+
+int rt_upload_scene(const rt_scene* sc) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (!sc || (sc->n_triangles && (!sc->v0 || !sc->v1 || !sc->v2 || !sc->normal || !sc->tri_material)) || !sc->materials || sc->n_materials == 0)
+        return fail(RT_ERR_INVALID, "incomplete rt_scene");
+    if (sc->n_spheres && !sc->spheres) return fail(RT_ERR_INVALID, "n_spheres > 0 but spheres is NULL");
+    const uint32_t n = sc->n_triangles;
+    for (uint32_t i = 0; i < n; ++i)
+        if (sc->tri_material[i] >= sc->n_materials) return fail(RT_ERR_INVALID, "triangle %u uses material %u of %u", i, sc->tri_material[i], sc->n_materials);
+    for (uint32_t i = 0; i < sc->n_spheres; ++i)
+        if (sc->spheres[i].material >= sc->n_materials) return fail(RT_ERR_INVALID, "sphere %u uses material %u of %u", i, sc->spheres[i].material, sc->n_materials);
+
+    // host-side packing: exact corners (3 float4 per triangle), normal+material, bounds
+    std::vector<float4> triv((size_t)3 * std::max(n, 1u)), nm(std::max(n, 1u));
+    float extent = 0.f;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* c[3] = {sc->v0 + 4 * i, sc->v1 + 4 * i, sc->v2 + 4 * i};
+        for (int k = 0; k < 3; ++k) {
+            triv[3 * i + k] = make_float4(c[k][0], c[k][1], c[k][2], 0.f);
+            for (int a = 0; a < 3; ++a) if (std::isfinite(c[k][a])) extent = std::max(extent, std::fabs(c[k][a]));
+        }
+        float4 v = make_float4(sc->normal[4 * i], sc->normal[4 * i + 1], sc->normal[4 * i + 2], 0.f);
+        memcpy(&v.w, &sc->tri_material[i], 4);
+        nm[i] = v;
+    }
+    std::vector<float4> sph((size_t)2 * std::max(sc->n_spheres, 1u));
+    for (uint32_t i = 0; i < sc->n_spheres; ++i) {
+        const rt_sphere& s = sc->spheres[i];
+        sph[2 * i] = make_float4(s.center[0], s.center[1], s.center[2], s.radius);
+        float4 m = make_float4(0, 0, 0, 0);
+        memcpy(&m.x, &s.material, 4);
+        sph[2 * i + 1] = m;
+        for (int a = 0; a < 3; ++a) extent = std::max(extent, std::fabs(s.center[a]) + std::fabs(s.radius));
+    }
+    g.any_transparent = false;
+    for (uint32_t i = 0; i < sc->n_materials; ++i)
+        if ((sc->materials[i].flags & RT_HAS_TR) && sc->materials[i].Tr < 1.0f) g.any_transparent = true;
+    g.scene_extent = extent;
+
+    for (RtDevice& d : g.devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaStreamSynchronize(d.stream));
+        for (float4** p : {&d.rec, &d.triv, &d.normal_mat, &d.materials, &d.spheres}) { if (*p) cudaFree(*p); *p = nullptr; }
+        d.ntri = (int)n;
+        d.ntiles = std::max(1, (int)((n + kTile - 1) / kTile));
+        d.nmat = (int)sc->n_materials;
+        d.nspheres = (int)sc->n_spheres;
+        d.M_built = 0.f;
+        CU(cudaMalloc(&d.rec, sizeof(float4) * (size_t)d.ntiles * kTile * kRecVec));
+        CU(cudaMalloc(&d.triv, sizeof(float4) * triv.size()));
+        CU(cudaMalloc(&d.normal_mat, sizeof(float4) * nm.size()));
+        CU(cudaMalloc(&d.materials, sizeof(rt_material) * sc->n_materials));
+        CU(cudaMalloc(&d.spheres, sizeof(float4) * sph.size()));
+        CU(cudaMemcpyAsync(d.triv, triv.data(), sizeof(float4) * triv.size(), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.normal_mat, nm.data(), sizeof(float4) * nm.size(), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.materials, sc->materials, sizeof(rt_material) * sc->n_materials, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.spheres, sph.data(), sizeof(float4) * sph.size(), cudaMemcpyHostToDevice, d.stream));
+        CU(cudaStreamSynchronize(d.stream));  // host staging vectors die at return
+    }
+    g.scene_ready = true;
+    g.frame_ready = false;
+    return RT_OK;
+}
+
+int rt_render_async(const rt_params* params) { return render_enqueue(params); }
+
+int rt_sync(void) {
+    int rc = check_ready();
+    if (rc) return rc;
+    return sync_all();
+}
+
+int rt_render(const rt_params* params) {
+    int rc = render_enqueue(params);
+    if (rc) return rc;
+    return sync_all();
+}
+
+int rt_download_framebuffer(float* rgb, int32_t* prim_id) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (!g.frame_ready) return fail(RT_ERR_STATE, "rt_download_framebuffer before rt_render");
+    if (!rgb && !prim_id) return fail(RT_ERR_INVALID, "nothing to download");
+    RtDevice& d0 = g.devs[0];
+    const rt_params& rp = g.last;
+    const uint32_t W = rp.width, H = rp.height, G = (uint32_t)g.world;
+    CU(cudaSetDevice(d0.device));
+    CU(cudaStreamSynchronize(d0.stream));
+    if (rgb) {
+        const float* src = (G > 1) ? d0.fb_final : d0.fb_local;
+        CU(cudaMemcpy(rgb, src, sizeof(float) * 3 * W * H, cudaMemcpyDeviceToHost));
+    }
+    if (prim_id) {
+        if (!rp.want_prim_id) return fail(RT_ERR_STATE, "prim_id requested but the frame was rendered with want_prim_id == 0");
+        const size_t row = (size_t)W * rp.pixelfactor_x * rp.pixelfactor_y;
+        if (g.single_process) {
+            std::vector<int32_t> tmp((size_t)g.rows_per_rank * row);
+            for (RtDevice& d : g.devs) {
+                CU(cudaSetDevice(d.device));
+                CU(cudaStreamSynchronize(d.stream));
+                CU(cudaMemcpy(tmp.data(), d.prim, sizeof(int32_t) * tmp.size(), cudaMemcpyDeviceToHost));
+                for (uint32_t ly = 0; (size_t)ly * G + d.rank < H; ++ly)
+                    memcpy(prim_id + ((size_t)ly * G + d.rank) * row, tmp.data() + (size_t)ly * row, sizeof(int32_t) * row);
+            }
+        } else {
+            // one process per GPU: only this rank's rows are known here; the others are left as -2
+            std::vector<int32_t> tmp((size_t)g.rows_per_rank * row);
+            CU(cudaMemcpy(tmp.data(), d0.prim, sizeof(int32_t) * tmp.size(), cudaMemcpyDeviceToHost));
+            if (G > 1) for (size_t i = 0; i < (size_t)H * row; ++i) prim_id[i] = -2;
+            for (uint32_t ly = 0; (size_t)ly * G + d0.rank < H; ++ly)
+                memcpy(prim_id + ((size_t)ly * G + d0.rank) * row, tmp.data() + (size_t)ly * row, sizeof(int32_t) * row);
+        }
+    }
+    return RT_OK;
+}
+
+int rt_download_framebuffer_u8(uint8_t* rgb8) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (!g.frame_ready) return fail(RT_ERR_STATE, "rt_download_framebuffer_u8 before rt_render");
+    if (!rgb8) return fail(RT_ERR_INVALID, "rgb8 is NULL");
+    RtDevice& d0 = g.devs[0];
+    const size_t n = (size_t)3 * g.last.width * g.last.height;
+    CU(cudaSetDevice(d0.device));
+    rc = ensure(d0.fb_u8, d0.cap_u8, n);
+    if (rc) return rc;
+    const float* src = (g.world > 1) ? d0.fb_final : d0.fb_local;
+    k_quantise<<<d0.num_sms * 4, 256, 0, d0.stream>>>(src, d0.fb_u8, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rgb8, d0.fb_u8, n, cudaMemcpyDeviceToHost, d0.stream));
+    CU(cudaStreamSynchronize(d0.stream));
+    return RT_OK;
+}
+
+int rt_trace(const rt_params* rp, int n, const float* origins, const float* dests, float* rgb, int32_t* prim_id, float* hit) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (!g.scene_ready) return fail(RT_ERR_STATE, "rt_trace before rt_upload_scene");
+    rc = validate_params(rp, false);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!origins || !dests || !rgb))) return fail(RT_ERR_INVALID, "bad rt_trace arguments");
+    if (n == 0) return RT_OK;
+    if ((size_t)n > kMaxChunkSamples) return fail(RT_ERR_INVALID, "rt_trace: at most %u rays per call", kMaxChunkSamples);
+    RtDevice& d = g.devs[0];
+    CU(cudaSetDevice(d.device));
+    float M = magnitude_bound(*rp, origins, 3 * n);
+    rc = build_records(d, M); if (rc) return rc;
+    rc = ensure_chunk_state(d, (size_t)n, false, 0); if (rc) return rc;
+    rc = ensure_counters(d, 1); if (rc) return rc;
+    std::vector<float4> ho(n), hd(n), ht(n, make_float4(1.f, 1.f, 1.f, 0.f)), ha(n, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int i = 0; i < n; ++i) {
+        ho[i] = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], 0.f);
+        hd[i] = make_float4(dests[3 * i], dests[3 * i + 1], dests[3 * i + 2], 0.f);  // w = lvl 0
+    }
+    CU(cudaMemcpyAsync(d.ray_o, ho.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(d.ray_d, hd.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(d.thr, ht.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(d.acc, ha.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords, d.stream));
+    FrameParams P;
+    fill_common(P, d, *rp, eps_r_for(M), d.counters);
+    P.trace_api = 1;
+    P.nsamples = (uint32_t)n;
+    P.G = 1;
+    // level 0 alone first, so that the primary hit records can be read back before bounces overwrite them
+    std::vector<float4> hh;
+    if (prim_id || hit) {
+        FrameParams P0 = P;
+        P0.features &= ~(RT_REFLECTION | RT_REFRACTION | RT_SHADOWS);
+        k_trace<kRP, kJ, true><<<d.num_sms * 2, kThreads, 0, d.stream>>>(P0, 0);
+        CU(cudaGetLastError());
+        hh.resize(n);
+        CU(cudaMemcpyAsync(hh.data(), d.hit, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords, d.stream));
+    }
+    int levels = run_wavefront(d, P, d.num_sms * 2);
+    if (levels < 0) return levels;
+    CU(cudaMemcpyAsync(ha.data(), d.acc, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    for (int i = 0; i < n; ++i) {
+        rgb[3 * i] = ha[i].x; rgb[3 * i + 1] = ha[i].y; rgb[3 * i + 2] = ha[i].z;
+        if (prim_id) memcpy(&prim_id[i], &hh[i].w, 4);
+        if (hit) { hit[3 * i] = hh[i].x; hit[3 * i + 1] = hh[i].y; hit[3 * i + 2] = hh[i].z; }
+    }
+    return RT_OK;
+}
+
+int rt_get_stats(rt_stats* out) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (!out) return fail(RT_ERR_INVALID, "out is NULL");
+    if (!g.frame_ready) return fail(RT_ERR_STATE, "rt_get_stats before rt_render");
+    rc = sync_all();
+    if (rc) return rc;
+    rc = collect_stats();
+    if (rc) return rc;
+    *out = g.stats;
+    return RT_OK;
+}
+
+int rt_event_record(int slot) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (slot < 0 || slot >= 16) return fail(RT_ERR_INVALID, "event slot out of range");
+    for (RtDevice& d : g.devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaEventRecord(d.ev[slot], d.stream));
+    }
+    return RT_OK;
+}
+
+int rt_event_elapsed_ms(int a, int b, float* ms) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (a < 0 || a >= 16 || b < 0 || b >= 16 || !ms) return fail(RT_ERR_INVALID, "bad event arguments");
+    float worst = 0.f;
+    for (RtDevice& d : g.devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaEventSynchronize(d.ev[b]));
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, d.ev[a], d.ev[b]));
+        worst = std::max(worst, t);
+    }
+    *ms = worst;
+    return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,781 @@
+// rt_kernels.cuh -- the sm_100a kernels of the render hot path.
+//
+// Reference functions replaced (paths under /root/reference/CG_Project):
+//   k_build_records   -- (new) per-triangle filter records; uses u,v,n,uu,uv,vv,D of raytracing.cpp:106-140
+//   k_trace           -- main.cpp:377-388 ray generation (PRIMARY) + intersectMesh raytracing.cpp:161-192
+//   k_shadow          -- isShadow raytracing.cpp:241-261
+//   k_shade           -- shade/diffuseOnly/blinnPhongSpecularOnly/reflection/refraction/addOffset/trace
+//                        raytracing.cpp:197-232, 266-330, 335-406
+//   k_resolve         -- main.cpp:391-393 + RGBValue clamp main.cpp:24-42
+//   k_deinterleave / k_quantise -- row gather after the all-gather; Image::writeImage's quantiser main.cpp:117
+//
+// How parity and speed coexist (DESIGN.md "filter + exact"):
+//   every (ray, triangle) pair first goes through a CONSERVATIVE FILTER evaluated with packed FP32 FMAs
+//   (FFMA2, two rays per instruction) on a precomputed 64-byte plane record; the filter may only say
+//   "certainly not a hit / certainly not nearer than the current best".  Pairs it cannot rule out are
+//   re-evaluated by exact_ray_triangle(), the reference's expression order with non-contracted IEEE
+//   operations, and only that exact result ever updates the nearest hit -- so primitive ids and hit
+//   points are the reference's, bit for bit, while ~all the work runs at FMA-pipe speed.
+#pragma once
+#include "rt_common.cuh"
+#include "../../include/rt_b200.h"
+
+namespace rt {
+
+constexpr int kTile = 128;         // triangles per shared-memory tile
+constexpr int kRecVec = 4;         // float4 per filter record (64 B)
+constexpr int kStages = 4;         // TMA ring depth
+constexpr int kWarps = 8;          // all warps are consumers; the last warp to finish a stage refills it
+constexpr int kThreads = kWarps * 32;
+constexpr uint32_t kTileBytes = kTile * kRecVec * sizeof(float4);
+
+constexpr float kU32 = 5.9604645e-8f;  // 2^-24
+constexpr float kCosMin = 1.0e-3f;     // |cos(ray, plane normal)| below this -> always exact ("grazing")
+
+// counters[] layout (uint32 unless noted)
+constexpr int kMaxLevels = 40;
+constexpr int kCntHit = 0;                 // [level] hits found by k_trace at that level
+constexpr int kCntRay = kMaxLevels;        // [level] rays queued for k_trace at that level
+constexpr int kCntExact = 2 * kMaxLevels;  // 64-bit: exact re-evaluations (2 words)
+constexpr int kCntWords = 2 * kMaxLevels + 4;
+
+struct FrameParams {
+    // scene
+    const float4* rec;          // filter records, ntiles*kTile*4 float4
+    const float4* triv;         // exact corners: 3 float4 per triangle
+    const float4* normal_mat;   // xyz unit face normal, w = material index (bits)
+    const float4* materials;    // 4 float4 per material: Kd|Ns, Ka|Ni, Ks|Tr, flags
+    const float4* spheres;      // 2 float4 per sphere: center|radius, material bits
+    int ntri, ntiles, nspheres;
+    // per-sample state (chunk local)
+    float4* ray_o;              // xyz origin
+    float4* ray_d;              // xyz dest, w = lvl (bits)
+    float4* thr;                // rgb throughput (product of K along the chain)
+    float4* acc;                // rgb accumulated colour
+    float4* hit;                // xyz intersection, w = primitive id (bits), -1 = miss
+    uint32_t* lit;              // bit l: light l reaches the hit point
+    uint32_t* q_ray;
+    uint32_t* q_hit;
+    uint32_t* counters;
+    int32_t* prim_out;          // optional: primary primitive id per local sample
+    // frame
+    float corners[24];
+    float divX, divY;
+    uint32_t W, H, pfx, pfy;
+    uint32_t row0, nrows;       // local rows of this chunk
+    uint32_t G, rank;           // row interleave: global y = local_row * G + rank
+    uint32_t nsamples;          // samples in this chunk
+    uint32_t sample_base;       // local sample index of the chunk's first sample
+    float eps_r;                // distance guard band of the filter
+    float camera[3];
+    int nlights;
+    float lights[RT_MAX_LIGHTS][3];
+    uint32_t features;
+    int max_lvl;
+    int trace_api;              // 1: rays come from ray_o/ray_d (rt_trace), not from the camera
+};
+
+// ------------------------------------------------------------------------------------------------
+// Filter records
+// ------------------------------------------------------------------------------------------------
+// Record of triangle i (4 float4):
+//   q0 = ( nx, ny, nz, dn )   unit plane normal, dn = -n.T0        -> aneg = n.O' + dn, b = n.d
+//   q1 = ( sx, sy, sz, ds')   s(P) = S.P + ds, ds' = ds + E0       (first barycentric of raytracing.cpp:144)
+//   q2 = ( tx, ty, tz, dt')   t(P) = T.P + dt, dt' = dt + E0       (second barycentric, :148)
+//   q3 = ( c1, -E1, bmin, 0 ) c1 = 1 + 3*E0
+// A pair is a CANDIDATE (goes to the exact path) iff
+//   ( min(s', t', c1 - s' - t') >= -E1*|1/b|  and  0 <= r' < rhi' )  or  |b| < bmin
+// with r' = aneg/(-b) (distance along the unit direction from the shifted origin O' = O - eps_r*d).
+//   bmin = kCosMin : normal triangle;   bmin = -1 : never a candidate (degenerate n == 0, padding);
+//   bmin = +inf    : always a candidate (ill-conditioned triangle, or one whose D is 0/NaN so that the
+//                    reference's NaN barycentrics pass its tests).
+// E0/E1 bound the difference between this evaluation and the reference's own rounding.
+__global__ void k_build_records(const float4* __restrict__ triv, int ntri, int npad, float M, float4* __restrict__ rec) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = make_float4(0, 0, -1.0f, 0);  // "never"
+    if (i < ntri) {
+        const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
+        // the reference's own float quantities decide degeneracy (raytracing.cpp:106-109,134-140)
+        v3 uf = e_sub(mk3(B), mk3(A)), vf = e_sub(mk3(C), mk3(A));
+        v3 nf = e_cross(uf, vf);
+        const bool null_n = (nf.x == 0.0f && nf.y == 0.0f && nf.z == 0.0f);
+        float uuf = e_dot(uf, uf), uvf = e_dot(uf, vf), vvf = e_dot(vf, vf);
+        float Df = __fsub_rn(__fmul_rn(uvf, uvf), __fmul_rn(uuf, vvf));
+        if (!null_n) {
+            bool always = !(fabsf(Df) > 0.0f) || !isfinite(Df);
+            double ux = (double)B.x - A.x, uy = (double)B.y - A.y, uz = (double)B.z - A.z;
+            double vx = (double)C.x - A.x, vy = (double)C.y - A.y, vz = (double)C.z - A.z;
+            double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+            double nn = sqrt(nx * nx + ny * ny + nz * nz);
+            double uu = ux * ux + uy * uy + uz * uz, uv = ux * vx + uy * vy + uz * vz, vv = vx * vx + vy * vy + vz * vz;
+            double D = uv * uv - uu * vv;
+            if (!(nn > 0.0) || !(D < 0.0) || !isfinite(nn) || !isfinite(D)) always = true;
+            if (!always) {
+                double inv = 1.0 / nn;
+                nx *= inv; ny *= inv; nz *= inv;
+                double sx = (uv * vx - vv * ux) / D, sy = (uv * vy - vv * uy) / D, sz = (uv * vz - vv * uz) / D;
+                double tx = (uv * ux - uu * vx) / D, ty = (uv * uy - uu * vy) / D, tz = (uv * uz - uu * vz) / D;
+                double gs = sqrt(sx * sx + sy * sy + sz * sz), gt = sqrt(tx * tx + ty * ty + tz * tz);
+                double gq = sqrt((sx + tx) * (sx + tx) + (sy + ty) * (sy + ty) + (sz + tz) * (sz + tz));
+                double gmax = fmax(gs, fmax(gt, gq));
+                double sinphi = nn / sqrt(uu * vv);
+                double kappa = fmax(1.0, 0.25 / sinphi);
+                double E0 = 128.0 * (double)kU32 * (double)M * gmax * kappa + 1e-6;
+                double E1 = 32.0 * (double)kU32 * (double)M * gmax * kappa;
+                if (!(E0 < 0.25)) {
+                    always = true;
+                } else {
+                    q0 = make_float4((float)nx, (float)ny, (float)nz, (float)(-(nx * A.x + ny * A.y + nz * A.z)));
+                    q1 = make_float4((float)sx, (float)sy, (float)sz, (float)(-(sx * A.x + sy * A.y + sz * A.z) + E0));
+                    q2 = make_float4((float)tx, (float)ty, (float)tz, (float)(-(tx * A.x + ty * A.y + tz * A.z) + E0));
+                    q3 = make_float4((float)(1.0 + 3.0 * E0), (float)(-E1), kCosMin, 0.0f);
+                }
+            }
+            if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3 = make_float4(0, 0, __int_as_float(0x7f800000), 0); }
+        }
+    }
+    rec[4 * i] = q0; rec[4 * i + 1] = q1; rec[4 * i + 2] = q2; rec[4 * i + 3] = q3;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact re-evaluation (cold path)
+// ------------------------------------------------------------------------------------------------
+// xyz = intersection point, w = Vec3Df::distance(origin, I) (raytracing.cpp:182) or -1 for "no hit".
+__device__ __noinline__ float4 exact_eval_tri(const float4* __restrict__ triv, int tri, float ox, float oy, float oz, float tx, float ty, float tz) {
+    const float4 A = __ldg(&triv[3 * tri]), B = __ldg(&triv[3 * tri + 1]), C = __ldg(&triv[3 * tri + 2]);
+    v3 I;
+    const v3 O = mk3(ox, oy, oz);
+    if (!exact_ray_triangle(O, mk3(tx, ty, tz), mk3(A), mk3(B), mk3(C), I)) return make_float4(0.f, 0.f, 0.f, -1.0f);
+    return make_float4(I.x, I.y, I.z, e_distance(O, I));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile pipeline: triangle records stream through a kStages-deep shared-memory ring filled by 1-D TMA bulk
+// copies.  There is no producer warp: the LAST warp to finish a stage re-arms its mbarrier and issues the
+// copy for the tile kStages iterations ahead, so nobody ever blocks on an "empty" barrier.
+// ------------------------------------------------------------------------------------------------
+struct __align__(128) ScanSmem {
+    float4 tiles[kStages][kTile * kRecVec];
+    unsigned long long full[kStages];
+    unsigned int done[kStages];
+};
+
+struct Pipe {
+    uint32_t tiles_addr, full_addr;
+    unsigned int* done;
+    const float4* tiles_ptr;
+    const float4* rec;
+    int ntiles;
+    uint32_t total_iters;  // tiles this CTA will consume over its whole life
+    uint32_t it;           // next iteration
+};
+
+__device__ __forceinline__ void pipe_issue(const Pipe& p, uint32_t iter) {
+    const uint32_t stage = iter % kStages;
+    const uint32_t bar = p.full_addr + stage * 8u;
+    const int tile = (int)(iter % (uint32_t)p.ntiles);
+    // generic-proxy reads of this stage (all warps are past it) are ordered before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive_expect_tx(bar, kTileBytes);
+    tma_bulk_g2s(p.tiles_addr + stage * kTileBytes, p.rec + (size_t)tile * kTile * kRecVec, kTileBytes, bar);
+}
+
+__device__ __forceinline__ void pipe_init(Pipe& p, ScanSmem& sm, const float4* rec, int ntiles, uint32_t total_iters) {
+    p.tiles_addr = smem_u32(&sm.tiles[0][0]);
+    p.full_addr = smem_u32(&sm.full[0]);
+    p.done = sm.done;
+    p.tiles_ptr = &sm.tiles[0][0];
+    p.rec = rec;
+    p.ntiles = ntiles;
+    p.total_iters = total_iters;
+    p.it = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(p.full_addr + s * 8u, 1); sm.done[s] = 0; }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t n = total_iters < (uint32_t)kStages ? total_iters : (uint32_t)kStages;
+        for (uint32_t i = 0; i < n; ++i) pipe_issue(p, i);
+    }
+}
+
+__device__ __forceinline__ const float4* pipe_acquire(const Pipe& p) {
+    const uint32_t stage = p.it % kStages;
+    mbar_wait(p.full_addr + stage * 8u, (p.it / kStages) & 1u);
+    return p.tiles_ptr + stage * (kTile * kRecVec);
+}
+
+__device__ __forceinline__ void pipe_release(Pipe& p) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t stage = p.it % kStages;
+        const unsigned int prev = atomicAdd(&p.done[stage], 1u);
+        if ((prev % kWarps) == kWarps - 1) {  // every warp has finished reading this stage
+            const uint32_t nxt = p.it + kStages;
+            if (nxt < p.total_iters) pipe_issue(p, nxt);
+        }
+    }
+    ++p.it;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The scan: R = 2*RP rays per thread against every triangle.
+// ------------------------------------------------------------------------------------------------
+template <int RP>
+struct FastRays {
+    float2 ox[RP], oy[RP], oz[RP];  // shifted origins O' = O - eps_r * d
+    float2 dx[RP], dy[RP], dz[RP];  // unit directions d
+    uint32_t rhi[2 * RP];           // bits of (best distance + 2*eps_r); 0 = ray finished / unused
+};
+
+template <int RP, int K>
+__device__ __forceinline__ void fast_set(FastRays<RP>& f, v3 O, v3 D, float eps_r, bool live) {
+    // d = normalize(D - O) only has to be accurate to a few ulp: it feeds the filter, never a result.
+    float dx = D.x - O.x, dy = D.y - O.y, dz = D.z - O.z;
+    float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-37f));
+    dx *= inv; dy *= inv; dz *= inv;
+    if (!live) { dx = dy = dz = 0.f; O = mk3(0.f, 0.f, 0.f); }
+    constexpr int p = K / 2;
+    if (K & 1) {
+        f.dx[p].y = dx; f.dy[p].y = dy; f.dz[p].y = dz;
+        f.ox[p].y = O.x - eps_r * dx; f.oy[p].y = O.y - eps_r * dy; f.oz[p].y = O.z - eps_r * dz;
+    } else {
+        f.dx[p].x = dx; f.dy[p].x = dy; f.dz[p].x = dz;
+        f.ox[p].x = O.x - eps_r * dx; f.oy[p].x = O.y - eps_r * dy; f.oz[p].x = O.z - eps_r * dz;
+    }
+    f.rhi[K] = live ? 0x7f7fffffu : 0u;  // FLT_MAX: the reference starts from dist = FLT_MAX (raytracing.cpp:164)
+}
+
+// One filter evaluation for a pair of rays against one record; returns the two candidate predicates.
+template <int RP>
+__device__ __forceinline__ void filter_pair(const FastRays<RP>& f, int p, const float4& q0, const float4& q1, const float4& q2,
+                                            const float4& q3, bool& c0, bool& c1) {
+    float2 b = __fmul2_rn(splat2(q0.x), f.dx[p]);
+    b = __ffma2_rn(splat2(q0.y), f.dy[p], b);
+    b = __ffma2_rn(splat2(q0.z), f.dz[p], b);
+    float2 a = __ffma2_rn(splat2(q0.x), f.ox[p], splat2(q0.w));
+    a = __ffma2_rn(splat2(q0.y), f.oy[p], a);
+    a = __ffma2_rn(splat2(q0.z), f.oz[p], a);
+    const float2 rc = make_float2(rcp_approx(-b.x), rcp_approx(-b.y));
+    const float2 r = __fmul2_rn(a, rc);
+    const float2 ix = __ffma2_rn(r, f.dx[p], f.ox[p]);
+    const float2 iy = __ffma2_rn(r, f.dy[p], f.oy[p]);
+    const float2 iz = __ffma2_rn(r, f.dz[p], f.oz[p]);
+    float2 s = __ffma2_rn(splat2(q1.x), ix, splat2(q1.w));
+    s = __ffma2_rn(splat2(q1.y), iy, s);
+    s = __ffma2_rn(splat2(q1.z), iz, s);
+    float2 t = __ffma2_rn(splat2(q2.x), ix, splat2(q2.w));
+    t = __ffma2_rn(splat2(q2.y), iy, t);
+    t = __ffma2_rn(splat2(q2.z), iz, t);
+    float2 q = __fadd2_rn(splat2(q3.x), make_float2(-s.x, -s.y));
+    q = __fadd2_rn(q, make_float2(-t.x, -t.y));
+    const float m0 = fminf(fminf(s.x, t.x), q.x), m1 = fminf(fminf(s.y, t.y), q.y);
+    const float e0 = q3.y * fabsf(rc.x), e1 = q3.y * fabsf(rc.y);
+    // every comparison is written so that NaN/inf anywhere makes the pair a candidate, never a miss
+    c0 = (!(m0 < e0) && (__float_as_uint(r.x) < f.rhi[2 * p])) || !(fabsf(b.x) >= q3.z);
+    c1 = (!(m1 < e1) && (__float_as_uint(r.y) < f.rhi[2 * p + 1])) || !(fabsf(b.y) >= q3.z);
+}
+
+template <int RP, int J>
+struct BitLayout {
+    static constexpr int R = 2 * RP;
+    static_assert(R * J <= 32, "candidate mask must fit 32 bits");
+    // bit j*R set for every j < J:  (2^(R*J) - 1) / (2^R - 1)
+    static constexpr uint32_t kRep = (uint32_t)((((uint64_t)1 << (R * J)) - 1) / (((uint64_t)1 << R) - 1));
+};
+
+// Scans all tiles of one pass.  NEAREST: keeps (dist, best) exactly like intersectMesh; !NEAREST: any-hit,
+// clears the ray's live bit on the first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
+template <int RP, int J, bool NEAREST, class Fetch>
+__device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
+                                          const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact) {
+    constexpr int R = 2 * RP;
+    constexpr uint32_t REP = BitLayout<RP, J>::kRep;
+    for (int tile = 0; tile < pipe.ntiles; ++tile) {
+        const float4* rec = pipe_acquire(pipe);
+        // warp-level early exit (shadow rays): nothing left to decide for any lane of this warp
+        if (!__all_sync(0xffffffffu, live == 0u)) {
+            const int tri0 = tile * kTile;
+#pragma unroll 1
+            for (int jb = 0; jb < kTile; jb += J) {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
+                    const float4 q2 = rec[(jb + j) * kRecVec + 2], q3 = rec[(jb + j) * kRecVec + 3];
+#pragma unroll
+                    for (int p = 0; p < RP; ++p) {
+                        bool c0, c1;
+                        filter_pair<RP>(fr, p, q0, q1, q2, q3, c0, c1);
+                        mask |= (c0 ? 1u : 0u) << (j * R + 2 * p);
+                        mask |= (c1 ? 1u : 0u) << (j * R + 2 * p + 1);
+                    }
+                }
+                mask &= live * REP;
+                if (mask) {  // cold: exact re-evaluation, per ray in ascending triangle order
+#pragma unroll
+                    for (int k = 0; k < R; ++k) {
+                        const uint32_t mk = (mask >> k) & REP;
+                        if (mk) {
+                            v3 O, D;
+                            fetch(k, O, D);
+#pragma unroll
+                            for (int j = 0; j < J; ++j) {
+                                if ((mk & (1u << (j * R))) && (NEAREST || ((live >> k) & 1u))) {
+                                    const int tri = tri0 + jb + j;
+                                    const float4 e = exact_eval_tri(triv, tri, O.x, O.y, O.z, D.x, D.y, D.z);
+                                    ++n_exact;
+                                    if (NEAREST) {
+                                        if (!(e.w < 0.0f) && e.w < dist[k]) {  // raytracing.cpp:183 strict <
+                                            dist[k] = e.w;
+                                            best[k] = tri;
+                                            fr.rhi[k] = __float_as_uint(__fadd_ru(e.w, eps_r2));
+                                        }
+                                    } else {
+                                        if (!(e.w < 0.0f) && (live & (1u << k))) {
+                                            live &= ~(1u << k);
+                                            best[k] = tri;
+                                            fr.rhi[k] = 0u;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        pipe_release(pipe);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ray generation, main.cpp:380-386 (exact)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ v3 lerp_corner(const float* c, int off, float xs, float omx, float ys, float omy) {
+    // yscale*(xscale*c00 + (1-xscale)*c10) + (1-yscale)*(xscale*c01 + (1-xscale)*c11)
+    const v3 c00 = mk3(c[0 + off], c[1 + off], c[2 + off]), c01 = mk3(c[6 + off], c[7 + off], c[8 + off]);
+    const v3 c10 = mk3(c[12 + off], c[13 + off], c[14 + off]), c11 = mk3(c[18 + off], c[19 + off], c[20 + off]);
+    const v3 top = e_scale(e_add(e_scale(c00, xs), e_scale(c10, omx)), ys);
+    const v3 bot = e_scale(e_add(e_scale(c01, xs), e_scale(c11, omx)), omy);
+    return e_add(top, bot);
+}
+
+__device__ __forceinline__ void primary_ray(const FrameParams& P, uint32_t s, v3& O, v3& D) {
+    const uint32_t spp = P.pfx * P.pfy;
+    const uint32_t pix = s / spp, sub = s - pix * spp;
+    const uint32_t subx = sub / P.pfy, suby = sub - subx * P.pfy;
+    const uint32_t ry = pix / P.W, x = pix - ry * P.W;
+    const uint32_t y = (P.row0 + ry) * P.G + P.rank;
+    const float xs = __fsub_rn(1.0f, __fdiv_rn(__fadd_rn(__fmul_rn((float)x, (float)P.pfx), (float)(int)subx), P.divX));  // main.cpp:380
+    const float ys = __fsub_rn(1.0f, __fdiv_rn(__fadd_rn(__fmul_rn((float)y, (float)P.pfy), (float)(int)suby), P.divY));  // main.cpp:381
+    const float omx = __fsub_rn(1.0f, xs), omy = __fsub_rn(1.0f, ys);
+    O = lerp_corner(P.corners, 0, xs, omx, ys, omy);
+    D = lerp_corner(P.corners, 3, xs, omx, ys, omy);
+}
+
+__device__ __forceinline__ uint32_t cta_total_chunks(uint32_t nchunks) {
+    return (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_trace: nearest hit for primary rays (generated in registers) or queued continuation rays.
+// ------------------------------------------------------------------------------------------------
+struct FetchFromRays {
+    const float4* ray_o;
+    const float4* ray_d;
+    const uint32_t* sid;
+    __device__ __forceinline__ void operator()(int k, v3& O, v3& D) const {
+        const float4 o = ray_o[sid[k]], d = ray_d[sid[k]];
+        O = mk3(o); D = mk3(d);
+    }
+};
+
+template <int RP, int J, bool PRIMARY>
+__global__ void __launch_bounds__(kThreads, 2) k_trace(const __grid_constant__ FrameParams P, int level) {
+    constexpr int R = 2 * RP;
+    __shared__ ScanSmem sm;
+    const uint32_t count = PRIMARY ? P.nsamples : P.counters[kCntRay + level];
+    const uint32_t per_chunk = kThreads * R;
+    const uint32_t nchunks = (count + per_chunk - 1) / per_chunk;
+    Pipe pipe;
+    pipe_init(pipe, sm, P.rec, P.ntiles, cta_total_chunks(nchunks) * (uint32_t)P.ntiles);
+    uint32_t n_exact = 0;
+    const float eps_r2 = 2.0f * P.eps_r;
+
+    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        FastRays<RP> fr;
+        float dist[R];
+        int best[R];
+        uint32_t sid[R];
+        uint32_t live = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const uint32_t item = chunk * per_chunk + k * kThreads + threadIdx.x;
+            const bool ok = item < count;
+            v3 O = mk3(0, 0, 0), D = mk3(0, 0, 1);
+            uint32_t s = 0;
+            if (ok) {
+                if (PRIMARY && !P.trace_api) {
+                    s = item;
+                    primary_ray(P, s, O, D);
+                    P.ray_o[s] = make_float4(O.x, O.y, O.z, 0.f);
+                    P.ray_d[s] = make_float4(D.x, D.y, D.z, __int_as_float(0));
+                    P.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
+                    P.acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    s = PRIMARY ? item : P.q_ray[item];
+                    const float4 o = P.ray_o[s], d = P.ray_d[s];
+                    O = mk3(o); D = mk3(d);
+                }
+                live |= 1u << k;
+            }
+            sid[k] = s;
+            dist[k] = FLT_MAX;
+            best[k] = -1;
+            // (fast_set needs a compile-time slot)
+            if (k == 0) fast_set<RP, 0>(fr, O, D, P.eps_r, ok);
+            if (k == 1) fast_set<RP, 1>(fr, O, D, P.eps_r, ok);
+            if (k == 2) fast_set<RP, (R > 2 ? 2 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 3) fast_set<RP, (R > 2 ? 3 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 4) fast_set<RP, (R > 4 ? 4 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 5) fast_set<RP, (R > 4 ? 5 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 6) fast_set<RP, (R > 6 ? 6 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 7) fast_set<RP, (R > 6 ? 7 : 0)>(fr, O, D, P.eps_r, ok);
+        }
+        FetchFromRays fetch{P.ray_o, P.ray_d, sid};
+        scan_pass<RP, J, true>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact);
+
+        // epilogue: exact hit point of the winner, analytic spheres, hit record, compaction
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const bool ok = (live >> k) & 1u;
+            int idx = -1;
+            v3 I = mk3(0, 0, 0);
+            if (ok) {
+                idx = best[k];
+                v3 O, D;
+                fetch(k, O, D);
+                if (idx >= 0) {
+                    const float4 e = exact_eval_tri(P.triv, idx, O.x, O.y, O.z, D.x, D.y, D.z);
+                    I = mk3(e);
+                }
+                float dbest = dist[k];
+                for (int sp = 0; sp < P.nspheres; ++sp) {  // spheres come after the triangles, strict <
+                    const float4 c = P.spheres[2 * sp];
+                    v3 Is;
+                    if (exact_ray_sphere(O, D, mk3(c), c.w, Is)) {
+                        const float ds = e_distance(O, Is);
+                        if (ds < dbest) { dbest = ds; idx = P.ntri + sp; I = Is; }
+                    }
+                }
+                P.hit[sid[k]] = make_float4(I.x, I.y, I.z, __int_as_float(idx));
+                P.lit[sid[k]] = 0u;
+                if (PRIMARY && P.prim_out) P.prim_out[P.sample_base + sid[k]] = idx;
+            }
+            warp_append(ok && idx >= 0, sid[k], P.q_hit, &P.counters[kCntHit + level]);
+        }
+    }
+    if (n_exact) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)n_exact);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_shadow: one work item = (hit sample, light).  isShadow, raytracing.cpp:241-261.
+//   ANY     : exact iff no material has (has_Tr && Tr < 1): any occluder shadows, warp-level early exit.
+//   NEAREST : the nearest occluder's material decides (transparent -> lit).
+// ------------------------------------------------------------------------------------------------
+struct FetchShadow {
+    const float4* hit;
+    const uint32_t* sid;
+    const v3* light;
+    __device__ __forceinline__ void operator()(int k, v3& O, v3& D) const {
+        const float4 h = hit[sid[k]];
+        O = e_add(mk3(h), mk3(0.1f, 0.1f, 0.1f));  // raytracing.cpp:246
+        D = light[k];
+    }
+};
+
+template <int RP, int J, bool NEAREST>
+__global__ void __launch_bounds__(kThreads, 2) k_shadow(const __grid_constant__ FrameParams P, int level) {
+    constexpr int R = 2 * RP;
+    __shared__ ScanSmem sm;
+    const uint32_t nl = (uint32_t)P.nlights;
+    const uint32_t count = P.counters[kCntHit + level] * nl;
+    const uint32_t per_chunk = kThreads * R;
+    const uint32_t nchunks = (count + per_chunk - 1) / per_chunk;
+    Pipe pipe;
+    pipe_init(pipe, sm, P.rec, P.ntiles, cta_total_chunks(nchunks) * (uint32_t)P.ntiles);
+    uint32_t n_exact = 0;
+    const float eps_r2 = 2.0f * P.eps_r;
+
+    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        FastRays<RP> fr;
+        float dist[R];
+        int best[R];
+        uint32_t sid[R], lid[R];
+        v3 light[R];
+        uint32_t live = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const uint32_t item = chunk * per_chunk + k * kThreads + threadIdx.x;
+            const bool ok = item < count;
+            v3 O = mk3(0, 0, 0), D = mk3(0, 0, 1);
+            sid[k] = 0; lid[k] = 0; light[k] = D;
+            if (ok) {
+                const uint32_t h = item / nl;
+                lid[k] = item - h * nl;
+                sid[k] = P.q_hit[h];
+                light[k] = mk3(P.lights[lid[k]][0], P.lights[lid[k]][1], P.lights[lid[k]][2]);
+                O = e_add(mk3(P.hit[sid[k]]), mk3(0.1f, 0.1f, 0.1f));
+                D = light[k];
+                live |= 1u << k;
+            }
+            dist[k] = FLT_MAX;
+            best[k] = -1;
+            if (k == 0) fast_set<RP, 0>(fr, O, D, P.eps_r, ok);
+            if (k == 1) fast_set<RP, 1>(fr, O, D, P.eps_r, ok);
+            if (k == 2) fast_set<RP, (R > 2 ? 2 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 3) fast_set<RP, (R > 2 ? 3 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 4) fast_set<RP, (R > 4 ? 4 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 5) fast_set<RP, (R > 4 ? 5 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 6) fast_set<RP, (R > 6 ? 6 : 0)>(fr, O, D, P.eps_r, ok);
+            if (k == 7) fast_set<RP, (R > 6 ? 7 : 0)>(fr, O, D, P.eps_r, ok);
+        }
+        const uint32_t valid = live;
+        FetchShadow fetch{P.hit, sid, light};
+        scan_pass<RP, J, NEAREST>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact);
+
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (!((valid >> k) & 1u)) continue;
+            bool lit;
+            v3 O, D;
+            fetch(k, O, D);
+            if (NEAREST) {
+                int idx = best[k];
+                float dbest = dist[k];
+                for (int sp = 0; sp < P.nspheres; ++sp) {
+                    const float4 c = P.spheres[2 * sp];
+                    v3 Is;
+                    if (exact_ray_sphere(O, D, mk3(c), c.w, Is)) {
+                        const float ds = e_distance(O, Is);
+                        if (ds < dbest) { dbest = ds; idx = P.ntri + sp; }
+                    }
+                }
+                if (idx < 0) {
+                    lit = true;
+                } else {
+                    const uint32_t m = (idx < P.ntri) ? __float_as_uint(P.normal_mat[idx].w) : __float_as_uint(P.spheres[2 * (idx - P.ntri) + 1].x);
+                    const float4 ks_tr = P.materials[4 * m + 2];
+                    const uint32_t flags = __float_as_uint(P.materials[4 * m + 3].x);
+                    lit = (flags & RT_HAS_TR) && (ks_tr.w < 1.0f);  // transparent occluder: no shadow (:254)
+                }
+            } else {
+                lit = (live >> k) & 1u;  // still alive after every triangle: no occluder found
+                for (int sp = 0; lit && sp < P.nspheres; ++sp) {
+                    const float4 c = P.spheres[2 * sp];
+                    v3 Is;
+                    if (exact_ray_sphere(O, D, mk3(c), c.w, Is)) lit = false;
+                }
+            }
+            if (lit) atomicOr(&P.lit[sid[k]], 1u << lid[k]);
+        }
+    }
+    if (n_exact) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)n_exact);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_shade: shade() for every hit of this level, then the continuation ray (reflection XOR refraction).
+// The colour recursion of the reference is a linear chain c0 + K0*(c1 + K1*(...)); it is evaluated
+// iteratively with a throughput thr = K0*K1*..., acc += thr*c (float rounding differs from the nested
+// form by ~1e-7 relative, far inside the 1/255 tolerance; geometry -- every ray origin/dest -- is exact).
+// ------------------------------------------------------------------------------------------------
+struct Mat {
+    v3 Kd, Ka, Ks;
+    float Ns, Ni, Tr;
+    uint32_t flags;
+};
+__device__ __forceinline__ Mat load_material(const float4* __restrict__ mats, uint32_t m) {
+    const float4 a = mats[4 * m], b = mats[4 * m + 1], c = mats[4 * m + 2], d = mats[4 * m + 3];
+    Mat M;
+    M.Kd = mk3(a); M.Ns = a.w; M.Ka = mk3(b); M.Ni = b.w; M.Ks = mk3(c); M.Tr = c.w; M.flags = __float_as_uint(d.x);
+    return M;
+}
+
+// reflection() + addOffset(), raytracing.cpp:277-285, 266-271. `ray` is normalised here (again).
+__device__ __forceinline__ void reflect_ray(v3 ray, v3 Ppos, v3 normal, v3& point, v3& dest) {
+    ray = e_normalize(ray);
+    const v3 Rv = e_sub(ray, e_scale(normal, __fmul_rn(2.0f, e_dot(normal, ray))));
+    dest = e_add(Ppos, Rv);
+    v3 off = e_normalize(e_sub(dest, Ppos));
+    off = e_scale(off, 0.01f);
+    point = e_add(Ppos, off);
+}
+__device__ __forceinline__ void offset_point(v3 Ppos, v3 dest, v3& point) {  // addOffset
+    v3 off = e_normalize(e_sub(dest, Ppos));
+    off = e_scale(off, 0.01f);
+    point = e_add(Ppos, off);
+}
+
+__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ FrameParams P, int level) {
+    const uint32_t count = P.counters[kCntHit + level];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (count + stride - 1) / stride;
+    const bool fAmbient = P.features & RT_AMBIENT, fDiffuse = P.features & RT_DIFFUSE, fSpecular = P.features & RT_SPECULAR;
+    const bool fReflection = P.features & RT_REFLECTION, fShadows = P.features & RT_SHADOWS, fRefraction = P.features & RT_REFRACTION;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t h = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool spawn = false;
+        uint32_t s = 0;
+        if (h < count) {
+            s = P.q_hit[h];
+            const float4 ro = P.ray_o[s], rd = P.ray_d[s], hp = P.hit[s];
+            const int lvl = __float_as_int(rd.w);
+            const int idx = __float_as_int(hp.w);
+            const v3 Ppos = mk3(hp);
+            const v3 ray = e_sub(mk3(rd), mk3(ro));  // raytracing.cpp:393
+            v3 normal;
+            uint32_t mi;
+            if (idx < P.ntri) {
+                const float4 nm = P.normal_mat[idx];
+                normal = mk3(nm);                     // never flipped toward the ray (:394)
+                mi = __float_as_uint(nm.w);
+            } else {
+                const float4 c = P.spheres[2 * (idx - P.ntri)];
+                normal = e_normalize(e_sub(Ppos, mk3(c)));  // Sphere.h:33-37
+                mi = __float_as_uint(P.spheres[2 * (idx - P.ntri) + 1].x);
+            }
+            const Mat M = load_material(P.materials, mi);
+            const v3 cam = mk3(P.camera[0], P.camera[1], P.camera[2]);
+
+            v3 c = mk3(0.f, 0.f, 0.f);
+            if (fAmbient && (M.flags & RT_HAS_KA)) c = e_add(c, M.Ka);                       // :337-340
+            const uint32_t litbits = fShadows ? P.lit[s] : 0xffffffffu;
+            for (int i = 0; i < P.nlights; ++i) {
+                if (!((litbits >> i) & 1u)) continue;                                          // isShadow :345
+                const v3 L = mk3(P.lights[i][0], P.lights[i][1], P.lights[i][2]);
+                if (fDiffuse && (M.flags & RT_HAS_KD)) {                                       // diffuseOnly :197-205
+                    normal = e_normalize(normal);
+                    const v3 lp = e_normalize(L);  // the light POSITION as a direction
+                    v3 d = e_add(mk3(0.f, 0.f, 0.f), e_scale(M.Kd, std_max(e_dot(normal, lp), 0.0f)));
+                    c = e_add(c, e_scale(d, M.Tr));
+                }
+                if (fSpecular && (M.flags & RT_HAS_KS) && (M.flags & RT_HAS_NS)) {             // blinnPhong :210-232
+                    v3 V = e_sub(cam, Ppos);
+                    normal = e_normalize(normal);
+                    V = e_normalize(V);
+                    v3 Lv = e_normalize(e_sub(L, Ppos));
+                    v3 H = e_normalize(e_add(V, Lv));
+                    float spec = std_max(e_dot(H, normal), 0.0f);
+                    spec = powf(spec, M.Ns);       // CUDA powf vs glibc powf: a few ulp, colour only
+                    v3 sp = e_add(mk3(0.f, 0.f, 0.f), e_scale(M.Ks, spec));
+                    c = e_add(c, e_scale(sp, M.Tr));
+                }
+            }
+            const float4 th = P.thr[s];
+            float4 ac = P.acc[s];
+            ac.x = __fadd_rn(ac.x, __fmul_rn(th.x, c.x));
+            ac.y = __fadd_rn(ac.y, __fmul_rn(th.y, c.y));
+            ac.z = __fadd_rn(ac.z, __fmul_rn(th.z, c.z));
+            P.acc[s] = ac;
+
+            // continuation: refraction XOR reflection (:357-364)
+            v3 point = Ppos, dest = Ppos, K = mk3(0.f, 0.f, 0.f);
+            int nlvl = lvl;
+            if (fRefraction && (M.Tr < 1.0f) && lvl < P.max_lvl) {                            // refraction(..., lvl+1) :290-330
+                const int L1 = lvl + 1;
+                const v3 rn = e_normalize(ray);
+                const float check = e_dot(rn, normal);
+                if (check < 0.0f) {
+                    const float angle = acosf(check);
+                    if (angle <= 2.0f && angle > 0.0f) {                                       // :298 grazing hack
+                        reflect_ray(rn, Ppos, normal, point, dest);
+                        K = M.Ks; nlvl = L1 + 1; spawn = true;
+                    } else {
+                        const float nr = __fdiv_rn(1.0f, M.Ni);
+                        const float dn = e_dot(normal, rn);
+                        float root = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(nr, nr), __fsub_rn(1.0f, __fmul_rn(dn, dn))));
+                        if (root >= 0.0f) {
+                            root = __fsqrt_rn(root);
+                            const v3 T = e_sub(e_scale(e_sub(rn, e_scale(normal, dn)), nr), e_scale(normal, root));  // :307
+                            dest = e_add(Ppos, T);
+                            offset_point(Ppos, dest, point);
+                            const float k = __fsub_rn(1.0f, M.Tr);
+                            K = mk3(k, k, k); nlvl = L1 + 1; spawn = true;
+                        }
+                    }
+                } else {
+                    const float nr = M.Ni;
+                    const v3 nn = e_neg(normal);
+                    const float dn = e_dot(nn, rn);
+                    float root = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(nr, nr), __fsub_rn(1.0f, __fmul_rn(dn, dn))));
+                    if (root >= 0.0f) {
+                        root = __fsqrt_rn(root);
+                        const v3 T = e_sub(e_scale(e_sub(rn, e_scale(nn, dn)), nr), e_scale(nn, root));                // :321
+                        dest = e_add(Ppos, T);
+                        offset_point(Ppos, dest, point);
+                        const float k = __fsub_rn(1.0f, M.Tr);
+                        K = mk3(k, k, k); nlvl = L1 + 1; spawn = true;
+                    }
+                }
+            } else if (fReflection && lvl < P.max_lvl) {                                      // Ks * reflection(..., lvl+1)
+                reflect_ray(ray, Ppos, normal, point, dest);
+                K = M.Ks; nlvl = lvl + 1; spawn = true;   // traced even when Ks == 0, like the reference
+            }
+            if (spawn) {
+                P.ray_o[s] = make_float4(point.x, point.y, point.z, 0.f);
+                P.ray_d[s] = make_float4(dest.x, dest.y, dest.z, __int_as_float(nlvl));
+                P.thr[s] = make_float4(__fmul_rn(th.x, K.x), __fmul_rn(th.y, K.y), __fmul_rn(th.z, K.z), 0.f);
+            }
+        }
+        warp_append(spawn, s, P.q_ray, &P.counters[kCntRay + level + 1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_resolve: per pixel, sum the samples (subx outer, suby inner == ascending sample index), divide by
+// raysPerPixel with a true division (Vec3D.h:36-38), clamp like RGBValue (main.cpp:29-41).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_resolve(const __grid_constant__ FrameParams P, float* __restrict__ fb_local) {
+    const uint32_t npix = P.nrows * P.W;
+    const uint32_t spp = P.pfx * P.pfy;
+    const float rays = (float)(int)spp;
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        float r = 0.f, g = 0.f, b = 0.f;
+        for (uint32_t k = 0; k < spp; ++k) {
+            const float4 a = P.acc[pix * spp + k];
+            r = __fadd_rn(r, a.x); g = __fadd_rn(g, a.y); b = __fadd_rn(b, a.z);
+        }
+        float ch[3] = {__fdiv_rn(r, rays), __fdiv_rn(g, rays), __fdiv_rn(b, rays)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (ch[c] > 1.0f) ch[c] = 1.0f;
+            if (ch[c] < 0.0f) ch[c] = 0.0f;   // NaN passes both, like the reference
+        }
+        float* dst = fb_local + 3 * ((size_t)P.row0 * P.W + pix);
+        dst[0] = ch[0]; dst[1] = ch[1]; dst[2] = ch[2];
+    }
+}
+
+// gathered: [G][rows_per_rank][W][3] (rank-major, as ncclAllGather leaves it) -> final [H][W][3]
+__global__ void k_deinterleave(const float* __restrict__ gathered, float* __restrict__ final_fb, uint32_t W, uint32_t H, uint32_t G, uint32_t rows_per_rank) {
+    const size_t n = (size_t)W * H * 3;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(i / (3u * W));
+        const uint32_t rem = (uint32_t)(i - (size_t)y * 3u * W);
+        const uint32_t rank = y % G, ly = y / G;
+        final_fb[i] = gathered[((size_t)rank * rows_per_rank + ly) * 3u * W + rem];
+    }
+}
+
+// Image::writeImage's quantiser (main.cpp:117): (unsigned char)(v * 255.0f), truncation toward zero.
+__global__ void k_quantise(const float* __restrict__ fb, uint8_t* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = __fmul_rn(fb[i], 255.0f);
+        out[i] = (uint8_t)(int)v;  // values are clamped to [0,1] upstream, so int conversion == uchar conversion
+    }
+}
+
+}  // namespace rt

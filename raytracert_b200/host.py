@@ -29,6 +29,7 @@ def lib():
         L.rth_get_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rth_get_normals.argtypes = [C.c_void_p, C.c_void_p]
         L.rth_get_material.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
+        L.rth_face_normals.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.rth_scene.restype = C.c_void_p
         L.rth_scene.argtypes = [C.c_void_p]
         L.rth_corner_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -72,6 +73,15 @@ class Scene:
         z = np.load(path, allow_pickle=False)
         return Scene(z["vertices"], z["indices"], z["tri_material"], z["normals"], z["materials"],
                      [str(s) for s in z["names"]], z["spheres"] if "spheres" in z.files else None)
+
+
+def face_normals(vertices, indices):
+    """Unit face normals with the reference's arithmetic (host/flatten.h append_face_normals)."""
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+    out = np.zeros((len(idx), 3), np.float32)
+    lib().rth_face_normals(len(v), v.ctypes.data, len(idx), idx.ctypes.data, out.ctypes.data)
+    return out
 
 
 def load_obj(path):

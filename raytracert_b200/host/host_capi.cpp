@@ -70,6 +70,17 @@ void rth_get_material(void* handle, int i, float* out, char* name, int name_cap)
     if (name && name_cap > 0) { strncpy(name, h->mesh.materials[i].name().c_str(), name_cap - 1); name[name_cap - 1] = 0; }
 }
 
+// Face normals for a flat indexed mesh, with calculateNormals()'s arithmetic (raytracing.cpp:78-86).
+void rth_face_normals(int nv, const float* verts, int nt, const uint32_t* idx, float* out) {
+    Mesh m;
+    for (int i = 0; i < nv; ++i) m.vertices.push_back(Vertex(Vec3Df(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2])));
+    for (int i = 0; i < nt; ++i) m.triangles.push_back(Triangle(idx[3 * i], 0, idx[3 * i + 1], 0, idx[3 * i + 2], 0));
+    std::vector<Vec3Df> n;
+    append_face_normals(m, n);
+    for (int i = 0; i < nt; ++i)
+        for (int c = 0; c < 3; ++c) out[3 * i + c] = n[i][c];
+}
+
 const rt_scene* rth_scene(void* handle) { return &static_cast<HostScene*>(handle)->view; }
 
 // The four produceRay() calls of main.cpp:355-358 for a W x H viewport: corner c at window
