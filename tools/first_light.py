@@ -7,6 +7,7 @@ from oracle import pyoracle
 
 def compare(name, R, P, scene, cam, pf, maxlvl, lights, feats=63):
     W, H = cam.W, cam.H
+    lights = [cam.eye] if lights is None else lights
     P.set_scene(scene); P.configure(cam.eye, lights, feats, maxlvl); P.reset_counts()
     t = time.time(); rgb_o, srgb_o, prim_o = P.render(cam.corners, W, H, pf, pf, want_samples=True); t_cpu = time.time() - t
     counts = P.ray_counts()
