@@ -111,7 +111,9 @@ int rt_init(int n_gpus);
 
 /* One-process-per-GPU mode (torchrun): this process drives `device` as rank `rank` of `world`.
  * nccl_id: the bytes of an ncclUniqueId made by rank 0 with rt_nccl_unique_id() and distributed by the
- * caller (ignored when world == 1). */
+ * caller (ignored when world == 1).  nccl_id == NULL with world > 1 makes a DETACHED rank: it renders its
+ * own rows (y % world == rank) and rt_download_framebuffer returns them in place with every other row
+ * zero -- no communicator, no all-gather (used to test the row interleave on a single device). */
 int rt_init_rank(int device, int rank, int world, const void* nccl_id, size_t nccl_id_bytes);
 int rt_nccl_unique_id(void* out, size_t cap, size_t* bytes);
 

@@ -307,7 +307,12 @@ int render_enqueue(const rt_params* rp) {
         CU(cudaEventRecord(d.ev_phase[1], d.stream));
     }
     // one all-gather per frame (rank-major slabs), then de-interleave rows
-    if (G > 1) {
+    if (G > 1 && !g.devs[0].comm) {
+        // detached rank (rt_init_rank without an ncclUniqueId): no exchange, own rows only
+        RtDevice& d = g.devs[0];
+        k_place_rows<<<d.num_sms * 4, 256, 0, d.stream>>>(d.fb_local, d.fb_final, W, H, G, (uint32_t)d.rank);
+        CU(cudaGetLastError());
+    } else if (G > 1) {
         const size_t count = (size_t)rows_per_rank * W * 3;
         if (g.single_process) NC(g.nccl.GroupStart());
         for (RtDevice& d : g.devs) {
@@ -435,9 +440,9 @@ int rt_init_rank(int device, int rank, int world, const void* nccl_id, size_t nc
     g.single_process = false;
     int rc = create_device(g.devs[0], device, rank);
     if (rc) { rt_shutdown(); return rc; }
-    if (world > 1) {
+    if (world > 1 && nccl_id) {
         if (!g.nccl.load()) { rt_shutdown(); return fail(RT_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror()); }
-        if (!nccl_id || nccl_id_bytes < sizeof(ncclUniqueId)) { rt_shutdown(); return fail(RT_ERR_INVALID, "world > 1 needs an ncclUniqueId"); }
+        if (nccl_id_bytes < sizeof(ncclUniqueId)) { rt_shutdown(); return fail(RT_ERR_INVALID, "ncclUniqueId needs %zu bytes", sizeof(ncclUniqueId)); }
         ncclUniqueId id;
         memcpy(&id, nccl_id, sizeof(id));
         ncclResult_t r = g.nccl.CommInitRank(&g.devs[0].comm, world, id, rank);

@@ -770,6 +770,17 @@ __global__ void k_deinterleave(const float* __restrict__ gathered, float* __rest
     }
 }
 
+// Detached rank (world > 1 without a communicator, used to test the row interleave on one device): this
+// rank's rows go to their final position, every other row is zero.
+__global__ void k_place_rows(const float* __restrict__ local, float* __restrict__ final_fb, uint32_t W, uint32_t H, uint32_t G, uint32_t rank) {
+    const size_t n = (size_t)W * H * 3;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(i / (3u * W));
+        const uint32_t rem = (uint32_t)(i - (size_t)y * 3u * W);
+        final_fb[i] = (y % G == rank) ? local[(size_t)(y / G) * 3u * W + rem] : 0.0f;
+    }
+}
+
 // Image::writeImage's quantiser (main.cpp:117): (unsigned char)(v * 255.0f), truncation toward zero.
 __global__ void k_quantise(const float* __restrict__ fb, uint8_t* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
