@@ -51,15 +51,16 @@ class _Oracle:
         f(*(1 if features & b else 0 for b in (1, 2, 4, 8, 16, 32)))
         f = self._f("set_max_lvl"); f.argtypes = [C.c_int]; f(int(max_lvl))
 
-    def render(self, corners, W, H, pfx=1, pfy=1, y0=0, ystep=1, want_samples=False, threads=0):
-        """Returns (rgb[H,W,3] clamped float32, sample_rgb or None, sample_prim or None)."""
+    def render(self, corners, W, H, pfx=1, pfy=1, y0=0, ystep=1, want_samples=False, threads=0, x0=0, xstep=1):
+        """Renders the pixel lattice rows y0::ystep x columns x0::xstep (default: the full frame).
+        Returns (rgb[H,W,3] clamped float32, sample_rgb or None, sample_prim or None)."""
         corners = np.ascontiguousarray(corners, np.float32)
         rgb = np.zeros((H, W, 3), np.float32)
         srgb = np.zeros((H * W * pfx * pfy, 3), np.float32) if want_samples else None
         sprim = np.full(H * W * pfx * pfy, -2, np.int32) if want_samples else None
         f = self._f("render")
-        f.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p] * 3 + [C.c_int]
-        f(corners.ctypes.data, W, H, pfx, pfy, y0, ystep, rgb.ctypes.data,
+        f.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p] * 3 + [C.c_int]
+        f(corners.ctypes.data, W, H, pfx, pfy, y0, ystep, x0, xstep, rgb.ctypes.data,
           srgb.ctypes.data if want_samples else None, sprim.ctypes.data if want_samples else None,
           threads or (os.cpu_count() or 1))
         return rgb, srgb, sprim

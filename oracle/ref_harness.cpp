@@ -145,10 +145,12 @@ void ref_set_max_lvl(int l) { max_lvl = l; }
 
 // corners: o00 d00 o01 d01 o10 d10 o11 d11 (3 floats each), i.e. produceRay at
 // (0,0), (0,H-1), (W-1,0), (W-1,H-1) as in main.cpp:355-358.
-// Renders rows y = y0, y0+ystep, ... < H.  rgb: 3*W*H floats (clamped like RGBValue, main.cpp:24-42),
-// rows not rendered are left untouched.  sample_rgb (optional): 3 floats per sample, sample index
-// ((y*W+x)*pfX+subx)*pfY+suby.  sample_prim (optional): primary primitive id per sample.
-void ref_render(const float* corners, int W, int H, int pfX, int pfY, int y0, int ystep, float* rgb,
+// Renders the pixel lattice y = y0, y0+ystep, ... < H  x  x = x0, x0+xstep, ... < W (the full frame for
+// 0,1,0,1).  rgb: 3*W*H floats (clamped like RGBValue, main.cpp:24-42), pixels not rendered are left
+// untouched.  sample_rgb (optional): 3 floats per sample, sample index ((y*W+x)*pfX+subx)*pfY+suby.
+// sample_prim (optional): primary primitive id per sample.  OpenMP runs over the lattice's pixels; each
+// pixel is computed by exactly the reference's per-pixel code, so the result does not depend on threads.
+void ref_render(const float* corners, int W, int H, int pfX, int pfY, int y0, int ystep, int x0, int xstep, float* rgb,
                 float* sample_rgb, int32_t* sample_prim, int nthreads) {
     Vec3Df origin00(corners[0], corners[1], corners[2]), dest00(corners[3], corners[4], corners[5]);
     Vec3Df origin01(corners[6], corners[7], corners[8]), dest01(corners[9], corners[10], corners[11]);
@@ -160,35 +162,36 @@ void ref_render(const float* corners, int W, int H, int pfX, int pfY, int y0, in
     float divY = (WindowSize_Y_ * pixelfactorY_ - 1);  // main.cpp:361
     int raysPerPixel = (pixelfactorX_ * pixelfactorY_); // main.cpp:362
     if (ystep < 1) ystep = 1;
-    int nrows = (H - y0 + ystep - 1) / ystep;
+    if (xstep < 1) xstep = 1;
+    const long nrows = (H - y0 + ystep - 1) / ystep, ncols = (W - x0 + xstep - 1) / xstep;
+    if (nrows <= 0 || ncols <= 0) return;
     (void)nthreads;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-    for (int row = 0; row < nrows; ++row) {
-        unsigned int y = y0 + row * ystep;
-        for (unsigned int x = 0; x < WindowSize_X_; ++x) {
-            Vec3Df rgbv = Vec3Df(0, 0, 0);
-            for (int subx = 0; subx < (int)pixelfactorX_; subx++) {
-                for (int suby = 0; suby < (int)pixelfactorY_; suby++) {
-                    float xscale = 1.0f - (float(x) * pixelfactorX_ + subx) / divX;  // main.cpp:380
-                    float yscale = 1.0f - (float(y) * pixelfactorY_ + suby) / divY;  // main.cpp:381
-                    Vec3Df origin = yscale * (xscale * origin00 + (1 - xscale) * origin10) +
-                                    (1 - yscale) * (xscale * origin01 + (1 - xscale) * origin11);
-                    Vec3Df dest = yscale * (xscale * dest00 + (1 - xscale) * dest10) +
-                                  (1 - yscale) * (xscale * dest01 + (1 - xscale) * dest11);
-                    Vec3Df c = performRayTracing(origin, dest);  // main.cpp:388
-                    rgbv += c;
-                    size_t s = (((size_t)y * W + x) * pfX + subx) * pfY + suby;
-                    if (sample_rgb) { sample_rgb[3 * s] = c[0]; sample_rgb[3 * s + 1] = c[1]; sample_rgb[3 * s + 2] = c[2]; }
-                    if (sample_prim) { Vec3Df tmp; sample_prim[s] = intersectMesh(origin, dest, &tmp); }
-                }
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (long item = 0; item < nrows * ncols; ++item) {
+        unsigned int y = y0 + (unsigned int)(item / ncols) * ystep;
+        unsigned int x = x0 + (unsigned int)(item % ncols) * xstep;
+        Vec3Df rgbv = Vec3Df(0, 0, 0);
+        for (int subx = 0; subx < (int)pixelfactorX_; subx++) {
+            for (int suby = 0; suby < (int)pixelfactorY_; suby++) {
+                float xscale = 1.0f - (float(x) * pixelfactorX_ + subx) / divX;  // main.cpp:380
+                float yscale = 1.0f - (float(y) * pixelfactorY_ + suby) / divY;  // main.cpp:381
+                Vec3Df origin = yscale * (xscale * origin00 + (1 - xscale) * origin10) +
+                                (1 - yscale) * (xscale * origin01 + (1 - xscale) * origin11);
+                Vec3Df dest = yscale * (xscale * dest00 + (1 - xscale) * dest10) +
+                              (1 - yscale) * (xscale * dest01 + (1 - xscale) * dest11);
+                Vec3Df c = performRayTracing(origin, dest);  // main.cpp:388
+                rgbv += c;
+                size_t s = (((size_t)y * W + x) * pfX + subx) * pfY + suby;
+                if (sample_rgb) { sample_rgb[3 * s] = c[0]; sample_rgb[3 * s + 1] = c[1]; sample_rgb[3 * s + 2] = c[2]; }
+                if (sample_prim) { Vec3Df tmp; sample_prim[s] = intersectMesh(origin, dest, &tmp); }
             }
-            rgbv = rgbv / raysPerPixel;  // main.cpp:391
-            float ch[3] = {rgbv[0], rgbv[1], rgbv[2]};
-            for (int c = 0; c < 3; ++c) {  // RGBValue ctor, main.cpp:29-41
-                if (ch[c] > 1) ch[c] = 1.0;
-                if (ch[c] < 0) ch[c] = 0.0;
-                rgb[3 * ((size_t)W * y + x) + c] = ch[c];
-            }
+        }
+        rgbv = rgbv / raysPerPixel;  // main.cpp:391
+        float ch[3] = {rgbv[0], rgbv[1], rgbv[2]};
+        for (int c = 0; c < 3; ++c) {  // RGBValue ctor, main.cpp:29-41
+            if (ch[c] > 1) ch[c] = 1.0;
+            if (ch[c] < 0) ch[c] = 0.0;
+            rgb[3 * ((size_t)W * y + x) + c] = ch[c];
         }
     }
 }

@@ -343,7 +343,7 @@ void orc_get_counts(uint64_t* out) { out[0] = g_counts[0]; out[1] = g_counts[1];
 
 /* Frame loop of the 'r' handler, main.cpp:347-395 (corner order main.cpp:355-358; scales :380-381;
  * bilinear rays :383-386; sample sum subx-outer/suby-inner :377-390; average :391; clamp :29-41). */
-void orc_render(const float* c, int W, int H, int pfX, int pfY, int y0, int ystep, float* rgb, float* sample_rgb, int32_t* sample_prim, int nthreads) {
+void orc_render(const float* c, int W, int H, int pfX, int pfY, int y0, int ystep, int x0, int xstep, float* rgb, float* sample_rgb, int32_t* sample_prim, int nthreads) {
     v3 origin00 = V(c[0], c[1], c[2]), dest00 = V(c[3], c[4], c[5]);
     v3 origin01 = V(c[6], c[7], c[8]), dest01 = V(c[9], c[10], c[11]);
     v3 origin10 = V(c[12], c[13], c[14]), dest10 = V(c[15], c[16], c[17]);
@@ -353,40 +353,42 @@ void orc_render(const float* c, int W, int H, int pfX, int pfY, int y0, int yste
     float divY = (WindowSize_Y * pixelfactorY - 1);
     int raysPerPixel = (pixelfactorX * pixelfactorY);
     if (ystep < 1) ystep = 1;
-    int nrows = (H - y0 + ystep - 1) / ystep;
+    if (xstep < 1) xstep = 1;
+    /* pixel lattice y = y0 + i*ystep, x = x0 + j*xstep (the full frame for 0,1,0,1); threads share the pixel list */
+    const long nrows = (H - y0 + ystep - 1) / ystep, ncols = (W - x0 + xstep - 1) / xstep;
+    if (nrows <= 0 || ncols <= 0) return;
     (void)nthreads;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-    for (int row = 0; row < nrows; row++) {
-        unsigned int y = y0 + row * ystep;
-        for (unsigned int x = 0; x < WindowSize_X; ++x) {
-            v3 acc = V(0, 0, 0);
-            for (int subx = 0; subx < (int)pixelfactorX; subx++) {
-                for (int suby = 0; suby < (int)pixelfactorY; suby++) {
-                    float xscale = 1.0f - ((float)x * pixelfactorX + subx) / divX;
-                    float yscale = 1.0f - ((float)y * pixelfactorY + suby) / divY;
-                    v3 origin = vadd(vscale(vadd(vscale(origin00, xscale), vscale(origin10, 1 - xscale)), yscale),
-                                     vscale(vadd(vscale(origin01, xscale), vscale(origin11, 1 - xscale)), 1 - yscale));
-                    v3 dest = vadd(vscale(vadd(vscale(dest00, xscale), vscale(dest10, 1 - xscale)), yscale),
-                                   vscale(vadd(vscale(dest01, xscale), vscale(dest11, 1 - xscale)), 1 - yscale));
-                    v3 col = perform_ray_tracing(origin, dest);
-                    acc = vadd(acc, col);
-                    size_t s = (((size_t)y * W + x) * pfX + subx) * pfY + suby;
-                    if (sample_rgb) { sample_rgb[3 * s] = col.x; sample_rgb[3 * s + 1] = col.y; sample_rgb[3 * s + 2] = col.z; }
-                    if (sample_prim) {
-                        v3 tmp;
-                        sample_prim[s] = intersect_mesh(origin, dest, &tmp, RAY_PRIMARY);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (long item = 0; item < nrows * ncols; item++) {
+        unsigned int y = y0 + (unsigned int)(item / ncols) * ystep;
+        unsigned int x = x0 + (unsigned int)(item % ncols) * xstep;
+        v3 acc = V(0, 0, 0);
+        for (int subx = 0; subx < (int)pixelfactorX; subx++) {
+            for (int suby = 0; suby < (int)pixelfactorY; suby++) {
+                float xscale = 1.0f - ((float)x * pixelfactorX + subx) / divX;
+                float yscale = 1.0f - ((float)y * pixelfactorY + suby) / divY;
+                v3 origin = vadd(vscale(vadd(vscale(origin00, xscale), vscale(origin10, 1 - xscale)), yscale),
+                                 vscale(vadd(vscale(origin01, xscale), vscale(origin11, 1 - xscale)), 1 - yscale));
+                v3 dest = vadd(vscale(vadd(vscale(dest00, xscale), vscale(dest10, 1 - xscale)), yscale),
+                               vscale(vadd(vscale(dest01, xscale), vscale(dest11, 1 - xscale)), 1 - yscale));
+                v3 col = perform_ray_tracing(origin, dest);
+                acc = vadd(acc, col);
+                size_t s = (((size_t)y * W + x) * pfX + subx) * pfY + suby;
+                if (sample_rgb) { sample_rgb[3 * s] = col.x; sample_rgb[3 * s + 1] = col.y; sample_rgb[3 * s + 2] = col.z; }
+                if (sample_prim) {
+                    v3 tmp;
+                    sample_prim[s] = intersect_mesh(origin, dest, &tmp, RAY_PRIMARY);
 #pragma omp atomic
-                        g_counts[RAY_PRIMARY]--;   /* the id query is not one of the reference's rays */
-                    }
+                    g_counts[RAY_PRIMARY]--;   /* the id query is not one of the reference's rays */
                 }
             }
-            acc = vdiv(acc, raysPerPixel);
-            float ch[3] = {acc.x, acc.y, acc.z};
-            for (int k = 0; k < 3; k++) {
-                if (ch[k] > 1) ch[k] = 1.0f;
-                if (ch[k] < 0) ch[k] = 0.0f;
-                rgb[3 * ((size_t)W * y + x) + k] = ch[k];
-            }
+        }
+        acc = vdiv(acc, raysPerPixel);
+        float ch[3] = {acc.x, acc.y, acc.z};
+        for (int k = 0; k < 3; k++) {
+            if (ch[k] > 1) ch[k] = 1.0f;
+            if (ch[k] < 0) ch[k] = 0.0f;
+            rgb[3 * ((size_t)W * y + x) + k] = ch[k];
         }
     }
 }

@@ -78,8 +78,14 @@ struct RtDevice {
     uint8_t* fb_u8 = nullptr; size_t cap_u8 = 0;
     cudaEvent_t ev[16] = {};
     cudaEvent_t ev_phase[8] = {};
+    // per-launch timing: events 2*i / 2*i+1 bracket launch i of the current frame; kind: see KernelKind
+    std::vector<cudaEvent_t> kev;
+    std::vector<int> kev_kind;
     int num_sms = 148;
 };
+
+enum KernelKind { kKindTrace = 0, kKindShadow, kKindShade, kKindResolve, kKindGather, kNumKinds };
+constexpr size_t kMaxTimedLaunches = 4096;  // beyond this a frame's launches are still counted, not timed
 
 struct Global {
     std::vector<RtDevice> devs;
@@ -148,9 +154,25 @@ void destroy_device(RtDevice& d) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     for (auto& e : d.ev_phase) if (e) cudaEventDestroy(e);
+    for (auto& e : d.kev) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
     d = RtDevice();
 }
+
+// Brackets one kernel launch with events on the device's stream (cheap: two event records).
+struct LaunchTimer {
+    RtDevice& d;
+    bool timed;
+    LaunchTimer(RtDevice& dev, int kind) : d(dev), timed(dev.kev_kind.size() < kMaxTimedLaunches) {
+        if (timed) {
+            const size_t i = d.kev_kind.size();
+            while (d.kev.size() < 2 * (i + 1)) { cudaEvent_t e; cudaEventCreate(&e); d.kev.push_back(e); }
+            cudaEventRecord(d.kev[2 * i], d.stream);
+        }
+        d.kev_kind.push_back(timed ? kind : -1 - kind);
+    }
+    ~LaunchTimer() { if (timed) cudaEventRecord(d.kev[2 * (d.kev_kind.size() - 1) + 1], d.stream); }
+};
 
 int check_ready() {
     if (g.devs.empty()) return fail(RT_ERR_STATE, "rt_init has not been called (or failed): there is no CPU fallback");
@@ -220,13 +242,20 @@ int run_wavefront(RtDevice& d, const FrameParams& P, int grid_scan) {
     const int levels = bounces ? std::min(P.max_lvl + 1, kMaxLevels - 2) : 1;
     const int grid_shade = d.num_sms * 4;
     for (int level = 0; level < levels; ++level) {
-        if (level == 0) k_trace<kRP, kJ, true><<<grid_scan, kThreads, 0, d.stream>>>(P, 0);
-        else k_trace<kRP, kJ, false><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
+        {
+            LaunchTimer t(d, kKindTrace);
+            if (level == 0) k_trace<kRP, kJ, true><<<grid_scan, kThreads, 0, d.stream>>>(P, 0);
+            else k_trace<kRP, kJ, false><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
+        }
         if (shadows) {
+            LaunchTimer t(d, kKindShadow);
             if (g.any_transparent) k_shadow<kRP, kJ, true><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
             else k_shadow<kRP, kJ, false><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
         }
-        k_shade<<<grid_shade, 256, 0, d.stream>>>(P, level);
+        {
+            LaunchTimer t(d, kKindShade);
+            k_shade<<<grid_shade, 256, 0, d.stream>>>(P, level);
+        }
     }
     CU(cudaGetLastError());
     return levels;
@@ -268,6 +297,7 @@ int render_enqueue(const rt_params* rp) {
 
     for (RtDevice& d : g.devs) {
         CU(cudaSetDevice(d.device));
+        d.kev_kind.clear();
         const uint32_t my_rows = (H > (uint32_t)d.rank) ? (H - d.rank + G - 1) / G : 0;
         const uint32_t nchunks = (my_rows + rows_per_chunk - 1) / rows_per_chunk;
         const size_t chunk_cap = (size_t)std::min(rows_per_chunk, std::max(my_rows, 1u)) * row_samples;
@@ -301,7 +331,10 @@ int render_enqueue(const rt_params* rp) {
             int levels = run_wavefront(d, P, grid_scan);
             if (levels < 0) return levels;
             g.stats.n_levels = (uint32_t)levels;
-            k_resolve<<<d.num_sms * 4, 256, 0, d.stream>>>(P, d.fb_local);
+            {
+                LaunchTimer t(d, kKindResolve);
+                k_resolve<<<d.num_sms * 4, 256, 0, d.stream>>>(P, d.fb_local);
+            }
             CU(cudaGetLastError());
         }
         CU(cudaEventRecord(d.ev_phase[1], d.stream));
@@ -310,7 +343,10 @@ int render_enqueue(const rt_params* rp) {
     if (G > 1 && !g.devs[0].comm) {
         // detached rank (rt_init_rank without an ncclUniqueId): no exchange, own rows only
         RtDevice& d = g.devs[0];
-        k_place_rows<<<d.num_sms * 4, 256, 0, d.stream>>>(d.fb_local, d.fb_final, W, H, G, (uint32_t)d.rank);
+        {
+            LaunchTimer t(d, kKindGather);
+            k_place_rows<<<d.num_sms * 4, 256, 0, d.stream>>>(d.fb_local, d.fb_final, W, H, G, (uint32_t)d.rank);
+        }
         CU(cudaGetLastError());
     } else if (G > 1) {
         const size_t count = (size_t)rows_per_rank * W * 3;
@@ -322,7 +358,10 @@ int render_enqueue(const rt_params* rp) {
         if (g.single_process) NC(g.nccl.GroupEnd());
         for (RtDevice& d : g.devs) {
             CU(cudaSetDevice(d.device));
-            k_deinterleave<<<d.num_sms * 4, 256, 0, d.stream>>>(d.fb_gather, d.fb_final, W, H, G, rows_per_rank);
+            {
+                LaunchTimer t(d, kKindGather);
+                k_deinterleave<<<d.num_sms * 4, 256, 0, d.stream>>>(d.fb_gather, d.fb_final, W, H, G, rows_per_rank);
+            }
             CU(cudaGetLastError());
         }
     }
@@ -371,9 +410,16 @@ int collect_stats() {
             st.exact_evals += (uint64_t)cw[kCntExact] | ((uint64_t)cw[kCntExact + 1] << 32);
         }
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, d.ev_phase[0], d.ev_phase[1]) == cudaSuccess) st.ms_intersect = std::max(st.ms_intersect, ms);
-        if (cudaEventElapsedTime(&ms, d.ev_phase[1], d.ev_phase[2]) == cudaSuccess) st.ms_gather = std::max(st.ms_gather, ms);
         if (cudaEventElapsedTime(&ms, d.ev_phase[0], d.ev_phase[2]) == cudaSuccess) st.ms_total = std::max(st.ms_total, ms);
+        float by_kind[kNumKinds] = {};
+        for (size_t i = 0; i < d.kev_kind.size(); ++i)
+            if (d.kev_kind[i] >= 0 && cudaEventElapsedTime(&ms, d.kev[2 * i], d.kev[2 * i + 1]) == cudaSuccess) by_kind[d.kev_kind[i]] += ms;
+        st.ms_trace = std::max(st.ms_trace, by_kind[kKindTrace]);
+        st.ms_shadow = std::max(st.ms_shadow, by_kind[kKindShadow]);
+        st.ms_shade = std::max(st.ms_shade, by_kind[kKindShade]);
+        st.ms_resolve = std::max(st.ms_resolve, by_kind[kKindResolve]);
+        if (cudaEventElapsedTime(&ms, d.ev_phase[1], d.ev_phase[2]) == cudaSuccess) st.ms_gather = std::max(st.ms_gather, ms);
+        st.n_launches = std::max(st.n_launches, (uint32_t)d.kev_kind.size());
     }
     st.tri_tests = (st.primary_rays + st.shadow_rays + st.bounce_rays) * (uint64_t)st.n_triangles;
     return RT_OK;
@@ -596,6 +642,7 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     if ((size_t)n > kMaxChunkSamples) return fail(RT_ERR_INVALID, "rt_trace: at most %u rays per call", kMaxChunkSamples);
     RtDevice& d = g.devs[0];
     CU(cudaSetDevice(d.device));
+    d.kev_kind.clear();
     float M = magnitude_bound(*rp, origins, 3 * n);
     rc = build_records(d, M); if (rc) return rc;
     rc = ensure_chunk_state(d, (size_t)n, false, 0); if (rc) return rc;

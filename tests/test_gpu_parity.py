@@ -181,22 +181,21 @@ def _detached_frame(scene, c, world):
     return total
 
 
-def test_virtual_row_sharding(built):
+def test_virtual_row_sharding(gpu):
     """Row interleave is a pure function of (y, G): G detached ranks on one device reproduce the G = 1 frame
     bit for bit (ids and float RGB) -- the multi-GPU path minus the NCCL exchange."""
     from raytracert_b200 import binding
     c = load_case("room_64_pf2_lvl4")
     c.update(W=61, H=45)   # H not a multiple of G
     s = load_scene(c["scene"])
-    R = binding.Renderer(1)
+    rgb1, prim1 = gpu_render(gpu, s, c)
     try:
-        rgb1, prim1 = gpu_render(R, s, c)
+        for world in (2, 8):
+            rgb, prim = _detached_frame(s, c, world)   # re-initialises the (process-global) library per rank
+            assert np.array_equal(prim, prim1)
+            assert np.array_equal(bits(rgb), bits(rgb1))
     finally:
-        R.shutdown()
-    for world in (2, 8):
-        rgb, prim = _detached_frame(s, c, world)
-        assert np.array_equal(prim, prim1)
-        assert np.array_equal(bits(rgb), bits(rgb1))
+        binding._check(gpu.L.rt_init(1))               # give the session fixture its single-GPU context back
 
 
 # ---- BASELINE.json full-size configurations: size-independent properties --------------------------
