@@ -334,7 +334,9 @@ __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&
                                             fr.rhi[k] = __float_as_uint(__fadd_ru(e.w, eps_r2));
                                         }
                                     } else {
-                                        if (!(e.w < 0.0f) && (live & (1u << k))) {
+                                        // isShadow ends with index != -1 iff some hit had distance < FLT_MAX
+                                        // (raytracing.cpp:164,183); a NaN / inf distance never registers
+                                        if (e.w >= 0.0f && e.w < FLT_MAX && (live & (1u << k))) {
                                             live &= ~(1u << k);
                                             best[k] = tri;
                                             fr.rhi[k] = 0u;
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_shadow(const __grid_constant__ 
                 for (int sp = 0; lit && sp < P.nspheres; ++sp) {
                     const float4 c = P.spheres[2 * sp];
                     v3 Is;
-                    if (exact_ray_sphere(O, D, mk3(c), c.w, Is)) lit = false;
+                    if (exact_ray_sphere(O, D, mk3(c), c.w, Is) && e_distance(O, Is) < FLT_MAX) lit = false;
                 }
             }
             if (lit) atomicOr(&P.lit[sid[k]], 1u << lid[k]);
