@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -18,8 +19,11 @@ namespace {
 using namespace rt;
 
 // ---- tunables -------------------------------------------------------------------------------------
-constexpr int kRP = 2;   // ray pairs per thread (R = 4 rays)
-constexpr int kJ = 8;    // triangles per filter block (R*J = 32 candidate bits)
+// Scan-kernel shapes compiled into the library: (ray pairs per thread, triangles per filter block,
+// resident CTAs per SM).  The first entry is the default; RT_B200_TUNE="rp,j,minb" selects another
+// (tools/tune.py sweeps them on the GPU).
+#define RT_SCAN_CONFIGS(X) X(2, 8, 2) X(2, 8, 3) X(1, 8, 4) X(1, 16, 4) X(1, 8, 3) X(1, 16, 3) X(1, 8, 5) X(1, 16, 5) X(2, 4, 2) X(2, 4, 3)
+struct ScanConfig { int rp, j, minb; };
 constexpr uint32_t kMaxChunkSamples = 1u << 23;  // 8 Mi samples per wavefront chunk (84 B of state each)
 
 // ---- NCCL through dlopen (no link-time dependency; inside python the already-loaded torch copy is reused)
@@ -93,6 +97,7 @@ struct Global {
     bool single_process = true;
     bool scene_ready = false, frame_ready = false;
     NcclApi nccl;
+    ScanConfig scan = {2, 8, 2};
     float scene_extent = 0.f;   // max |coordinate| over the scene
     bool any_transparent = false;
     rt_params last;             // params of the last frame
@@ -174,6 +179,39 @@ struct LaunchTimer {
     ~LaunchTimer() { if (timed) cudaEventRecord(d.kev[2 * (d.kev_kind.size() - 1) + 1], d.stream); }
 };
 
+template <int RP, int J, int MINB>
+void launch_scan(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
+    switch (which) {
+        case 0: k_trace<RP, J, MINB, true><<<grid, kThreads, 0, st>>>(P, level); break;
+        case 1: k_trace<RP, J, MINB, false><<<grid, kThreads, 0, st>>>(P, level); break;
+        case 2: k_shadow<RP, J, MINB, false><<<grid, kThreads, 0, st>>>(P, level); break;
+        default: k_shadow<RP, J, MINB, true><<<grid, kThreads, 0, st>>>(P, level); break;
+    }
+}
+enum { kScanPrimary = 0, kScanBounce = 1, kScanShadowAny = 2, kScanShadowNearest = 3 };
+
+// which: kScan*; the grid is one CTA per resident slot (persistent CTAs stride over ray chunks)
+void dispatch_scan(const ScanConfig& c, int which, int num_sms, cudaStream_t st, const FrameParams& P, int level) {
+#define RT_X(RP, J, MINB) if (c.rp == RP && c.j == J && c.minb == MINB) return launch_scan<RP, J, MINB>(which, num_sms * MINB, st, P, level);
+    RT_SCAN_CONFIGS(RT_X)
+#undef RT_X
+}
+
+bool scan_config_exists(const ScanConfig& c) {
+#define RT_X(RP, J, MINB) if (c.rp == RP && c.j == J && c.minb == MINB) return true;
+    RT_SCAN_CONFIGS(RT_X)
+#undef RT_X
+    return false;
+}
+
+void read_tuning_env() {
+    const char* e = getenv("RT_B200_TUNE");
+    if (!e) return;
+    ScanConfig c = g.scan;
+    if (sscanf(e, "%d,%d,%d", &c.rp, &c.j, &c.minb) == 3 && scan_config_exists(c)) g.scan = c;
+    else fprintf(stderr, "librt_b200: RT_B200_TUNE=%s is not a compiled scan configuration; keeping %d,%d,%d\n", e, g.scan.rp, g.scan.j, g.scan.minb);
+}
+
 int check_ready() {
     if (g.devs.empty()) return fail(RT_ERR_STATE, "rt_init has not been called (or failed): there is no CPU fallback");
     return RT_OK;
@@ -236,7 +274,7 @@ void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float e
 }
 
 // Wavefront for one chunk whose rays are either generated (primary) or already in ray_o/ray_d (trace API).
-int run_wavefront(RtDevice& d, const FrameParams& P, int grid_scan) {
+int run_wavefront(RtDevice& d, const FrameParams& P) {
     const bool shadows = (P.features & RT_SHADOWS) && P.nlights > 0;
     const bool bounces = (P.features & (RT_REFLECTION | RT_REFRACTION)) != 0;
     const int levels = bounces ? std::min(P.max_lvl + 1, kMaxLevels - 2) : 1;
@@ -244,13 +282,11 @@ int run_wavefront(RtDevice& d, const FrameParams& P, int grid_scan) {
     for (int level = 0; level < levels; ++level) {
         {
             LaunchTimer t(d, kKindTrace);
-            if (level == 0) k_trace<kRP, kJ, true><<<grid_scan, kThreads, 0, d.stream>>>(P, 0);
-            else k_trace<kRP, kJ, false><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
+            dispatch_scan(g.scan, level == 0 ? kScanPrimary : kScanBounce, d.num_sms, d.stream, P, level);
         }
         if (shadows) {
             LaunchTimer t(d, kKindShadow);
-            if (g.any_transparent) k_shadow<kRP, kJ, true><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
-            else k_shadow<kRP, kJ, false><<<grid_scan, kThreads, 0, d.stream>>>(P, level);
+            dispatch_scan(g.scan, g.any_transparent ? kScanShadowNearest : kScanShadowAny, d.num_sms, d.stream, P, level);
         }
         {
             LaunchTimer t(d, kKindShade);
@@ -327,8 +363,7 @@ int render_enqueue(const rt_params* rp) {
             P.nsamples = (uint32_t)(P.nrows * row_samples);
             P.sample_base = (uint32_t)(P.row0 * row_samples);
             P.prim_out = rp->want_prim_id ? d.prim : nullptr;
-            const int grid_scan = d.num_sms * 2;
-            int levels = run_wavefront(d, P, grid_scan);
+            int levels = run_wavefront(d, P);
             if (levels < 0) return levels;
             g.stats.n_levels = (uint32_t)levels;
             {
@@ -445,6 +480,7 @@ int rt_init(int n_gpus) {
     if (e != cudaSuccess || count == 0)
         return fail(RT_ERR_NO_DEVICE, "no CUDA device (%s); librt_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count == 0");
     if (n_gpus < 1 || n_gpus > count) return fail(RT_ERR_INVALID, "n_gpus=%d but %d device(s) are visible", n_gpus, count);
+    read_tuning_env();
     g.devs.resize(n_gpus);
     g.world = n_gpus;
     g.single_process = true;
@@ -481,6 +517,7 @@ int rt_init_rank(int device, int rank, int world, const void* nccl_id, size_t nc
     if (e != cudaSuccess || count == 0)
         return fail(RT_ERR_NO_DEVICE, "no CUDA device (%s); librt_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count == 0");
     if (device < 0 || device >= count || world < 1 || rank < 0 || rank >= world) return fail(RT_ERR_INVALID, "bad device/rank/world %d/%d/%d", device, rank, world);
+    read_tuning_env();
     g.devs.resize(1);
     g.world = world;
     g.single_process = false;
@@ -667,13 +704,13 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     if (prim_id || hit) {
         FrameParams P0 = P;
         P0.features &= ~(RT_REFLECTION | RT_REFRACTION | RT_SHADOWS);
-        k_trace<kRP, kJ, true><<<d.num_sms * 2, kThreads, 0, d.stream>>>(P0, 0);
+        dispatch_scan(g.scan, kScanPrimary, d.num_sms, d.stream, P0, 0);
         CU(cudaGetLastError());
         hh.resize(n);
         CU(cudaMemcpyAsync(hh.data(), d.hit, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
         CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords, d.stream));
     }
-    int levels = run_wavefront(d, P, d.num_sms * 2);
+    int levels = run_wavefront(d, P);
     if (levels < 0) return levels;
     CU(cudaMemcpyAsync(ha.data(), d.acc, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));

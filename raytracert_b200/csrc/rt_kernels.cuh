@@ -395,8 +395,8 @@ struct FetchFromRays {
     }
 };
 
-template <int RP, int J, bool PRIMARY>
-__global__ void __launch_bounds__(kThreads, 2) k_trace(const __grid_constant__ FrameParams P, int level) {
+template <int RP, int J, int MINB, bool PRIMARY>
+__global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant__ FrameParams P, int level) {
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
     const uint32_t count = PRIMARY ? P.nsamples : P.counters[kCntRay + level];
@@ -499,8 +499,8 @@ struct FetchShadow {
     }
 };
 
-template <int RP, int J, bool NEAREST>
-__global__ void __launch_bounds__(kThreads, 2) k_shadow(const __grid_constant__ FrameParams P, int level) {
+template <int RP, int J, int MINB, bool NEAREST>
+__global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant__ FrameParams P, int level) {
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
     const uint32_t nl = (uint32_t)P.nlights;
