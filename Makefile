@@ -29,7 +29,7 @@ $(BUILD)/librt_b200.so: $(wildcard $(CSRC)/*.cu) $(wildcard $(CSRC)/*.cuh) inclu
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/rt_b200.cu -cudart static -ldl
 
-$(BUILD)/rt_main: $(HOSTDIR)/main.cpp $(HOSTDIR)/raytracing.cpp $(HOSTDIR)/mesh.cpp $(wildcard $(HOSTDIR)/*.h) $(BUILD)/librt_b200.so
+$(BUILD)/rt_main: $(HOSTDIR)/main.cpp $(HOSTDIR)/raytracing.cpp $(HOSTDIR)/mesh.cpp $(wildcard $(HOSTDIR)/*.h) include/rt_b200.h $(BUILD)/librt_b200.so
 	$(CXX) $(HOSTFLAGS) -o $@ $(HOSTDIR)/main.cpp $(HOSTDIR)/raytracing.cpp $(HOSTDIR)/mesh.cpp -L$(BUILD) -lrt_b200 -Wl,-rpath,'$$ORIGIN'
 
 clean:

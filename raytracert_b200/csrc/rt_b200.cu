@@ -305,7 +305,10 @@ float magnitude_bound(const rt_params& rp, const float* extra, int n_extra) {
     return pow2_ceil(m);
 }
 
-float eps_r_for(float M) { return M * (24.0f * kU32 / kCosMin + 64.0f * kU32); }
+// Guard band of the distance tests (DESIGN.md "filter soundness"): the reference's r = a/b is within
+// 24uM/|cos| of the true distance, its rounded hit point within 8uM of that, the filter's own r' within
+// 10uM/|cos|; pairs with |cos| < kCosMin never rely on it (they always go to the exact path).
+float eps_r_for(float M) { return M * (48.0f * kU32 / kCosMin + 128.0f * kU32); }
 
 int validate_params(const rt_params* p, bool need_frame) {
     if (!p) return fail(RT_ERR_INVALID, "params is NULL");

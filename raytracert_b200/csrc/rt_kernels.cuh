@@ -121,9 +121,12 @@ __global__ void k_build_records(const float4* __restrict__ triv, int ntri, int n
                 double gmax = fmax(gs, fmax(gt, gq));
                 double sinphi = nn / sqrt(uu * vv);
                 double kappa = fmax(1.0, 0.25 / sinphi);
-                double E0 = 128.0 * (double)kU32 * (double)M * gmax * kappa + 1e-6;
-                double E1 = 32.0 * (double)kU32 * (double)M * gmax * kappa;
-                if (!(E0 < 0.25)) {
+                // DESIGN.md "filter soundness": E0 covers the rounding of the reference's own dot-product
+                // barycentrics (<= 28uM*gmax/sin(phi) + 8u/sin^2(phi)) plus this filter's arithmetic (<= 16uM*gmax),
+                // E1*|1/cos| the in-plane shift caused by the two sides' error along the ray (<= 34uM/|cos|)
+                double E0 = 256.0 * (double)kU32 * (double)M * gmax * kappa + 1e-6;
+                double E1 = 64.0 * (double)kU32 * (double)M * gmax * kappa;
+                if (!(E0 < 0.5)) {
                     always = true;
                 } else {
                     q0 = make_float4((float)nx, (float)ny, (float)nz, (float)(-(nx * A.x + ny * A.y + nz * A.z)));
