@@ -67,12 +67,15 @@ struct RtDevice {
     ncclComm_t comm = nullptr;
     // scene
     float4 *rec = nullptr, *triv = nullptr, *normal_mat = nullptr, *materials = nullptr, *spheres = nullptr;
+    size_t cap_rec = 0, cap_triv = 0, cap_nm = 0, cap_mat = 0, cap_sph = 0;  // in float4; buffers are reused across uploads
     int ntri = 0, ntiles = 0, nmat = 0, nspheres = 0;
     float M_built = 0.f;
     // per-chunk state
     size_t cap_samples = 0;
     float4 *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *acc = nullptr, *hit = nullptr;
     uint32_t *lit = nullptr, *q_ray = nullptr, *q_hit = nullptr;
+    unsigned long long* key = nullptr;  // nearest-hit merge keys, kKeyEmpty between launches
+    float4* hit0 = nullptr;             // rt_trace: copy of the level-0 hit records
     uint32_t* counters = nullptr;      // kCntWords per chunk slot
     int counters_slots = 0;
     int32_t* prim = nullptr; size_t cap_prim = 0;
@@ -155,7 +158,7 @@ void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
     void* ptrs[] = {d.rec, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
-                    d.q_hit, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
+                    d.q_hit, d.key, d.hit0, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     for (auto& e : d.ev_phase) if (e) cudaEventDestroy(e);
@@ -227,7 +230,7 @@ float pow2_ceil(float v) {
 int build_records(RtDevice& d, float M) {
     if (d.M_built >= M && d.rec) return RT_OK;
     CU(cudaSetDevice(d.device));
-    const int npad = d.ntiles * kTile;
+    const int npad = (d.ntiles + kPadTiles) * kTile;
     k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.ntri, npad, M, d.rec);
     CU(cudaGetLastError());
     d.M_built = M;
@@ -237,13 +240,15 @@ int build_records(RtDevice& d, float M) {
 int ensure_chunk_state(RtDevice& d, size_t nsamples, bool want_prim, size_t prim_total) {
     CU(cudaSetDevice(d.device));
     if (nsamples > d.cap_samples) {
-        void** ptrs[] = {(void**)&d.ray_o, (void**)&d.ray_d, (void**)&d.thr, (void**)&d.acc, (void**)&d.hit, (void**)&d.lit, (void**)&d.q_ray, (void**)&d.q_hit};
-        const size_t sizes[] = {16, 16, 16, 16, 16, 4, 4, 4};
-        for (int i = 0; i < 8; ++i) {
+        void** ptrs[] = {(void**)&d.ray_o, (void**)&d.ray_d, (void**)&d.thr, (void**)&d.acc, (void**)&d.hit, (void**)&d.lit, (void**)&d.q_ray, (void**)&d.q_hit, (void**)&d.key};
+        const size_t sizes[] = {16, 16, 16, 16, 16, 4, 4, 4, 8};
+        for (int i = 0; i < 9; ++i) {
             if (*ptrs[i]) cudaFree(*ptrs[i]);
             *ptrs[i] = nullptr;
             CU(cudaMalloc(ptrs[i], sizes[i] * nsamples));
         }
+        // keys are kKeyEmpty whenever no scan is in flight: set once here, restored by k_finish after every read
+        CU(cudaMemsetAsync(d.key, 0xff, 8 * nsamples, d.stream));
         d.cap_samples = nsamples;
     }
     if (want_prim) { int rc = ensure(d.prim, d.cap_prim, prim_total); if (rc) return rc; }
@@ -264,7 +269,7 @@ void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float e
     P.rec = d.rec; P.triv = d.triv; P.normal_mat = d.normal_mat; P.materials = d.materials; P.spheres = d.spheres;
     P.ntri = d.ntri; P.ntiles = d.ntiles; P.nspheres = d.nspheres;
     P.ray_o = d.ray_o; P.ray_d = d.ray_d; P.thr = d.thr; P.acc = d.acc; P.hit = d.hit; P.lit = d.lit;
-    P.q_ray = d.q_ray; P.q_hit = d.q_hit; P.counters = counters;
+    P.q_ray = d.q_ray; P.q_hit = d.q_hit; P.counters = counters; P.key = d.key;
     P.eps_r = eps_r;
     memcpy(P.camera, rp.camera, sizeof(P.camera));
     P.nlights = (int)rp.n_lights;
@@ -274,23 +279,29 @@ void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float e
 }
 
 // Wavefront for one chunk whose rays are either generated (primary) or already in ray_o/ray_d (trace API).
-int run_wavefront(RtDevice& d, const FrameParams& P) {
+int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullptr) {
     const bool shadows = (P.features & RT_SHADOWS) && P.nlights > 0;
     const bool bounces = (P.features & (RT_REFLECTION | RT_REFRACTION)) != 0;
     const int levels = bounces ? std::min(P.max_lvl + 1, kMaxLevels - 2) : 1;
-    const int grid_shade = d.num_sms * 4;
+    const int grid_small = d.num_sms * 4;
     for (int level = 0; level < levels; ++level) {
         {
             LaunchTimer t(d, kKindTrace);
             dispatch_scan(g.scan, level == 0 ? kScanPrimary : kScanBounce, d.num_sms, d.stream, P, level);
         }
+        {
+            LaunchTimer t(d, kKindShade);
+            if (level == 0) k_finish<true><<<grid_small, 256, 0, d.stream>>>(P, 0);
+            else k_finish<false><<<grid_small, 256, 0, d.stream>>>(P, level);
+        }
+        if (level == 0 && level0_hits) CU(cudaMemcpyAsync(level0_hits, d.hit, sizeof(float4) * P.nsamples, cudaMemcpyDeviceToDevice, d.stream));
         if (shadows) {
             LaunchTimer t(d, kKindShadow);
             dispatch_scan(g.scan, g.any_transparent ? kScanShadowNearest : kScanShadowAny, d.num_sms, d.stream, P, level);
         }
         {
             LaunchTimer t(d, kKindShade);
-            k_shade<<<grid_shade, 256, 0, d.stream>>>(P, level);
+            k_shade<<<grid_small, 256, 0, d.stream>>>(P, level);
         }
     }
     CU(cudaGetLastError());
@@ -579,17 +590,17 @@ int rt_upload_scene(const rt_scene* sc) {
     for (RtDevice& d : g.devs) {
         CU(cudaSetDevice(d.device));
         CU(cudaStreamSynchronize(d.stream));
-        for (float4** p : {&d.rec, &d.triv, &d.normal_mat, &d.materials, &d.spheres}) { if (*p) cudaFree(*p); *p = nullptr; }
         d.ntri = (int)n;
         d.ntiles = std::max(1, (int)((n + kTile - 1) / kTile));
         d.nmat = (int)sc->n_materials;
         d.nspheres = (int)sc->n_spheres;
         d.M_built = 0.f;
-        CU(cudaMalloc(&d.rec, sizeof(float4) * (size_t)d.ntiles * kTile * kRecVec));
-        CU(cudaMalloc(&d.triv, sizeof(float4) * triv.size()));
-        CU(cudaMalloc(&d.normal_mat, sizeof(float4) * nm.size()));
-        CU(cudaMalloc(&d.materials, sizeof(rt_material) * sc->n_materials));
-        CU(cudaMalloc(&d.spheres, sizeof(float4) * sph.size()));
+        // grow-only device buffers: re-uploading a scene of the same size allocates nothing
+        rc = ensure(d.rec, d.cap_rec, (size_t)(d.ntiles + kPadTiles) * kTile * kRecVec); if (rc) return rc;
+        rc = ensure(d.triv, d.cap_triv, triv.size()); if (rc) return rc;
+        rc = ensure(d.normal_mat, d.cap_nm, nm.size()); if (rc) return rc;
+        rc = ensure(d.materials, d.cap_mat, (size_t)4 * sc->n_materials); if (rc) return rc;
+        rc = ensure(d.spheres, d.cap_sph, sph.size()); if (rc) return rc;
         CU(cudaMemcpyAsync(d.triv, triv.data(), sizeof(float4) * triv.size(), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.normal_mat, nm.data(), sizeof(float4) * nm.size(), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.materials, sc->materials, sizeof(rt_material) * sc->n_materials, cudaMemcpyHostToDevice, d.stream));
@@ -702,19 +713,19 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     P.trace_api = 1;
     P.nsamples = (uint32_t)n;
     P.G = 1;
-    // level 0 alone first, so that the primary hit records can be read back before bounces overwrite them
+    // the level-0 hit records are copied aside on the device before the bounces overwrite them
     std::vector<float4> hh;
     if (prim_id || hit) {
-        FrameParams P0 = P;
-        P0.features &= ~(RT_REFLECTION | RT_REFRACTION | RT_SHADOWS);
-        dispatch_scan(g.scan, kScanPrimary, d.num_sms, d.stream, P0, 0);
-        CU(cudaGetLastError());
-        hh.resize(n);
-        CU(cudaMemcpyAsync(hh.data(), d.hit, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
-        CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords, d.stream));
+        if (d.hit0) cudaFree(d.hit0);
+        d.hit0 = nullptr;
+        CU(cudaMalloc(&d.hit0, sizeof(float4) * (size_t)n));
     }
-    int levels = run_wavefront(d, P);
+    int levels = run_wavefront(d, P, (prim_id || hit) ? d.hit0 : nullptr);
     if (levels < 0) return levels;
+    if (prim_id || hit) {
+        hh.resize(n);
+        CU(cudaMemcpyAsync(hh.data(), d.hit0, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+    }
     CU(cudaMemcpyAsync(ha.data(), d.acc, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
     for (int i = 0; i < n; ++i) {

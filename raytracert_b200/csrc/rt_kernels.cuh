@@ -28,6 +28,9 @@ constexpr int kStages = 4;         // TMA ring depth
 constexpr int kWarps = 8;          // all warps are consumers; the last warp to finish a stage refills it
 constexpr int kThreads = kWarps * 32;
 constexpr uint32_t kTileBytes = kTile * kRecVec * sizeof(float4);
+constexpr int kMaxParts = 64;      // a launch with few rays splits the triangle range into <= kMaxParts parts per ray chunk
+constexpr int kPadTiles = kMaxParts;  // "never" tiles appended to the record array so that every part has the same length
+constexpr unsigned long long kKeyEmpty = ~0ull;  // (distance bits << 32 | primitive id); all ones = no hit yet
 
 constexpr float kU32 = 5.9604645e-8f;  // 2^-24
 constexpr float kCosMin = 1.0e-3f;     // |cos(ray, plane normal)| below this -> always exact ("grazing")
@@ -57,6 +60,7 @@ struct FrameParams {
     uint32_t* q_ray;
     uint32_t* q_hit;
     uint32_t* counters;
+    unsigned long long* key;    // per sample: nearest (distance, triangle) found by the scan parts, merged with atomicMin
     int32_t* prim_out;          // optional: primary primitive id per local sample
     // frame
     float corners[24];
@@ -164,12 +168,34 @@ struct __align__(128) ScanSmem {
     unsigned int done[kStages];
 };
 
+// Work decomposition of one scan launch.  count rays -> nchunks chunks of kThreads*R rays; when there are fewer chunks
+// than CTAs the triangle tiles are split into `parts` ranges of `len` tiles each (the record array carries kPadTiles
+// "never" tiles, so the last range may run past ntiles).  Work item w = chunk * parts + part; CTA b takes items
+// b, b + gridDim.x, ...  Results of the parts of a chunk are merged through atomics on per-ray keys / lit bits.
+struct Split {
+    uint32_t nchunks, parts, len, nitems;
+};
+__device__ __forceinline__ Split make_split(uint32_t count, uint32_t per_chunk, int ntiles, bool allow_split) {
+    Split sp;
+    sp.nchunks = (count + per_chunk - 1) / per_chunk;
+    uint32_t parts = 1;
+    if (allow_split && sp.nchunks > 0 && sp.nchunks < gridDim.x) {
+        parts = (gridDim.x + sp.nchunks - 1) / sp.nchunks;
+        if (parts > (uint32_t)kMaxParts) parts = kMaxParts;
+        if (parts > (uint32_t)ntiles) parts = ntiles;
+    }
+    sp.len = ((uint32_t)ntiles + parts - 1) / parts;
+    sp.parts = ((uint32_t)ntiles + sp.len - 1) / sp.len;   // no empty part
+    sp.nitems = sp.nchunks * sp.parts;
+    return sp;
+}
+
 struct Pipe {
     uint32_t tiles_addr, full_addr;
     unsigned int* done;
     const float4* tiles_ptr;
     const float4* rec;
-    int ntiles;
+    uint32_t parts, len;   // see Split
     uint32_t total_iters;  // tiles this CTA will consume over its whole life
     uint32_t it;           // next iteration
 };
@@ -177,21 +203,28 @@ struct Pipe {
 __device__ __forceinline__ void pipe_issue(const Pipe& p, uint32_t iter) {
     const uint32_t stage = iter % kStages;
     const uint32_t bar = p.full_addr + stage * 8u;
-    const int tile = (int)(iter % (uint32_t)p.ntiles);
+    const uint32_t q = iter / p.len;                                   // this CTA's q-th work item
+    const uint32_t item = blockIdx.x + q * gridDim.x;
+    const uint32_t tile = (item % p.parts) * p.len + (iter - q * p.len);
     // generic-proxy reads of this stage (all warps are past it) are ordered before the async-proxy write
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive_expect_tx(bar, kTileBytes);
     tma_bulk_g2s(p.tiles_addr + stage * kTileBytes, p.rec + (size_t)tile * kTile * kRecVec, kTileBytes, bar);
 }
 
-__device__ __forceinline__ void pipe_init(Pipe& p, ScanSmem& sm, const float4* rec, int ntiles, uint32_t total_iters) {
+__device__ __forceinline__ uint32_t cta_items(uint32_t nitems) {
+    return (nitems > blockIdx.x) ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+}
+
+__device__ __forceinline__ void pipe_init(Pipe& p, ScanSmem& sm, const float4* rec, const Split& sp) {
     p.tiles_addr = smem_u32(&sm.tiles[0][0]);
     p.full_addr = smem_u32(&sm.full[0]);
     p.done = sm.done;
     p.tiles_ptr = &sm.tiles[0][0];
     p.rec = rec;
-    p.ntiles = ntiles;
-    p.total_iters = total_iters;
+    p.parts = sp.parts;
+    p.len = sp.len;
+    p.total_iters = cta_items(sp.nitems) * sp.len;
     p.it = 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(p.full_addr + s * 8u, 1); sm.done[s] = 0; }
@@ -199,7 +232,7 @@ __device__ __forceinline__ void pipe_init(Pipe& p, ScanSmem& sm, const float4* r
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t n = total_iters < (uint32_t)kStages ? total_iters : (uint32_t)kStages;
+        const uint32_t n = p.total_iters < (uint32_t)kStages ? p.total_iters : (uint32_t)kStages;
         for (uint32_t i = 0; i < n; ++i) pipe_issue(p, i);
     }
 }
@@ -293,10 +326,10 @@ struct BitLayout {
 // clears the ray's live bit on the first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
 template <int RP, int J, bool NEAREST, class Fetch>
 __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
-                                          const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact) {
+                                          const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact, int tile_begin) {
     constexpr int R = 2 * RP;
     constexpr uint32_t REP = BitLayout<RP, J>::kRep;
-    for (int tile = 0; tile < pipe.ntiles; ++tile) {
+    for (int tile = tile_begin; tile < tile_begin + (int)pipe.len; ++tile) {
         const float4* rec = pipe_acquire(pipe);
         // warp-level early exit (shadow rays): nothing left to decide for any lane of this warp
         if (!__all_sync(0xffffffffu, live == 0u)) {
@@ -381,22 +414,23 @@ __device__ __forceinline__ void primary_ray(const FrameParams& P, uint32_t s, v3
     D = lerp_corner(P.corners, 3, xs, omx, ys, omy);
 }
 
-__device__ __forceinline__ uint32_t cta_total_chunks(uint32_t nchunks) {
-    return (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-}
-
 // ------------------------------------------------------------------------------------------------
 // k_trace: nearest hit for primary rays (generated in registers) or queued continuation rays.
 // ------------------------------------------------------------------------------------------------
-struct FetchFromRays {
-    const float4* ray_o;
-    const float4* ray_d;
-    const uint32_t* sid;
-    __device__ __forceinline__ void operator()(int k, v3& O, v3& D) const {
-        const float4 o = ray_o[sid[k]], d = ray_d[sid[k]];
-        O = mk3(o); D = mk3(d);
-    }
-};
+// Ray set-up shared by the scan kernels: slot k of this thread gets ray (O, D) or is marked unused.
+template <int RP>
+__device__ __forceinline__ void fast_set_slot(FastRays<RP>& fr, int k, v3 O, v3 D, float eps_r, bool ok) {
+    constexpr int R = 2 * RP;
+    // (fast_set needs a compile-time slot)
+    if (k == 0) fast_set<RP, 0>(fr, O, D, eps_r, ok);
+    if (k == 1) fast_set<RP, 1>(fr, O, D, eps_r, ok);
+    if (k == 2) fast_set<RP, (R > 2 ? 2 : 0)>(fr, O, D, eps_r, ok);
+    if (k == 3) fast_set<RP, (R > 2 ? 3 : 0)>(fr, O, D, eps_r, ok);
+    if (k == 4) fast_set<RP, (R > 4 ? 4 : 0)>(fr, O, D, eps_r, ok);
+    if (k == 5) fast_set<RP, (R > 4 ? 5 : 0)>(fr, O, D, eps_r, ok);
+    if (k == 6) fast_set<RP, (R > 6 ? 6 : 0)>(fr, O, D, eps_r, ok);
+    if (k == 7) fast_set<RP, (R > 6 ? 7 : 0)>(fr, O, D, eps_r, ok);
+}
 
 template <int RP, int J, int MINB, bool PRIMARY>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant__ FrameParams P, int level) {
@@ -404,13 +438,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
     __shared__ ScanSmem sm;
     const uint32_t count = PRIMARY ? P.nsamples : P.counters[kCntRay + level];
     const uint32_t per_chunk = kThreads * R;
-    const uint32_t nchunks = (count + per_chunk - 1) / per_chunk;
+    const Split sp = make_split(count, per_chunk, P.ntiles, true);
     Pipe pipe;
-    pipe_init(pipe, sm, P.rec, P.ntiles, cta_total_chunks(nchunks) * (uint32_t)P.ntiles);
+    pipe_init(pipe, sm, P.rec, sp);
     uint32_t n_exact = 0;
     const float eps_r2 = 2.0f * P.eps_r;
 
-    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (uint32_t item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
+        const uint32_t chunk = item / sp.parts, part = item - chunk * sp.parts;
         FastRays<RP> fr;
         float dist[R];
         int best[R];
@@ -418,20 +453,22 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
         uint32_t live = 0;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            const uint32_t item = chunk * per_chunk + k * kThreads + threadIdx.x;
-            const bool ok = item < count;
+            const uint32_t ray = chunk * per_chunk + k * kThreads + threadIdx.x;
+            const bool ok = ray < count;
             v3 O = mk3(0, 0, 0), D = mk3(0, 0, 1);
             uint32_t s = 0;
             if (ok) {
                 if (PRIMARY && !P.trace_api) {
-                    s = item;
+                    s = ray;
                     primary_ray(P, s, O, D);
-                    P.ray_o[s] = make_float4(O.x, O.y, O.z, 0.f);
-                    P.ray_d[s] = make_float4(D.x, D.y, D.z, __int_as_float(0));
-                    P.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
-                    P.acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (part == 0) {  // every part regenerates the ray (cheap); one of them publishes it
+                        P.ray_o[s] = make_float4(O.x, O.y, O.z, 0.f);
+                        P.ray_d[s] = make_float4(D.x, D.y, D.z, __int_as_float(0));
+                        P.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
+                        P.acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 } else {
-                    s = PRIMARY ? item : P.q_ray[item];
+                    s = PRIMARY ? ray : P.q_ray[ray];
                     const float4 o = P.ray_o[s], d = P.ray_d[s];
                     O = mk3(o); D = mk3(d);
                 }
@@ -440,56 +477,76 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
             sid[k] = s;
             dist[k] = FLT_MAX;
             best[k] = -1;
-            // (fast_set needs a compile-time slot)
-            if (k == 0) fast_set<RP, 0>(fr, O, D, P.eps_r, ok);
-            if (k == 1) fast_set<RP, 1>(fr, O, D, P.eps_r, ok);
-            if (k == 2) fast_set<RP, (R > 2 ? 2 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 3) fast_set<RP, (R > 2 ? 3 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 4) fast_set<RP, (R > 4 ? 4 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 5) fast_set<RP, (R > 4 ? 5 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 6) fast_set<RP, (R > 6 ? 6 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 7) fast_set<RP, (R > 6 ? 7 : 0)>(fr, O, D, P.eps_r, ok);
+            fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
         }
-        FetchFromRays fetch{P.ray_o, P.ray_d, sid};
-        scan_pass<RP, J, true>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact);
+        // fetch() re-reads a ray for the exact path: primary rays of other parts may not be published yet
+        auto fetch = [&](int k, v3& O, v3& D) {
+            if (PRIMARY && !P.trace_api) { primary_ray(P, sid[k], O, D); }
+            else { const float4 o = P.ray_o[sid[k]], d = P.ray_d[sid[k]]; O = mk3(o); D = mk3(d); }
+        };
+        scan_pass<RP, J, true>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len));
 
-        // epilogue: exact hit point of the winner, analytic spheres, hit record, compaction
+        // merge: (distance bits, triangle id) -- the smallest distance wins, equal distances go to the lowest
+        // index, which is exactly the sequential rule of intersectMesh (strict <, raytracing.cpp:183)
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const bool ok = (live >> k) & 1u;
-            int idx = -1;
-            v3 I = mk3(0, 0, 0);
-            if (ok) {
-                idx = best[k];
-                v3 O, D;
-                fetch(k, O, D);
-                if (idx >= 0) {
-                    const float4 e = exact_eval_tri(P.triv, idx, O.x, O.y, O.z, D.x, D.y, D.z);
-                    I = mk3(e);
-                }
-                float dbest = dist[k];
-                for (int sp = 0; sp < P.nspheres; ++sp) {  // spheres come after the triangles, strict <
-                    const float4 c = P.spheres[2 * sp];
-                    v3 Is;
-                    if (exact_ray_sphere(O, D, mk3(c), c.w, Is)) {
-                        const float ds = e_distance(O, Is);
-                        if (ds < dbest) { dbest = ds; idx = P.ntri + sp; I = Is; }
-                    }
-                }
-                P.hit[sid[k]] = make_float4(I.x, I.y, I.z, __int_as_float(idx));
-                P.lit[sid[k]] = 0u;
-                if (PRIMARY && P.prim_out) P.prim_out[P.sample_base + sid[k]] = idx;
-            }
-            warp_append(ok && idx >= 0, sid[k], P.q_hit, &P.counters[kCntHit + level]);
-        }
+        for (int k = 0; k < R; ++k)
+            if (((live >> k) & 1u) && best[k] >= 0)
+                atomicMin(&P.key[sid[k]], ((unsigned long long)__float_as_uint(dist[k]) << 32) | (unsigned int)best[k]);
     }
     if (n_exact) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)n_exact);
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_finish: one thread per ray of this level.  Reads the merged nearest-triangle key, recomputes the exact hit
+// point of the winner, tests the analytic spheres (after the triangles, strict <), writes the hit record,
+// arms the lit bits for k_shadow and appends hits to the queue (warp-aggregated).
+// ------------------------------------------------------------------------------------------------
+template <bool PRIMARY>
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FrameParams P, int level) {
+    const uint32_t count = PRIMARY ? P.nsamples : P.counters[kCntRay + level];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (count + stride - 1) / stride;
+    const uint32_t all_lit = (P.nlights >= 32) ? 0xffffffffu : ((1u << P.nlights) - 1u);
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool hit_any = false;
+        uint32_t s = 0;
+        if (i < count) {
+            s = PRIMARY ? i : P.q_ray[i];
+            const unsigned long long key = P.key[s];
+            P.key[s] = kKeyEmpty;  // ready for the next level / frame
+            int idx = (key == kKeyEmpty) ? -1 : (int)(unsigned int)(key & 0xffffffffull);
+            float dbest = (key == kKeyEmpty) ? FLT_MAX : __uint_as_float((unsigned int)(key >> 32));
+            const float4 o = P.ray_o[s], d = P.ray_d[s];
+            const v3 O = mk3(o), D = mk3(d);
+            v3 I = mk3(0, 0, 0);
+            if (idx >= 0) {
+                const float4 e = exact_eval_tri(P.triv, idx, O.x, O.y, O.z, D.x, D.y, D.z);
+                I = mk3(e);
+            }
+            for (int sp = 0; sp < P.nspheres; ++sp) {  // spheres come after the triangles, strict <
+                const float4 c = P.spheres[2 * sp];
+                v3 Is;
+                if (exact_ray_sphere(O, D, mk3(c), c.w, Is)) {
+                    const float ds = e_distance(O, Is);
+                    if (ds < dbest) { dbest = ds; idx = P.ntri + sp; I = Is; }
+                }
+            }
+            P.hit[s] = make_float4(I.x, I.y, I.z, __int_as_float(idx));
+            P.lit[s] = all_lit;    // k_shadow clears the bit of every light that is occluded
+            if (PRIMARY && P.prim_out) P.prim_out[P.sample_base + s] = idx;
+            hit_any = idx >= 0;
+        }
+        warp_append(hit_any, s, P.q_hit, &P.counters[kCntHit + level]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_shadow: one work item = (hit sample, light).  isShadow, raytracing.cpp:241-261.
-//   ANY     : exact iff no material has (has_Tr && Tr < 1): any occluder shadows, warp-level early exit.
-//   NEAREST : the nearest occluder's material decides (transparent -> lit).
+//   ANY     : exact iff no material has (has_Tr && Tr < 1): any occluder shadows, warp-level early exit;
+//             the triangle range may be split over CTAs (an occluder found by any part clears the lit bit).
+//   NEAREST : the nearest occluder's material decides (transparent -> lit); never split.
+// lit[] arrives with every light's bit set (k_finish); occluded lights are cleared here.
 // ------------------------------------------------------------------------------------------------
 struct FetchShadow {
     const float4* hit;
@@ -509,13 +566,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
     const uint32_t nl = (uint32_t)P.nlights;
     const uint32_t count = P.counters[kCntHit + level] * nl;
     const uint32_t per_chunk = kThreads * R;
-    const uint32_t nchunks = (count + per_chunk - 1) / per_chunk;
+    const Split sp = make_split(count, per_chunk, P.ntiles, !NEAREST);
     Pipe pipe;
-    pipe_init(pipe, sm, P.rec, P.ntiles, cta_total_chunks(nchunks) * (uint32_t)P.ntiles);
+    pipe_init(pipe, sm, P.rec, sp);
     uint32_t n_exact = 0;
     const float eps_r2 = 2.0f * P.eps_r;
 
-    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (uint32_t item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
+        const uint32_t chunk = item / sp.parts, part = item - chunk * sp.parts;
         FastRays<RP> fr;
         float dist[R];
         int best[R];
@@ -524,13 +582,13 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
         uint32_t live = 0;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            const uint32_t item = chunk * per_chunk + k * kThreads + threadIdx.x;
-            const bool ok = item < count;
+            const uint32_t ray = chunk * per_chunk + k * kThreads + threadIdx.x;
+            const bool ok = ray < count;
             v3 O = mk3(0, 0, 0), D = mk3(0, 0, 1);
             sid[k] = 0; lid[k] = 0; light[k] = D;
             if (ok) {
-                const uint32_t h = item / nl;
-                lid[k] = item - h * nl;
+                const uint32_t h = ray / nl;
+                lid[k] = ray - h * nl;
                 sid[k] = P.q_hit[h];
                 light[k] = mk3(P.lights[lid[k]][0], P.lights[lid[k]][1], P.lights[lid[k]][2]);
                 O = e_add(mk3(P.hit[sid[k]]), mk3(0.1f, 0.1f, 0.1f));
@@ -539,18 +597,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
             }
             dist[k] = FLT_MAX;
             best[k] = -1;
-            if (k == 0) fast_set<RP, 0>(fr, O, D, P.eps_r, ok);
-            if (k == 1) fast_set<RP, 1>(fr, O, D, P.eps_r, ok);
-            if (k == 2) fast_set<RP, (R > 2 ? 2 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 3) fast_set<RP, (R > 2 ? 3 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 4) fast_set<RP, (R > 4 ? 4 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 5) fast_set<RP, (R > 4 ? 5 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 6) fast_set<RP, (R > 6 ? 6 : 0)>(fr, O, D, P.eps_r, ok);
-            if (k == 7) fast_set<RP, (R > 6 ? 7 : 0)>(fr, O, D, P.eps_r, ok);
+            fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
         }
         const uint32_t valid = live;
         FetchShadow fetch{P.hit, sid, light};
-        scan_pass<RP, J, NEAREST>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact);
+        scan_pass<RP, J, NEAREST>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len));
 
 #pragma unroll
         for (int k = 0; k < R; ++k) {
@@ -561,12 +612,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
             if (NEAREST) {
                 int idx = best[k];
                 float dbest = dist[k];
-                for (int sp = 0; sp < P.nspheres; ++sp) {
-                    const float4 c = P.spheres[2 * sp];
+                for (int sph = 0; sph < P.nspheres; ++sph) {
+                    const float4 c = P.spheres[2 * sph];
                     v3 Is;
                     if (exact_ray_sphere(O, D, mk3(c), c.w, Is)) {
                         const float ds = e_distance(O, Is);
-                        if (ds < dbest) { dbest = ds; idx = P.ntri + sp; }
+                        if (ds < dbest) { dbest = ds; idx = P.ntri + sph; }
                     }
                 }
                 if (idx < 0) {
@@ -578,14 +629,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
                     lit = (flags & RT_HAS_TR) && (ks_tr.w < 1.0f);  // transparent occluder: no shadow (:254)
                 }
             } else {
-                lit = (live >> k) & 1u;  // still alive after every triangle: no occluder found
-                for (int sp = 0; lit && sp < P.nspheres; ++sp) {
-                    const float4 c = P.spheres[2 * sp];
-                    v3 Is;
-                    if (exact_ray_sphere(O, D, mk3(c), c.w, Is) && e_distance(O, Is) < FLT_MAX) lit = false;
-                }
+                lit = (live >> k) & 1u;  // still alive after every triangle of this part: no occluder found here
+                if (part == 0)
+                    for (int sph = 0; lit && sph < P.nspheres; ++sph) {
+                        const float4 c = P.spheres[2 * sph];
+                        v3 Is;
+                        if (exact_ray_sphere(O, D, mk3(c), c.w, Is) && e_distance(O, Is) < FLT_MAX) lit = false;
+                    }
             }
-            if (lit) atomicOr(&P.lit[sid[k]], 1u << lid[k]);
+            if (!lit) atomicAnd(&P.lit[sid[k]], ~(1u << lid[k]));
         }
     }
     if (n_exact) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)n_exact);
