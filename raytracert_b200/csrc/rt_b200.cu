@@ -101,6 +101,7 @@ struct Global {
     bool scene_ready = false, frame_ready = false;
     NcclApi nccl;
     ScanConfig scan = {2, 8, 2};
+    float cos_min = kCosMinDefault;  // grazing threshold of the filter (RT_B200_COSMIN overrides, for experiments)
     float scene_extent = 0.f;   // max |coordinate| over the scene
     bool any_transparent = false;
     rt_params last;             // params of the last frame
@@ -208,6 +209,10 @@ bool scan_config_exists(const ScanConfig& c) {
 }
 
 void read_tuning_env() {
+    if (const char* c = getenv("RT_B200_COSMIN")) {
+        const float v = (float)atof(c);
+        if (v >= 1e-6f && v <= 0.1f) g.cos_min = v;
+    }
     const char* e = getenv("RT_B200_TUNE");
     if (!e) return;
     ScanConfig c = g.scan;
@@ -231,7 +236,7 @@ int build_records(RtDevice& d, float M) {
     if (d.M_built >= M && d.rec) return RT_OK;
     CU(cudaSetDevice(d.device));
     const int npad = (d.ntiles + kPadTiles) * kTile;
-    k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.ntri, npad, M, d.rec);
+    k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.ntri, npad, M, g.cos_min, d.rec);
     CU(cudaGetLastError());
     d.M_built = M;
     return RT_OK;
@@ -318,8 +323,8 @@ float magnitude_bound(const rt_params& rp, const float* extra, int n_extra) {
 
 // Guard band of the distance tests (DESIGN.md "filter soundness"): the reference's r = a/b is within
 // 24uM/|cos| of the true distance, its rounded hit point within 8uM of that, the filter's own r' within
-// 10uM/|cos|; pairs with |cos| < kCosMin never rely on it (they always go to the exact path).
-float eps_r_for(float M) { return M * (48.0f * kU32 / kCosMin + 128.0f * kU32); }
+// 10uM/|cos|; pairs with |cos| < cos_min never rely on it (they always go to the exact path).
+float eps_r_for(float M) { return M * (48.0f * kU32 / g.cos_min + 128.0f * kU32); }
 
 int validate_params(const rt_params* p, bool need_frame) {
     if (!p) return fail(RT_ERR_INVALID, "params is NULL");

@@ -33,7 +33,7 @@ constexpr int kPadTiles = kMaxParts;  // "never" tiles appended to the record ar
 constexpr unsigned long long kKeyEmpty = ~0ull;  // (distance bits << 32 | primitive id); all ones = no hit yet
 
 constexpr float kU32 = 5.9604645e-8f;  // 2^-24
-constexpr float kCosMin = 1.0e-3f;     // |cos(ray, plane normal)| below this -> always exact ("grazing")
+constexpr float kCosMinDefault = 1.0e-5f;  // |cos(ray, plane normal)| below this -> always exact ("grazing")
 
 // counters[] layout (uint32 unless noted)
 constexpr int kMaxLevels = 40;
@@ -90,11 +90,11 @@ struct FrameParams {
 // A pair is a CANDIDATE (goes to the exact path) iff
 //   ( min(s', t', c1 - s' - t') >= -E1*|1/b|  and  0 <= r' < rhi' )  or  |b| < bmin
 // with r' = aneg/(-b) (distance along the unit direction from the shifted origin O' = O - eps_r*d).
-//   bmin = kCosMin : normal triangle;   bmin = -1 : never a candidate (degenerate n == 0, padding);
+//   bmin = cos_min : normal triangle;   bmin = -1 : never a candidate (degenerate n == 0, padding);
 //   bmin = +inf    : always a candidate (ill-conditioned triangle, or one whose D is 0/NaN so that the
 //                    reference's NaN barycentrics pass its tests).
 // E0/E1 bound the difference between this evaluation and the reference's own rounding.
-__global__ void k_build_records(const float4* __restrict__ triv, int ntri, int npad, float M, float4* __restrict__ rec) {
+__global__ void k_build_records(const float4* __restrict__ triv, int ntri, int npad, float M, float cos_min, float4* __restrict__ rec) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npad) return;
     float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = make_float4(0, 0, -1.0f, 0);  // "never"
@@ -130,13 +130,13 @@ __global__ void k_build_records(const float4* __restrict__ triv, int ntri, int n
                 // E1*|1/cos| the in-plane shift caused by the two sides' error along the ray (<= 34uM/|cos|)
                 double E0 = 256.0 * (double)kU32 * (double)M * gmax * kappa + 1e-6;
                 double E1 = 64.0 * (double)kU32 * (double)M * gmax * kappa;
-                if (!(E0 < 0.5)) {
+                if (!(E0 < 64.0)) {  // beyond this the dilated triangle is so large that "always exact" is cheaper
                     always = true;
                 } else {
                     q0 = make_float4((float)nx, (float)ny, (float)nz, (float)(-(nx * A.x + ny * A.y + nz * A.z)));
                     q1 = make_float4((float)sx, (float)sy, (float)sz, (float)(-(sx * A.x + sy * A.y + sz * A.z) + E0));
                     q2 = make_float4((float)tx, (float)ty, (float)tz, (float)(-(tx * A.x + ty * A.y + tz * A.z) + E0));
-                    q3 = make_float4((float)(1.0 + 3.0 * E0), (float)(-E1), kCosMin, 0.0f);
+                    q3 = make_float4((float)(1.0 + 3.0 * E0), (float)(-E1), cos_min, 0.0f);
                 }
             }
             if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3 = make_float4(0, 0, __int_as_float(0x7f800000), 0); }
@@ -272,7 +272,8 @@ __device__ __forceinline__ void fast_set(FastRays<RP>& f, v3 O, v3 D, float eps_
     float dx = D.x - O.x, dy = D.y - O.y, dz = D.z - O.z;
     float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-37f));
     dx *= inv; dy *= inv; dz *= inv;
-    if (!live) { dx = dy = dz = 0.f; O = mk3(0.f, 0.f, 0.f); }
+    // an unused / finished slot gets a NaN direction: cos = NaN fails every clause of the candidate test
+    if (!live) { dx = dy = dz = __int_as_float(0x7fc00000); O = mk3(0.f, 0.f, 0.f); }
     constexpr int p = K / 2;
     if (K & 1) {
         f.dx[p].y = dx; f.dy[p].y = dy; f.dz[p].y = dz;
@@ -308,10 +309,19 @@ __device__ __forceinline__ void filter_pair(const FastRays<RP>& f, int p, const 
     float2 q = __fadd2_rn(splat2(q3.x), make_float2(-s.x, -s.y));
     q = __fadd2_rn(q, make_float2(-t.x, -t.y));
     const float m0 = fminf(fminf(s.x, t.x), q.x), m1 = fminf(fminf(s.y, t.y), q.y);
-    const float e0 = q3.y * fabsf(rc.x), e1 = q3.y * fabsf(rc.y);
-    // every comparison is written so that NaN/inf anywhere makes the pair a candidate, never a miss
-    c0 = (!(m0 < e0) && (__float_as_uint(r.x) < f.rhi[2 * p])) || !(fabsf(b.x) >= q3.z);
-    c1 = (!(m1 < e1) && (__float_as_uint(r.y) < f.rhi[2 * p + 1])) || !(fabsf(b.y) >= q3.z);
+    const float2 e = __fmul2_rn(splat2(q3.y), rc);  // tolerance -E1*|1/cos| = -|e|
+    // a NaN in s/t/q/e (non-finite geometry) keeps the pair a candidate; a NaN cos (dead ray slot) never is one
+    c0 = (!(m0 < -fabsf(e.x)) && (__float_as_uint(r.x) < f.rhi[2 * p])) || (fabsf(b.x) < q3.z);
+    c1 = (!(m1 < -fabsf(e.y)) && (__float_as_uint(r.y) < f.rhi[2 * p + 1])) || (fabsf(b.y) < q3.z);
+}
+
+// Finished ray (shadow ray that found its occluder): no further candidates.
+template <int RP>
+__device__ __forceinline__ void kill_slot(FastRays<RP>& f, int k) {
+    const float nan = __int_as_float(0x7fc00000);
+    if (k & 1) { f.dx[k / 2].y = nan; f.dy[k / 2].y = nan; f.dz[k / 2].y = nan; }
+    else { f.dx[k / 2].x = nan; f.dy[k / 2].x = nan; f.dz[k / 2].x = nan; }
+    f.rhi[k] = 0u;
 }
 
 template <int RP, int J>
@@ -336,7 +346,8 @@ __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&
             const int tri0 = tile * kTile;
 #pragma unroll 1
             for (int jb = 0; jb < kTile; jb += J) {
-                uint32_t mask = 0;
+                // hot: only "is there any candidate in this block" (the predicate ORs fold into the compares)
+                bool any = false;
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
@@ -345,12 +356,23 @@ __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&
                     for (int p = 0; p < RP; ++p) {
                         bool c0, c1;
                         filter_pair<RP>(fr, p, q0, q1, q2, q3, c0, c1);
-                        mask |= (c0 ? 1u : 0u) << (j * R + 2 * p);
-                        mask |= (c1 ? 1u : 0u) << (j * R + 2 * p + 1);
+                        any = any || c0 || c1;
                     }
                 }
-                mask &= live * REP;
-                if (mask) {  // cold: exact re-evaluation, per ray in ascending triangle order
+                if (any) {  // cold: redo the block's filter to find which pairs, then exact re-evaluation per ray in ascending triangle order
+                    uint32_t mask = 0;
+#pragma unroll 1
+                    for (int j = 0; j < J; ++j) {
+                        const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
+                        const float4 q2 = rec[(jb + j) * kRecVec + 2], q3 = rec[(jb + j) * kRecVec + 3];
+#pragma unroll
+                        for (int p = 0; p < RP; ++p) {
+                            bool c0, c1;
+                            filter_pair<RP>(fr, p, q0, q1, q2, q3, c0, c1);
+                            mask |= ((c0 ? 1u : 0u) << (2 * p) | (c1 ? 1u : 0u) << (2 * p + 1)) << (j * R);
+                        }
+                    }
+                    mask &= live * REP;
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
                         const uint32_t mk = (mask >> k) & REP;
@@ -375,7 +397,7 @@ __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&
                                         if (e.w >= 0.0f && e.w < FLT_MAX && (live & (1u << k))) {
                                             live &= ~(1u << k);
                                             best[k] = tri;
-                                            fr.rhi[k] = 0u;
+                                            kill_slot<RP>(fr, k);
                                         }
                                     }
                                 }
