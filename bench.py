@@ -25,6 +25,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner (printed at NCCL_DEBUG=VERSION and above) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "Mrays/s (Balls stand-in 800x800, 16 spp, shadows + reflection depth 3)"
 FLOPS_PER_TEST = 42  # minimal ray-dependent restatement of raytracing.cpp:111-151, FMA = 2
@@ -249,7 +252,10 @@ def main():
         trace_rays = (counts[0] + counts[2]) / world                                        # per GPU
         ach = FLOPS_PER_TEST * trace_rays * ntri / (kinds[0] * 1e-3) / 1e12 if kinds[0] > 0 else 0.0
         roof = {"bound": "fp32", "kernel": "k_trace (nearest-hit scan, all bounce levels)", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ach / fp32_peak, "traffic": None, "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
+                "frac": ach / fp32_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the frame's largest k_trace launch (8.39 M primary rays), one
+                # `ncu --set full` capture of this command (profiles/r1b_k_trace_primary_full.txt); only meaningful for the default workload
+                "traffic": 592.2e6 if args.workload == "balls" and world == 1 else None, "traffic_unit": "B per launch (primary scan, chunk 0)", "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
                 "frac_at_measured_clock": (ach / (fp32_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])) if clocks.get("sm_mhz") else None,
                 "frame_achieved": FLOPS_PER_TEST * rays * ntri / world / (ms_dev * 1e-3) / 1e12,
                 "ms_by_kernel": dict(zip(["k_trace", "k_shadow", "k_shade", "k_resolve", "gather"], [float(x) for x in kinds]))}

@@ -29,6 +29,8 @@ constexpr int kWarps = 8;          // all warps are consumers; the last warp to 
 constexpr int kThreads = kWarps * 32;
 constexpr uint32_t kTileBytes = kTile * kRecVec * sizeof(float4);
 constexpr int kMaxParts = 64;      // a launch with few rays splits the triangle range into <= kMaxParts parts per ray chunk
+constexpr uint32_t kItemsPerCta = 24;   // load-balance target of make_split
+constexpr uint32_t kMinPartTiles = 8;   // >= 1024 triangles per part unless the launch is tiny
 constexpr int kPadTiles = kMaxParts;  // "never" tiles appended to the record array so that every part has the same length
 constexpr unsigned long long kKeyEmpty = ~0ull;  // (distance bits << 32 | primitive id); all ones = no hit yet
 
@@ -179,10 +181,15 @@ __device__ __forceinline__ Split make_split(uint32_t count, uint32_t per_chunk, 
     Split sp;
     sp.nchunks = (count + per_chunk - 1) / per_chunk;
     uint32_t parts = 1;
-    if (allow_split && sp.nchunks > 0 && sp.nchunks < gridDim.x) {
-        parts = (gridDim.x + sp.nchunks - 1) / sp.nchunks;
+    if (allow_split && sp.nchunks > 0 && sp.nchunks < kItemsPerCta * gridDim.x) {
+        // aim at >= kItemsPerCta items per CTA so that the last (partial) round of the static item striding costs
+        // a few per cent at most, but keep >= kMinPartTiles tiles per part to amortise the per-item ray set-up;
+        // a launch with fewer chunks than CTAs is always split as far as the tiles allow
+        parts = (kItemsPerCta * gridDim.x + sp.nchunks - 1) / sp.nchunks;
+        const uint32_t cap = (sp.nchunks < gridDim.x) ? (uint32_t)ntiles : ((uint32_t)ntiles + kMinPartTiles - 1) / kMinPartTiles;
+        if (parts > cap) parts = cap;
         if (parts > (uint32_t)kMaxParts) parts = kMaxParts;
-        if (parts > (uint32_t)ntiles) parts = ntiles;
+        if (parts < 1) parts = 1;
     }
     sp.len = ((uint32_t)ntiles + parts - 1) / parts;
     sp.parts = ((uint32_t)ntiles + sp.len - 1) / sp.len;   // no empty part

@@ -1,0 +1,55 @@
+"""The C++ drop-in (raytracert_b200/host/main.cpp: the reference's skeleton without GLUT) end to end on the GPU:
+OBJ/MTL load -> rt_upload_scene -> 'r' key -> rt_render -> Image::writeImage, compared with the PPM the
+unmodified reference would have written for the same scene, camera and keys (fixture quirks_72_pf2)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, load_case
+
+pytestmark = pytest.mark.gpu
+APP = os.path.join(ROOT, "raytracert_b200", "_build", "rt_main")
+
+
+def read_ppm(path):
+    raw = open(path, "rb").read()
+    assert raw[:3] == b"P6\n"
+    parts = raw.split(b"\n", 3)
+    w, h = (int(x) for x in parts[1].split())
+    assert parts[2] == b"255"
+    return np.frombuffer(parts[3], np.uint8).reshape(h, w, 3)
+
+
+def run_app(tmp_path, *args):
+    if not os.path.exists(APP):
+        subprocess.run(["make", "-C", ROOT, "app"], check=True, stdout=subprocess.DEVNULL)
+    out = str(tmp_path / "result.ppm")
+    r = subprocess.run([APP, os.path.join(GOLDEN, "obj", "quirks.obj"), "--out", out, *args], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:]
+    return read_ppm(out), r.stdout
+
+
+def test_app_writes_the_reference_image(built, tmp_path):
+    c = load_case("quirks_72_pf2")
+    img, log = run_app(tmp_path, "--size", "72x72", "--pf", "2", "--lvl", "6", "--eye", "3.4,3.0,4.6", "--center", "0.4,0.2,0.2",
+                       "--light", "3,5,4")
+    assert img.shape == c["u8"].shape
+    d = np.abs(img.astype(int) - c["u8"].astype(int))
+    assert d.max() <= 1 and np.mean(np.any(d > 0, axis=2)) <= 0.01
+    assert "Raytracing" in log and "Mrays/s" in log
+
+
+def test_app_key_replay_toggles(built, tmp_path, port):
+    """--keys replays the reference's key presses: '5' toggles shadows off, '4' reflection off, then 'r' renders."""
+    from conftest import load_scene
+    from raytracert_b200 import host
+    img, _ = run_app(tmp_path, "--size", "64x48", "--pf", "1", "--lvl", "6", "--eye", "3.4,3.0,4.6", "--center", "0.4,0.2,0.2",
+                     "--light", "3,5,4", "--keys", "54r")
+    cam = host.Camera(64, 48, (3.4, 3.0, 4.6), (0.4, 0.2, 0.2))
+    port.set_scene(load_scene("quirks"))
+    port.configure(cam.eye, [(3, 5, 4)], 63 & ~16 & ~8, 6)
+    rgb, _, _ = port.render(cam.corners, 64, 48, 1, 1)
+    d = np.abs(img.astype(int) - port.quantise(rgb).astype(int))
+    assert d.max() <= 1
