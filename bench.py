@@ -228,16 +228,28 @@ def main():
     st = R.stats()
     # end-to-end through the public API with host buffers (scene H2D + frame + framebuffer D2H every step)
     e2e_steps = [frame_ms(e2e=True) for _ in range(max(3, min(args.steps, 5)))]
+    fb_brute = fb_host.copy()
+    # opt-in extra (not the contract path): conservative tile culling, same image bit for bit, reported separately
+    R.set_option(binding.RT_OPT_TILE_CULLING, 1)
+    for _ in range(3):
+        frame_ms()
+    barrier()
+    cull_steps = [frame_ms() for _ in range(max(3, min(args.steps, 10)))]
+    barrier()
+    R.download_into(fb_host)
+    cull_identical = bool(np.array_equal(fb_host.view(np.uint32), fb_brute.view(np.uint32)))
+    R.set_option(binding.RT_OPT_TILE_CULLING, 0)
 
     ms_dev = float(np.mean(per_step))
     ms_e2e = float(np.mean(e2e_steps))
+    ms_cull = float(np.mean(cull_steps))
     counts = np.array([st["primary_rays"], st["shadow_rays"], st["bounce_rays"], st["exact_evals"]], np.float64)
     kinds = np.array([st["ms_trace"], st["ms_shadow"], st["ms_shade"], st["ms_resolve"], st["ms_gather"]], np.float64)
     if world > 1:
         import torch.distributed as td
-        t = torch.tensor([ms_dev, ms_e2e] + list(kinds), dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([ms_dev, ms_e2e, ms_cull] + list(kinds), dtype=torch.float64, device=f"cuda:{local}")
         td.all_reduce(t, op=td.ReduceOp.MAX)
-        ms_dev, ms_e2e, kinds = float(t[0]), float(t[1]), t[2:].cpu().numpy()
+        ms_dev, ms_e2e, ms_cull, kinds = float(t[0]), float(t[1]), float(t[2]), t[3:].cpu().numpy()
         c = torch.tensor(counts, dtype=torch.float64, device=f"cuda:{local}")
         td.all_reduce(c, op=td.ReduceOp.SUM)
         counts = c.cpu().numpy()
@@ -271,6 +283,8 @@ def main():
                         "h2d_bytes_per_step": int(ntri * (4 * 16 + 4) + scene.materials.shape[0] * 64 + 432), "d2h_bytes_per_step": int(fb_host.nbytes),
                         "path": "rt_upload_scene + rt_render + rt_download_framebuffer with host buffers, every step"},
                 "gpu_launches": int(st["n_launches"]) * args.steps,
+                "accelerated": {"option": "RT_OPT_TILE_CULLING (opt-in; not the brute-force contract path, not used for value/e2e/roofline)",
+                                "ms_per_step": ms_cull, "value": rays / ms_cull / 1e3, "unit": "Mrays/s", "image_bit_identical_to_brute_force": cull_identical},
                 "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1

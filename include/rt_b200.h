@@ -144,6 +144,15 @@ int rt_download_framebuffer_u8(uint8_t* rgb8);
 int rt_trace(const rt_params* params, int n, const float* origins, const float* dests, float* rgb,
              int32_t* prim_id, float* hit);
 
+/* Options (rt_set_option; they persist until rt_shutdown).
+ * RT_OPT_TILE_CULLING (default 0): 1 = conservative tile culling.  Triangles are scanned in tiles of 128; with this
+ *   option a warp skips a tile when none of its rays can reach the bounding box of the tile's (tolerance-dilated)
+ *   triangles.  The image and the primitive ids are IDENTICAL to the brute-force scan (same filter + exact tiers on every
+ *   tile that is not skipped) -- it only stops being the O(rays x triangles) loop of the reference
+ *   (raytracing.cpp:174-189), which is why it is opt-in and reported separately by bench.py. */
+#define RT_OPT_TILE_CULLING 1
+int rt_set_option(int option, int value);
+
 int rt_get_stats(rt_stats* out);
 
 /* Device-side timing on the library's own stream (CUDA events): slots 0..15. */

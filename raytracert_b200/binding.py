@@ -14,6 +14,7 @@ from . import BUILD_DIR
 RT_AMBIENT, RT_DIFFUSE, RT_SPECULAR, RT_REFLECTION, RT_SHADOWS, RT_REFRACTION = 1, 2, 4, 8, 16, 32
 RT_ALL_FEATURES = 63
 RT_MAX_LIGHTS = 16
+RT_OPT_TILE_CULLING = 1
 
 
 class RtMaterial(C.Structure):
@@ -47,7 +48,7 @@ class RtStats(C.Structure):
 
 
 EXPORTS = ["rt_init", "rt_init_rank", "rt_nccl_unique_id", "rt_upload_scene", "rt_render", "rt_render_async",
-           "rt_sync", "rt_download_framebuffer", "rt_download_framebuffer_u8", "rt_trace", "rt_get_stats",
+           "rt_sync", "rt_download_framebuffer", "rt_download_framebuffer_u8", "rt_trace", "rt_get_stats", "rt_set_option",
            "rt_event_record", "rt_event_elapsed_ms", "rt_last_error", "rt_shutdown"]
 
 _LIB = None
@@ -76,6 +77,7 @@ def lib():
         L.rt_download_framebuffer_u8.argtypes = [C.c_void_p]
         L.rt_trace.argtypes = [C.POINTER(RtParams), C.c_int] + [C.c_void_p] * 5
         L.rt_get_stats.argtypes = [C.POINTER(RtStats)]
+        L.rt_set_option.argtypes = [C.c_int, C.c_int]
         L.rt_event_record.argtypes = [C.c_int]
         L.rt_event_elapsed_ms.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.rt_shutdown.restype = None
@@ -197,6 +199,9 @@ class Renderer:
         hit = np.zeros((n, 3), np.float32)
         _check(self.L.rt_trace(C.byref(params), n, o.ctypes.data, d.ctypes.data, rgb.ctypes.data, prim.ctypes.data, hit.ctypes.data))
         return rgb, prim, hit
+
+    def set_option(self, option, value):
+        _check(self.L.rt_set_option(int(option), int(value)))
 
     def stats(self):
         st = RtStats()

@@ -66,7 +66,8 @@ struct RtDevice {
     cudaStream_t stream = nullptr;
     ncclComm_t comm = nullptr;
     // scene
-    float4 *rec = nullptr, *triv = nullptr, *normal_mat = nullptr, *materials = nullptr, *spheres = nullptr;
+    float4 *rec = nullptr, *triv = nullptr, *normal_mat = nullptr, *materials = nullptr, *spheres = nullptr, *tile_box = nullptr;
+    size_t cap_box = 0;
     size_t cap_rec = 0, cap_triv = 0, cap_nm = 0, cap_mat = 0, cap_sph = 0;  // in float4; buffers are reused across uploads
     int ntri = 0, ntiles = 0, nmat = 0, nspheres = 0;
     float M_built = 0.f;
@@ -101,6 +102,7 @@ struct Global {
     bool scene_ready = false, frame_ready = false;
     NcclApi nccl;
     ScanConfig scan = {2, 8, 2};
+    bool tile_culling = false;       // RT_OPT_TILE_CULLING
     float cos_min = kCosMinDefault;  // grazing threshold of the filter (RT_B200_COSMIN overrides, for experiments)
     float scene_extent = 0.f;   // max |coordinate| over the scene
     bool any_transparent = false;
@@ -158,7 +160,7 @@ int create_device(RtDevice& d, int device, int rank) {
 void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
-    void* ptrs[] = {d.rec, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+    void* ptrs[] = {d.rec, d.tile_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
                     d.q_hit, d.key, d.hit0, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -213,6 +215,7 @@ void read_tuning_env() {
         const float v = (float)atof(c);
         if (v >= 1e-6f && v <= 0.1f) g.cos_min = v;
     }
+    if (const char* c = getenv("RT_B200_CULL")) g.tile_culling = atoi(c) != 0;   // same as rt_set_option(RT_OPT_TILE_CULLING, ..)
     const char* e = getenv("RT_B200_TUNE");
     if (!e) return;
     ScanConfig c = g.scan;
@@ -237,6 +240,8 @@ int build_records(RtDevice& d, float M) {
     CU(cudaSetDevice(d.device));
     const int npad = (d.ntiles + kPadTiles) * kTile;
     k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.ntri, npad, M, g.cos_min, d.rec);
+    const int tiles_padded = d.ntiles + kPadTiles;
+    k_build_tile_boxes<<<(tiles_padded + 127) / 128, 128, 0, d.stream>>>(d.triv, d.rec, d.ntri, tiles_padded, M, d.tile_box);
     CU(cudaGetLastError());
     d.M_built = M;
     return RT_OK;
@@ -275,6 +280,7 @@ void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float e
     P.ntri = d.ntri; P.ntiles = d.ntiles; P.nspheres = d.nspheres;
     P.ray_o = d.ray_o; P.ray_d = d.ray_d; P.thr = d.thr; P.acc = d.acc; P.hit = d.hit; P.lit = d.lit;
     P.q_ray = d.q_ray; P.q_hit = d.q_hit; P.counters = counters; P.key = d.key;
+    P.tile_box = d.tile_box; P.cull = g.tile_culling ? 1 : 0;
     P.eps_r = eps_r;
     memcpy(P.camera, rp.camera, sizeof(P.camera));
     P.nlights = (int)rp.n_lights;
@@ -348,7 +354,8 @@ int render_enqueue(const rt_params* rp) {
     const float eps_r = eps_r_for(M);
     const size_t row_samples = (size_t)W * spp;
     if (row_samples > kMaxChunkSamples * 4ull) return fail(RT_ERR_INVALID, "one row of samples (%zu) is too large", row_samples);
-    const uint32_t rows_per_chunk = (uint32_t)std::max<size_t>(1, kMaxChunkSamples / row_samples);
+    uint32_t rows_per_chunk = (uint32_t)std::max<size_t>(1, kMaxChunkSamples / row_samples);
+    if (rows_per_chunk >= 8) rows_per_chunk &= ~7u;   // whole 8x8-pixel blocks per chunk (slot_to_sample)
 
     for (RtDevice& d : g.devs) {
         CU(cudaSetDevice(d.device));
@@ -380,6 +387,8 @@ int render_enqueue(const rt_params* rp) {
             P.nrows = std::min(rows_per_chunk, my_rows - P.row0);
             P.G = G; P.rank = (uint32_t)d.rank;
             P.nsamples = (uint32_t)(P.nrows * row_samples);
+            P.tiles_x = (W + 7) / 8;
+            P.nslots = P.tiles_x * ((P.nrows + 7) / 8) * 64u * spp;
             P.sample_base = (uint32_t)(P.row0 * row_samples);
             P.prim_out = rp->want_prim_id ? d.prim : nullptr;
             int levels = run_wavefront(d, P);
@@ -490,6 +499,7 @@ void rt_shutdown(void) {
     g.devs.clear();
     g.world = 0;
     g.scene_ready = g.frame_ready = false;
+    g.tile_culling = false;
 }
 
 int rt_init(int n_gpus) {
@@ -602,6 +612,7 @@ int rt_upload_scene(const rt_scene* sc) {
         d.M_built = 0.f;
         // grow-only device buffers: re-uploading a scene of the same size allocates nothing
         rc = ensure(d.rec, d.cap_rec, (size_t)(d.ntiles + kPadTiles) * kTile * kRecVec); if (rc) return rc;
+        rc = ensure(d.tile_box, d.cap_box, (size_t)(d.ntiles + kPadTiles) * 2); if (rc) return rc;
         rc = ensure(d.triv, d.cap_triv, triv.size()); if (rc) return rc;
         rc = ensure(d.normal_mat, d.cap_nm, nm.size()); if (rc) return rc;
         rc = ensure(d.materials, d.cap_mat, (size_t)4 * sc->n_materials); if (rc) return rc;
@@ -717,6 +728,7 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     fill_common(P, d, *rp, eps_r_for(M), d.counters);
     P.trace_api = 1;
     P.nsamples = (uint32_t)n;
+    P.nslots = (uint32_t)n;
     P.G = 1;
     // the level-0 hit records are copied aside on the device before the bounces overwrite them
     std::vector<float4> hh;
@@ -739,6 +751,11 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
         if (hit) { hit[3 * i] = hh[i].x; hit[3 * i + 1] = hh[i].y; hit[3 * i + 2] = hh[i].z; }
     }
     return RT_OK;
+}
+
+int rt_set_option(int option, int value) {
+    if (option == RT_OPT_TILE_CULLING) { g.tile_culling = value != 0; return RT_OK; }
+    return fail(RT_ERR_INVALID, "unknown option %d", option);
 }
 
 int rt_get_stats(rt_stats* out) {

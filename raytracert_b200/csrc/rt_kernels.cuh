@@ -63,6 +63,8 @@ struct FrameParams {
     uint32_t* q_hit;
     uint32_t* counters;
     unsigned long long* key;    // per sample: nearest (distance, triangle) found by the scan parts, merged with atomicMin
+    const float4* tile_box;     // 2 float4 per tile: conservative AABB (lo, hi) of the tile's candidate region
+    int cull;                   // RT_OPT_TILE_CULLING: warps skip tiles whose box none of their rays can reach
     int32_t* prim_out;          // optional: primary primitive id per local sample
     // frame
     float corners[24];
@@ -71,6 +73,8 @@ struct FrameParams {
     uint32_t row0, nrows;       // local rows of this chunk
     uint32_t G, rank;           // row interleave: global y = local_row * G + rank
     uint32_t nsamples;          // samples in this chunk
+    uint32_t nslots;            // primary work slots: samples in tiled order, padded to whole 8x8-pixel blocks (== nsamples for rt_trace)
+    uint32_t tiles_x;           // 8x8-pixel blocks per row of blocks
     uint32_t sample_base;       // local sample index of the chunk's first sample
     float eps_r;                // distance guard band of the filter
     float camera[3];
@@ -145,6 +149,58 @@ __global__ void k_build_records(const float4* __restrict__ triv, int ntri, int n
         }
     }
     rec[4 * i] = q0; rec[4 * i + 1] = q1; rec[4 * i + 2] = q2; rec[4 * i + 3] = q3;
+}
+
+// Conservative bounding box of everything a tile can make a hit of (RT_OPT_TILE_CULLING).
+// A hit accepted by the exact path has its point I within 8uM of the ray, within 4uM of the triangle's plane and,
+// because the reference's own barycentrics are off by at most E0 (DESIGN.md "filter soundness"), inside the triangle
+// dilated by E0 in barycentric units, i.e. by <= 3*E0*diameter.  So a ray that misses the box of the dilated
+// triangles (+ rounding slack) cannot hit any of them.  E0 is read back from the record (c1 = 1 + 3*E0).
+// A tile holding an "always exact" triangle (bmin = +inf: the bound does not exist) is unbounded and never skipped;
+// "never" records (degenerate, padding) contribute nothing.
+__global__ void k_build_tile_boxes(const float4* __restrict__ triv, const float4* __restrict__ rec, int ntri, int ntiles_padded, float M,
+                                   float4* __restrict__ tile_box) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= ntiles_padded) return;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    bool unbounded = false;
+    for (int j = 0; j < kTile; ++j) {
+        const int i = tile * kTile + j;
+        if (i >= ntri) break;
+        const float4 q3 = rec[4 * i + 3];
+        if (q3.z < 0.0f) continue;                          // never a candidate
+        if (!(q3.z < inf)) { unbounded = true; break; }     // always exact
+        const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
+        const float e0 = fmaxf(q3.x - 1.0f, 0.0f) * (1.0f / 3.0f) + 1e-6f;
+        const float ab = sqrtf((B.x - A.x) * (B.x - A.x) + (B.y - A.y) * (B.y - A.y) + (B.z - A.z) * (B.z - A.z));
+        const float ac = sqrtf((C.x - A.x) * (C.x - A.x) + (C.y - A.y) * (C.y - A.y) + (C.z - A.z) * (C.z - A.z));
+        const float bc = sqrtf((C.x - B.x) * (C.x - B.x) + (C.y - B.y) * (C.y - B.y) + (C.z - B.z) * (C.z - B.z));
+        const float m = 4.0f * e0 * fmaxf(ab, fmaxf(ac, bc)) + M * 6.103515625e-5f;   // dilation (x4/3 slack) + 2^-14 M >> 12uM
+        const float4 v[3] = {A, B, C};
+        for (int k = 0; k < 3; ++k) {
+            const float c[3] = {v[k].x, v[k].y, v[k].z};
+            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], c[a] - m); hi[a] = fmaxf(hi[a], c[a] + m); }
+        }
+    }
+    if (unbounded) { for (int a = 0; a < 3; ++a) { lo[a] = -inf; hi[a] = inf; } }
+    // an empty tile keeps lo = +inf, hi = -inf: no ray reaches it
+    tile_box[2 * tile] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    tile_box[2 * tile + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+}
+
+// Slab test of the half-line O' + t d, 0 <= t < rhi, against a box.  NaN-safe in the conservative direction:
+// fminf/fmaxf drop NaN operands (0 * inf on a slab boundary), and a ray whose direction is NaN (dead slot) is
+// filtered by the caller's live mask.
+__device__ __forceinline__ bool ray_reaches_box(float ox, float oy, float oz, float dx, float dy, float dz, float rhi, const float4& lo, const float4& hi) {
+    const float ix = rcp_approx(dx), iy = rcp_approx(dy), iz = rcp_approx(dz);
+    const float x1 = (lo.x - ox) * ix, x2 = (hi.x - ox) * ix;
+    const float y1 = (lo.y - oy) * iy, y2 = (hi.y - oy) * iy;
+    const float z1 = (lo.z - oz) * iz, z2 = (hi.z - oz) * iz;
+    const float tmin = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), 0.0f));
+    const float tmax = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), rhi));
+    // relative slack for the approximate reciprocals / products (the box already carries an absolute margin)
+    return !(tmin > tmax * 1.0001f + 1e-30f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -343,13 +399,29 @@ struct BitLayout {
 // clears the ray's live bit on the first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
 template <int RP, int J, bool NEAREST, class Fetch>
 __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
-                                          const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact, int tile_begin) {
+                                          const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact, int tile_begin,
+                                          const float4* __restrict__ tile_box) {
     constexpr int R = 2 * RP;
     constexpr uint32_t REP = BitLayout<RP, J>::kRep;
     for (int tile = tile_begin; tile < tile_begin + (int)pipe.len; ++tile) {
         const float4* rec = pipe_acquire(pipe);
-        // warp-level early exit (shadow rays): nothing left to decide for any lane of this warp
-        if (!__all_sync(0xffffffffu, live == 0u)) {
+        // does any live ray of this warp reach the tile?  (always, without tile culling)
+        bool need = live != 0u;
+        if (tile_box != nullptr && need) {
+            const float4 lo = __ldg(&tile_box[2 * tile]), hi = __ldg(&tile_box[2 * tile + 1]);
+            need = false;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int p = k / 2;
+                const bool odd = k & 1;
+                const bool reach = ray_reaches_box(odd ? fr.ox[p].y : fr.ox[p].x, odd ? fr.oy[p].y : fr.oy[p].x, odd ? fr.oz[p].y : fr.oz[p].x,
+                                                   odd ? fr.dx[p].y : fr.dx[p].x, odd ? fr.dy[p].y : fr.dy[p].x, odd ? fr.dz[p].y : fr.dz[p].x,
+                                                   __uint_as_float(fr.rhi[k]), lo, hi);
+                need = need || (reach && ((live >> k) & 1u));
+            }
+        }
+        // warp-level early exit: shadow rays that all found their occluder, or a tile no ray of the warp can reach
+        if (__any_sync(0xffffffffu, need)) {
             const int tri0 = tile * kTile;
 #pragma unroll 1
             for (int jb = 0; jb < kTile; jb += J) {
@@ -430,6 +502,24 @@ __device__ __forceinline__ v3 lerp_corner(const float* c, int off, float xs, flo
     return e_add(top, bot);
 }
 
+// Primary work order.  Slot i -> sample: pixels are visited in 8x8 blocks (Morton order inside a block, blocks row-major),
+// the sub-samples of a pixel innermost, so that every warp / CTA / chunk of consecutive slots -- and, through the
+// compaction order, of secondary rays -- covers a compact screen region (coherent rays make the shadow early-exit and
+// tile culling effective).  Slots of a partial block that fall outside the chunk's pixels are invalid.
+__device__ __forceinline__ bool slot_to_sample(const FrameParams& P, uint32_t slot, uint32_t& s) {
+    if (P.trace_api) { s = slot; return slot < P.nsamples; }
+    const uint32_t spp = P.pfx * P.pfy;
+    const uint32_t t = slot / spp, sub = slot - t * spp;
+    const uint32_t blk = t >> 6, m = t & 63u;
+    const uint32_t by = blk / P.tiles_x, bx = blk - by * P.tiles_x;
+    // Morton decode of 6 bits: x = bits 0,2,4   y = bits 1,3,5
+    const uint32_t mx = (m & 1u) | ((m >> 1) & 2u) | ((m >> 2) & 4u);
+    const uint32_t my = ((m >> 1) & 1u) | ((m >> 2) & 2u) | ((m >> 3) & 4u);
+    const uint32_t x = bx * 8u + mx, ry = by * 8u + my;
+    s = (ry * P.W + x) * spp + sub;
+    return x < P.W && ry < P.nrows;
+}
+
 __device__ __forceinline__ void primary_ray(const FrameParams& P, uint32_t s, v3& O, v3& D) {
     const uint32_t spp = P.pfx * P.pfy;
     const uint32_t pix = s / spp, sub = s - pix * spp;
@@ -465,7 +555,7 @@ template <int RP, int J, int MINB, bool PRIMARY>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant__ FrameParams P, int level) {
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
-    const uint32_t count = PRIMARY ? P.nsamples : P.counters[kCntRay + level];
+    const uint32_t count = PRIMARY ? P.nslots : P.counters[kCntRay + level];
     const uint32_t per_chunk = kThreads * R;
     const Split sp = make_split(count, per_chunk, P.ntiles, true);
     Pipe pipe;
@@ -482,13 +572,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
         uint32_t live = 0;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            const uint32_t ray = chunk * per_chunk + k * kThreads + threadIdx.x;
-            const bool ok = ray < count;
+            // a thread's R rays are consecutive slots (neighbouring sub-samples / pixels)
+            const uint32_t ray = chunk * per_chunk + threadIdx.x * R + k;
+            bool ok = ray < count;
             v3 O = mk3(0, 0, 0), D = mk3(0, 0, 1);
             uint32_t s = 0;
+            if (PRIMARY && ok) ok = slot_to_sample(P, ray, s);
             if (ok) {
                 if (PRIMARY && !P.trace_api) {
-                    s = ray;
                     primary_ray(P, s, O, D);
                     if (part == 0) {  // every part regenerates the ray (cheap); one of them publishes it
                         P.ray_o[s] = make_float4(O.x, O.y, O.z, 0.f);
@@ -497,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
                         P.acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 } else {
-                    s = PRIMARY ? ray : P.q_ray[ray];
+                    if (!PRIMARY) s = P.q_ray[ray];
                     const float4 o = P.ray_o[s], d = P.ray_d[s];
                     O = mk3(o); D = mk3(d);
                 }
@@ -513,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
             if (PRIMARY && !P.trace_api) { primary_ray(P, sid[k], O, D); }
             else { const float4 o = P.ray_o[sid[k]], d = P.ray_d[sid[k]]; O = mk3(o); D = mk3(d); }
         };
-        scan_pass<RP, J, true>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len));
+        scan_pass<RP, J, true>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr);
 
         // merge: (distance bits, triangle id) -- the smallest distance wins, equal distances go to the lowest
         // index, which is exactly the sequential rule of intersectMesh (strict <, raytracing.cpp:183)
@@ -532,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 template <bool PRIMARY>
 __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FrameParams P, int level) {
-    const uint32_t count = PRIMARY ? P.nsamples : P.counters[kCntRay + level];
+    const uint32_t count = PRIMARY ? P.nslots : P.counters[kCntRay + level];
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounds = (count + stride - 1) / stride;
     const uint32_t all_lit = (P.nlights >= 32) ? 0xffffffffu : ((1u << P.nlights) - 1u);
@@ -540,8 +631,9 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FramePar
         const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
         bool hit_any = false;
         uint32_t s = 0;
-        if (i < count) {
-            s = PRIMARY ? i : P.q_ray[i];
+        bool ok = i < count;
+        if (ok) { if (PRIMARY) ok = slot_to_sample(P, i, s); else s = P.q_ray[i]; }
+        if (ok) {
             const unsigned long long key = P.key[s];
             P.key[s] = kKeyEmpty;  // ready for the next level / frame
             int idx = (key == kKeyEmpty) ? -1 : (int)(unsigned int)(key & 0xffffffffull);
@@ -611,7 +703,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
         uint32_t live = 0;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            const uint32_t ray = chunk * per_chunk + k * kThreads + threadIdx.x;
+            const uint32_t ray = chunk * per_chunk + threadIdx.x * R + k;
             const bool ok = ray < count;
             v3 O = mk3(0, 0, 0), D = mk3(0, 0, 1);
             sid[k] = 0; lid[k] = 0; light[k] = D;
@@ -630,7 +722,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
         }
         const uint32_t valid = live;
         FetchShadow fetch{P.hit, sid, light};
-        scan_pass<RP, J, NEAREST>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len));
+        scan_pass<RP, J, NEAREST>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr);
 
 #pragma unroll
         for (int k = 0; k < R; ++k) {

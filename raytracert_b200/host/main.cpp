@@ -6,7 +6,7 @@
 // -> Image -> writeImage("result.ppm").
 //
 //   rt_main [scene.obj] [--size WxH] [--pf N] [--lvl N] [--eye x,y,z --center x,y,z] [--light x,y,z]...
-//           [--sphere cx,cy,cz,r,material_index]... [--gpus N] [--out result.ppm] [--keys STRING]
+//           [--sphere cx,cy,cz,r,material_index]... [--gpus N] [--cull] [--out result.ppm] [--keys STRING]
 //
 // --keys replays key presses in order (default "r"); e.g. --keys "5r" renders with shadows toggled off,
 // "Lr" adds a light at the camera first.  Without --eye the camera is the reference's start-up pose:
@@ -101,7 +101,7 @@ static bool parse_floats(const char* s, float* out, int n) {
 int main(int argc, char** argv) {
     std::string scene = "cube.obj", keys = "r";
     float eye[3], center[3] = {0, 0, 0};
-    bool have_eye = false;
+    bool have_eye = false, cull = false;
     std::vector<Vec3Df> lights;
     struct SphereArg { float v[5]; };
     std::vector<SphereArg> spheres;
@@ -119,6 +119,7 @@ int main(int argc, char** argv) {
         else if (a == "--light") { float l[3]; if (!parse_floats(next("--light"), l, 3)) return 2; lights.push_back(Vec3Df(l[0], l[1], l[2])); }
         else if (a == "--sphere") { SphereArg s; if (!parse_floats(next("--sphere"), s.v, 5)) return 2; spheres.push_back(s); }
         else if (a == "--gpus") { RtGpuCount = atoi(next("--gpus")); }
+        else if (a == "--cull") { cull = true; }
         else if (a == "--out") { g_out = next("--out"); }
         else if (a == "--keys") { keys = next("--keys"); }
         else if (a[0] == '-') { printf("unknown option %s\n", a.c_str()); return 2; }
@@ -140,6 +141,7 @@ int main(int argc, char** argv) {
     name.push_back(0);
     init(name.data());  // main.cpp:258
     if (MyMesh.triangles.empty() && spheres.empty()) { printf("no geometry loaded from %s\n", scene.c_str()); return 1; }
+    if (cull && rt_set_option(RT_OPT_TILE_CULLING, 1) != RT_OK) { printf("%s\n", rt_last_error()); return 1; }  // same image, fewer tests
     if (!lights.empty()) MyLightPositions = lights;  // replaces the start-up light at the eye
     if (!spheres.empty()) {
         for (const SphereArg& s : spheres) {

@@ -250,3 +250,28 @@ def test_full_size_C3_dodge(gpu, port):
     s = load_scene("dodge")
     cam = host.Camera(1920, 1080, (.75, .55, 1.1), (.07, 0, .23))
     _full_size_checks(gpu, port, s, cam, 4, 10, [cam.eye], rows=[540])
+
+
+def test_tile_culling_is_invisible(gpu, port):
+    """RT_OPT_TILE_CULLING skips tiles no ray of a warp can reach; ids, float RGB bits and ray counts must not change."""
+    from raytracert_b200 import binding, host, scenes
+    cases = [load_case(n) for n in ("glass_56_lvl6", "dodge_32x18_pf2_lvl2", "quirks_72_pf2", "shadow_test_2lights_lvl3", "room_64_pf2_lvl4")]
+    big = scenes.balls_standin()
+    cam = host.Camera(200, 160, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0))
+    cases.append(dict(scene=None, corners=cam.corners, W=200, H=160, pfx=2, pfy=2, max_lvl=3, features=63, eye=cam.eye, lights=[(2.5, 4.0, 3.0)]))
+    try:
+        for c in cases:
+            s = big if c["scene"] is None else load_scene(c["scene"])
+            gpu.set_option(binding.RT_OPT_TILE_CULLING, 0)
+            rgb0, prim0 = gpu_render(gpu, s, c)
+            st0 = gpu.stats()
+            gpu.set_option(binding.RT_OPT_TILE_CULLING, 1)
+            rgb1, prim1 = gpu_render(gpu, s, c)
+            st1 = gpu.stats()
+            assert np.array_equal(prim0, prim1)
+            assert np.array_equal(bits(rgb0), bits(rgb1))
+            for k in ("primary_rays", "shadow_rays", "bounce_rays"):
+                assert st0[k] == st1[k]
+            assert st1["exact_evals"] <= st0["exact_evals"]
+    finally:
+        gpu.set_option(binding.RT_OPT_TILE_CULLING, 0)
