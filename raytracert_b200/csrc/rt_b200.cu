@@ -22,7 +22,7 @@ using namespace rt;
 // Scan-kernel shapes compiled into the library: (ray pairs per thread, triangles per filter block,
 // resident CTAs per SM).  The first entry is the default; RT_B200_TUNE="rp,j,minb" selects another
 // (tools/tune.py sweeps them on the GPU).
-#define RT_SCAN_CONFIGS(X) X(2, 8, 2) X(2, 8, 3) X(1, 8, 4) X(1, 16, 4) X(1, 8, 3) X(1, 16, 3) X(1, 8, 5) X(1, 16, 5) X(2, 4, 2) X(2, 4, 3)
+#define RT_SCAN_CONFIGS(X) X(2, 8, 2) X(2, 4, 2) X(1, 8, 4) X(1, 16, 4)
 struct ScanConfig { int rp, j, minb; };
 constexpr uint32_t kMaxChunkSamples = 1u << 23;  // 8 Mi samples per wavefront chunk (84 B of state each)
 
@@ -70,6 +70,9 @@ struct RtDevice {
     size_t cap_box = 0;
     size_t cap_rec = 0, cap_triv = 0, cap_nm = 0, cap_mat = 0, cap_sph = 0;  // in float4; buffers are reused across uploads
     int ntri = 0, ntiles = 0, nmat = 0, nspheres = 0;
+    int cls1 = 0, cls2 = 0;             // first tile of dominant-axis class 1 / 2
+    uint32_t* perm = nullptr;           // record position -> triangle id (kNoTriangle = padding)
+    size_t cap_perm = 0;
     float M_built = 0.f;
     // per-chunk state
     size_t cap_samples = 0;
@@ -160,7 +163,7 @@ int create_device(RtDevice& d, int device, int rank) {
 void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
-    void* ptrs[] = {d.rec, d.tile_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+    void* ptrs[] = {d.rec, d.perm, d.tile_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
                     d.q_hit, d.key, d.hit0, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -239,9 +242,9 @@ int build_records(RtDevice& d, float M) {
     if (d.M_built >= M && d.rec) return RT_OK;
     CU(cudaSetDevice(d.device));
     const int npad = (d.ntiles + kPadTiles) * kTile;
-    k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.ntri, npad, M, g.cos_min, d.rec);
+    k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.perm, npad, d.cls1 * kTile, d.cls2 * kTile, M, g.cos_min, d.rec);
     const int tiles_padded = d.ntiles + kPadTiles;
-    k_build_tile_boxes<<<(tiles_padded + 127) / 128, 128, 0, d.stream>>>(d.triv, d.rec, d.ntri, tiles_padded, M, d.tile_box);
+    k_build_tile_boxes<<<(tiles_padded + 127) / 128, 128, 0, d.stream>>>(d.triv, d.rec, tiles_padded, M, d.tile_box);
     CU(cudaGetLastError());
     d.M_built = M;
     return RT_OK;
@@ -277,7 +280,7 @@ int ensure_counters(RtDevice& d, int slots) {
 void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float eps_r, uint32_t* counters) {
     memset(&P, 0, sizeof(P));
     P.rec = d.rec; P.triv = d.triv; P.normal_mat = d.normal_mat; P.materials = d.materials; P.spheres = d.spheres;
-    P.ntri = d.ntri; P.ntiles = d.ntiles; P.nspheres = d.nspheres;
+    P.ntri = d.ntri; P.ntiles = d.ntiles; P.nspheres = d.nspheres; P.cls1 = d.cls1; P.cls2 = d.cls2;
     P.ray_o = d.ray_o; P.ray_d = d.ray_d; P.thr = d.thr; P.acc = d.acc; P.hit = d.hit; P.lit = d.lit;
     P.q_ray = d.q_ray; P.q_hit = d.q_hit; P.counters = counters; P.key = d.key;
     P.tile_box = d.tile_box; P.cull = g.tile_culling ? 1 : 0;
@@ -588,6 +591,31 @@ int rt_upload_scene(const rt_scene* sc) {
         memcpy(&v.w, &sc->tri_material[i], 4);
         nm[i] = v;
     }
+    // group the triangles by the dominant axis of their plane normal (rt_kernels.cuh: 2-D projected filter); stable
+    // inside a class, every class padded to whole tiles
+    std::vector<uint32_t> perm;
+    int cls_tiles[3] = {0, 0, 0};
+    {
+        std::vector<uint8_t> cls(n);
+        size_t cnt[3] = {0, 0, 0};
+        for (uint32_t i = 0; i < n; ++i) {
+            const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i;
+            const double u[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]};
+            const double v[3] = {(double)C[0] - A[0], (double)C[1] - A[1], (double)C[2] - A[2]};
+            const double nx = std::fabs(u[1] * v[2] - u[2] * v[1]), ny = std::fabs(u[2] * v[0] - u[0] * v[2]), nz = std::fabs(u[0] * v[1] - u[1] * v[0]);
+            int w = 0;
+            if (ny > nx) w = 1;
+            if (nz > (w == 1 ? ny : nx)) w = 2;   // NaN compares false: non-finite triangles land in class 0 (and are "always exact")
+            cls[i] = (uint8_t)w;
+            ++cnt[w];
+        }
+        size_t start[3], total = 0;
+        for (int c = 0; c < 3; ++c) { start[c] = total; cls_tiles[c] = (int)((cnt[c] + kTile - 1) / kTile); total += (size_t)cls_tiles[c] * kTile; }
+        if (total == 0) { cls_tiles[0] = 1; total = kTile; }   // an empty scene still has one (padding) tile
+        perm.assign(total + (size_t)kPadTiles * kTile, kNoTriangle);
+        size_t fill[3] = {start[0], start[1], start[2]};
+        for (uint32_t i = 0; i < n; ++i) perm[fill[cls[i]]++] = i;
+    }
     std::vector<float4> sph((size_t)2 * std::max(sc->n_spheres, 1u));
     for (uint32_t i = 0; i < sc->n_spheres; ++i) {
         const rt_sphere& s = sc->spheres[i];
@@ -606,13 +634,17 @@ int rt_upload_scene(const rt_scene* sc) {
         CU(cudaSetDevice(d.device));
         CU(cudaStreamSynchronize(d.stream));
         d.ntri = (int)n;
-        d.ntiles = std::max(1, (int)((n + kTile - 1) / kTile));
+        d.ntiles = cls_tiles[0] + cls_tiles[1] + cls_tiles[2];
+        d.cls1 = cls_tiles[0];
+        d.cls2 = cls_tiles[0] + cls_tiles[1];
         d.nmat = (int)sc->n_materials;
         d.nspheres = (int)sc->n_spheres;
         d.M_built = 0.f;
         // grow-only device buffers: re-uploading a scene of the same size allocates nothing
         rc = ensure(d.rec, d.cap_rec, (size_t)(d.ntiles + kPadTiles) * kTile * kRecVec); if (rc) return rc;
         rc = ensure(d.tile_box, d.cap_box, (size_t)(d.ntiles + kPadTiles) * 2); if (rc) return rc;
+        rc = ensure(d.perm, d.cap_perm, perm.size()); if (rc) return rc;
+        CU(cudaMemcpyAsync(d.perm, perm.data(), sizeof(uint32_t) * perm.size(), cudaMemcpyHostToDevice, d.stream));
         rc = ensure(d.triv, d.cap_triv, triv.size()); if (rc) return rc;
         rc = ensure(d.normal_mat, d.cap_nm, nm.size()); if (rc) return rc;
         rc = ensure(d.materials, d.cap_mat, (size_t)4 * sc->n_materials); if (rc) return rc;

@@ -52,6 +52,7 @@ struct FrameParams {
     const float4* materials;    // 4 float4 per material: Kd|Ns, Ka|Ni, Ks|Tr, flags
     const float4* spheres;      // 2 float4 per sphere: center|radius, material bits
     int ntri, ntiles, nspheres;
+    int cls1, cls2;             // first tile of dominant-axis class 1 / class 2 (records are grouped by class)
     // per-sample state (chunk local)
     float4* ray_o;              // xyz origin
     float4* ray_d;              // xyz dest, w = lvl (bits)
@@ -88,23 +89,34 @@ struct FrameParams {
 // ------------------------------------------------------------------------------------------------
 // Filter records
 // ------------------------------------------------------------------------------------------------
-// Record of triangle i (4 float4):
-//   q0 = ( nx, ny, nz, dn )   unit plane normal, dn = -n.T0        -> aneg = n.O' + dn, b = n.d
-//   q1 = ( sx, sy, sz, ds')   s(P) = S.P + ds, ds' = ds + E0       (first barycentric of raytracing.cpp:144)
-//   q2 = ( tx, ty, tz, dt')   t(P) = T.P + dt, dt' = dt + E0       (second barycentric, :148)
-//   q3 = ( c1, -E1, bmin, 0 ) c1 = 1 + 3*E0
+// Triangles are grouped by the dominant axis W of their plane normal (class 0: W = x, 1: W = y, 2: W = z; `perm`
+// maps record position -> triangle id, classes are padded to whole tiles with "never" records).  On a plane that is not
+// parallel to W the barycentrics are affine functions of the two other coordinates (U, V) alone, so the filter needs
+// only two components of the plane hit point and two-term functionals: 16 packed FP32 instructions per (ray pair,
+// triangle) instead of 19.  (U, V) = (y, z), (z, x), (x, y) for W = x, y, z.
+//
+// Record at position p (4 float4):
+//   q0 = ( nx, ny, nz, dn )     unit plane normal, dn = -n.T0        -> h = n.O' + dn, cos = n.d
+//   q1 = ( su, sv, cs', c1 )    s(P) = su*Pu + sv*Pv + cs, cs' = cs + E0   (first barycentric of raytracing.cpp:144), c1 = 1 + 3*E0
+//   q2 = ( tu, tv, ct', -E1 )   t(P) = tu*Pu + tv*Pv + ct, ct' = ct + E0   (second barycentric, :148)
+//   q3 = ( bmin, id, 0, 0 )     id = triangle index (bits)
 // A pair is a CANDIDATE (goes to the exact path) iff
-//   ( min(s', t', c1 - s' - t') >= -E1*|1/b|  and  0 <= r' < rhi' )  or  |b| < bmin
-// with r' = aneg/(-b) (distance along the unit direction from the shifted origin O' = O - eps_r*d).
+//   ( min(s', t', c1 - s' - t') >= -E1*|1/cos|  and  0 <= r' < rhi' )  or  |cos| < bmin
+// with r' = h/(-cos) (distance along the unit direction from the shifted origin O' = O - eps_r*d).
 //   bmin = cos_min : normal triangle;   bmin = -1 : never a candidate (degenerate n == 0, padding);
 //   bmin = +inf    : always a candidate (ill-conditioned triangle, or one whose D is 0/NaN so that the
 //                    reference's NaN barycentrics pass its tests).
 // E0/E1 bound the difference between this evaluation and the reference's own rounding.
-__global__ void k_build_records(const float4* __restrict__ triv, int ntri, int npad, float M, float cos_min, float4* __restrict__ rec) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npad) return;
-    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = make_float4(0, 0, -1.0f, 0);  // "never"
-    if (i < ntri) {
+constexpr uint32_t kNoTriangle = 0xffffffffu;
+
+__global__ void k_build_records(const float4* __restrict__ triv, const uint32_t* __restrict__ perm, int npos, int c1_end, int c2_end, float M,
+                                float cos_min, float4* __restrict__ rec) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const uint32_t i = perm[pos];
+    const int W = pos < c1_end ? 0 : (pos < c2_end ? 1 : 2);   // class of this position (tile granular)
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = make_float4(-1.0f, __uint_as_float(i), 0, 0);  // "never"
+    if (i != kNoTriangle) {
         const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
         // the reference's own float quantities decide degeneracy (raytracing.cpp:106-109,134-140)
         v3 uf = e_sub(mk3(B), mk3(A)), vf = e_sub(mk3(C), mk3(A));
@@ -114,41 +126,43 @@ __global__ void k_build_records(const float4* __restrict__ triv, int ntri, int n
         float Df = __fsub_rn(__fmul_rn(uvf, uvf), __fmul_rn(uuf, vvf));
         if (!null_n) {
             bool always = !(fabsf(Df) > 0.0f) || !isfinite(Df);
-            double ux = (double)B.x - A.x, uy = (double)B.y - A.y, uz = (double)B.z - A.z;
-            double vx = (double)C.x - A.x, vy = (double)C.y - A.y, vz = (double)C.z - A.z;
-            double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
-            double nn = sqrt(nx * nx + ny * ny + nz * nz);
-            double uu = ux * ux + uy * uy + uz * uz, uv = ux * vx + uy * vy + uz * vz, vv = vx * vx + vy * vy + vz * vz;
-            double D = uv * uv - uu * vv;
-            if (!(nn > 0.0) || !(D < 0.0) || !isfinite(nn) || !isfinite(D)) always = true;
+            const double a3[3] = {A.x, A.y, A.z};
+            const double u3[3] = {(double)B.x - A.x, (double)B.y - A.y, (double)B.z - A.z};
+            const double v3d[3] = {(double)C.x - A.x, (double)C.y - A.y, (double)C.z - A.z};
+            double n3[3] = {u3[1] * v3d[2] - u3[2] * v3d[1], u3[2] * v3d[0] - u3[0] * v3d[2], u3[0] * v3d[1] - u3[1] * v3d[0]};
+            const double nn = sqrt(n3[0] * n3[0] + n3[1] * n3[1] + n3[2] * n3[2]);
+            const double uu = u3[0] * u3[0] + u3[1] * u3[1] + u3[2] * u3[2], vv = v3d[0] * v3d[0] + v3d[1] * v3d[1] + v3d[2] * v3d[2];
+            const int U = (W + 1) % 3, V = (W + 2) % 3;
+            const double det = u3[U] * v3d[V] - u3[V] * v3d[U];   // == n3[W]
+            if (!(nn > 0.0) || !isfinite(nn) || !(uu > 0.0) || !(vv > 0.0) || !(fabs(det) > 0.0) || !isfinite(det)) always = true;
             if (!always) {
-                double inv = 1.0 / nn;
-                nx *= inv; ny *= inv; nz *= inv;
-                double sx = (uv * vx - vv * ux) / D, sy = (uv * vy - vv * uy) / D, sz = (uv * vz - vv * uz) / D;
-                double tx = (uv * ux - uu * vx) / D, ty = (uv * uy - uu * vy) / D, tz = (uv * uz - uu * vz) / D;
-                double gs = sqrt(sx * sx + sy * sy + sz * sz), gt = sqrt(tx * tx + ty * ty + tz * tz);
-                double gq = sqrt((sx + tx) * (sx + tx) + (sy + ty) * (sy + ty) + (sz + tz) * (sz + tz));
-                double gmax = fmax(gs, fmax(gt, gq));
-                double sinphi = nn / sqrt(uu * vv);
-                double kappa = fmax(1.0, 0.25 / sinphi);
+                // s = 1 at B, t = 1 at C, both 0 at A, as functions of the (U, V) coordinates
+                const double su = v3d[V] / det, sv = -v3d[U] / det, tu = -u3[V] / det, tv = u3[U] / det;
+                const double gs = sqrt(su * su + sv * sv), gt = sqrt(tu * tu + tv * tv);
+                const double gq = sqrt((su + tu) * (su + tu) + (sv + tv) * (sv + tv));
+                const double gmax = fmax(gs, fmax(gt, gq));   // >= the in-plane gradients (the projection only stretches them)
+                const double sinphi = nn / sqrt(uu * vv);
+                const double kappa = fmax(1.0, 0.25 / sinphi);
                 // DESIGN.md "filter soundness": E0 covers the rounding of the reference's own dot-product
                 // barycentrics (<= 28uM*gmax/sin(phi) + 8u/sin^2(phi)) plus this filter's arithmetic (<= 16uM*gmax),
-                // E1*|1/cos| the in-plane shift caused by the two sides' error along the ray (<= 34uM/|cos|)
-                double E0 = 256.0 * (double)kU32 * (double)M * gmax * kappa + 1e-6;
-                double E1 = 64.0 * (double)kU32 * (double)M * gmax * kappa;
-                if (!(E0 < 64.0)) {  // beyond this the dilated triangle is so large that "always exact" is cheaper
+                // E1*|1/cos| the shift of (Pu, Pv) caused by the two sides' error along the ray (<= 34uM/|cos|)
+                const double E0 = 256.0 * (double)kU32 * (double)M * gmax * kappa + 1e-6;
+                const double E1 = 64.0 * (double)kU32 * (double)M * gmax * kappa;
+                if (!(E0 < 64.0) || !isfinite(E0)) {  // beyond this the dilated triangle is so large that "always exact" is cheaper
                     always = true;
                 } else {
-                    q0 = make_float4((float)nx, (float)ny, (float)nz, (float)(-(nx * A.x + ny * A.y + nz * A.z)));
-                    q1 = make_float4((float)sx, (float)sy, (float)sz, (float)(-(sx * A.x + sy * A.y + sz * A.z) + E0));
-                    q2 = make_float4((float)tx, (float)ty, (float)tz, (float)(-(tx * A.x + ty * A.y + tz * A.z) + E0));
-                    q3 = make_float4((float)(1.0 + 3.0 * E0), (float)(-E1), cos_min, 0.0f);
+                    const double inv = 1.0 / nn;
+                    n3[0] *= inv; n3[1] *= inv; n3[2] *= inv;
+                    q0 = make_float4((float)n3[0], (float)n3[1], (float)n3[2], (float)(-(n3[0] * a3[0] + n3[1] * a3[1] + n3[2] * a3[2])));
+                    q1 = make_float4((float)su, (float)sv, (float)(-(su * a3[U] + sv * a3[V]) + E0), (float)(1.0 + 3.0 * E0));
+                    q2 = make_float4((float)tu, (float)tv, (float)(-(tu * a3[U] + tv * a3[V]) + E0), (float)(-E1));
+                    q3.x = cos_min;
                 }
             }
-            if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3 = make_float4(0, 0, __int_as_float(0x7f800000), 0); }
+            if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3.x = __int_as_float(0x7f800000); }
         }
     }
-    rec[4 * i] = q0; rec[4 * i + 1] = q1; rec[4 * i + 2] = q2; rec[4 * i + 3] = q3;
+    rec[4 * pos] = q0; rec[4 * pos + 1] = q1; rec[4 * pos + 2] = q2; rec[4 * pos + 3] = q3;
 }
 
 // Conservative bounding box of everything a tile can make a hit of (RT_OPT_TILE_CULLING).
@@ -158,7 +172,7 @@ __global__ void k_build_records(const float4* __restrict__ triv, int ntri, int n
 // triangles (+ rounding slack) cannot hit any of them.  E0 is read back from the record (c1 = 1 + 3*E0).
 // A tile holding an "always exact" triangle (bmin = +inf: the bound does not exist) is unbounded and never skipped;
 // "never" records (degenerate, padding) contribute nothing.
-__global__ void k_build_tile_boxes(const float4* __restrict__ triv, const float4* __restrict__ rec, int ntri, int ntiles_padded, float M,
+__global__ void k_build_tile_boxes(const float4* __restrict__ triv, const float4* __restrict__ rec, int ntiles_padded, float M,
                                    float4* __restrict__ tile_box) {
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= ntiles_padded) return;
@@ -166,13 +180,13 @@ __global__ void k_build_tile_boxes(const float4* __restrict__ triv, const float4
     float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
     bool unbounded = false;
     for (int j = 0; j < kTile; ++j) {
-        const int i = tile * kTile + j;
-        if (i >= ntri) break;
-        const float4 q3 = rec[4 * i + 3];
-        if (q3.z < 0.0f) continue;                          // never a candidate
-        if (!(q3.z < inf)) { unbounded = true; break; }     // always exact
+        const int pos = tile * kTile + j;
+        const float4 q3 = rec[4 * pos + 3];
+        if (q3.x < 0.0f) continue;                          // never a candidate
+        if (!(q3.x < inf)) { unbounded = true; break; }     // always exact
+        const uint32_t i = __float_as_uint(q3.y);
         const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
-        const float e0 = fmaxf(q3.x - 1.0f, 0.0f) * (1.0f / 3.0f) + 1e-6f;
+        const float e0 = fmaxf(rec[4 * pos + 1].w - 1.0f, 0.0f) * (1.0f / 3.0f) + 1e-6f;
         const float ab = sqrtf((B.x - A.x) * (B.x - A.x) + (B.y - A.y) * (B.y - A.y) + (B.z - A.z) * (B.z - A.z));
         const float ac = sqrtf((C.x - A.x) * (C.x - A.x) + (C.y - A.y) * (C.y - A.y) + (C.z - A.z) * (C.z - A.z));
         const float bc = sqrtf((C.x - B.x) * (C.x - B.x) + (C.y - B.y) * (C.y - B.y) + (C.z - B.z) * (C.z - B.z));
@@ -348,10 +362,15 @@ __device__ __forceinline__ void fast_set(FastRays<RP>& f, v3 O, v3 D, float eps_
     f.rhi[K] = live ? 0x7f7fffffu : 0u;  // FLT_MAX: the reference starts from dist = FLT_MAX (raytracing.cpp:164)
 }
 
-// One filter evaluation for a pair of rays against one record; returns the two candidate predicates.
-template <int RP>
+// One filter evaluation for a pair of rays against one record of dominant-axis class W; returns the two candidate
+// predicates.  16 packed FP32 instructions + 2 MUFU.RCP + the compare logic.
+template <int RP, int W>
 __device__ __forceinline__ void filter_pair(const FastRays<RP>& f, int p, const float4& q0, const float4& q1, const float4& q2,
                                             const float4& q3, bool& c0, bool& c1) {
+    const float2 ou = (W == 0) ? f.oy[p] : (W == 1) ? f.oz[p] : f.ox[p];
+    const float2 ov = (W == 0) ? f.oz[p] : (W == 1) ? f.ox[p] : f.oy[p];
+    const float2 du = (W == 0) ? f.dy[p] : (W == 1) ? f.dz[p] : f.dx[p];
+    const float2 dv = (W == 0) ? f.dz[p] : (W == 1) ? f.dx[p] : f.dy[p];
     float2 b = __fmul2_rn(splat2(q0.x), f.dx[p]);
     b = __ffma2_rn(splat2(q0.y), f.dy[p], b);
     b = __ffma2_rn(splat2(q0.z), f.dz[p], b);
@@ -360,22 +379,19 @@ __device__ __forceinline__ void filter_pair(const FastRays<RP>& f, int p, const 
     a = __ffma2_rn(splat2(q0.z), f.oz[p], a);
     const float2 rc = make_float2(rcp_approx(-b.x), rcp_approx(-b.y));
     const float2 r = __fmul2_rn(a, rc);
-    const float2 ix = __ffma2_rn(r, f.dx[p], f.ox[p]);
-    const float2 iy = __ffma2_rn(r, f.dy[p], f.oy[p]);
-    const float2 iz = __ffma2_rn(r, f.dz[p], f.oz[p]);
-    float2 s = __ffma2_rn(splat2(q1.x), ix, splat2(q1.w));
-    s = __ffma2_rn(splat2(q1.y), iy, s);
-    s = __ffma2_rn(splat2(q1.z), iz, s);
-    float2 t = __ffma2_rn(splat2(q2.x), ix, splat2(q2.w));
-    t = __ffma2_rn(splat2(q2.y), iy, t);
-    t = __ffma2_rn(splat2(q2.z), iz, t);
-    float2 q = __fadd2_rn(splat2(q3.x), make_float2(-s.x, -s.y));
+    const float2 iu = __ffma2_rn(r, du, ou);
+    const float2 iv = __ffma2_rn(r, dv, ov);
+    float2 s = __ffma2_rn(splat2(q1.x), iu, splat2(q1.z));
+    s = __ffma2_rn(splat2(q1.y), iv, s);
+    float2 t = __ffma2_rn(splat2(q2.x), iu, splat2(q2.z));
+    t = __ffma2_rn(splat2(q2.y), iv, t);
+    float2 q = __fadd2_rn(splat2(q1.w), make_float2(-s.x, -s.y));
     q = __fadd2_rn(q, make_float2(-t.x, -t.y));
     const float m0 = fminf(fminf(s.x, t.x), q.x), m1 = fminf(fminf(s.y, t.y), q.y);
-    const float2 e = __fmul2_rn(splat2(q3.y), rc);  // tolerance -E1*|1/cos| = -|e|
+    const float2 e = __fmul2_rn(splat2(q2.w), rc);  // tolerance -E1*|1/cos| = -|e|
     // a NaN in s/t/q/e (non-finite geometry) keeps the pair a candidate; a NaN cos (dead ray slot) never is one
-    c0 = (!(m0 < -fabsf(e.x)) && (__float_as_uint(r.x) < f.rhi[2 * p])) || (fabsf(b.x) < q3.z);
-    c1 = (!(m1 < -fabsf(e.y)) && (__float_as_uint(r.y) < f.rhi[2 * p + 1])) || (fabsf(b.y) < q3.z);
+    c0 = (!(m0 < -fabsf(e.x)) && (__float_as_uint(r.x) < f.rhi[2 * p])) || (fabsf(b.x) < q3.x);
+    c1 = (!(m1 < -fabsf(e.y)) && (__float_as_uint(r.y) < f.rhi[2 * p + 1])) || (fabsf(b.y) < q3.x);
 }
 
 // Finished ray (shadow ray that found its occluder): no further candidates.
@@ -397,12 +413,86 @@ struct BitLayout {
 
 // Scans all tiles of one pass.  NEAREST: keeps (dist, best) exactly like intersectMesh; !NEAREST: any-hit,
 // clears the ray's live bit on the first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
+// One tile (kTile records of dominant-axis class W) against this thread's R rays.
+template <int RP, int J, bool NEAREST, int W, class Fetch>
+__device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
+                                          const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact) {
+    constexpr int R = 2 * RP;
+    constexpr uint32_t REP = BitLayout<RP, J>::kRep;
+#pragma unroll 1
+    for (int jb = 0; jb < kTile; jb += J) {
+        // hot: only "is there any candidate in this block" (the predicate ORs fold into the compares)
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
+            const float4 q2 = rec[(jb + j) * kRecVec + 2], q3 = rec[(jb + j) * kRecVec + 3];
+#pragma unroll
+            for (int p = 0; p < RP; ++p) {
+                bool c0, c1;
+                filter_pair<RP, W>(fr, p, q0, q1, q2, q3, c0, c1);
+                any = any || c0 || c1;
+            }
+        }
+        if (any) {  // cold: redo the block's filter to find which pairs, then exact re-evaluation per ray
+            uint32_t mask = 0;
+#pragma unroll 1
+            for (int j = 0; j < J; ++j) {
+                const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
+                const float4 q2 = rec[(jb + j) * kRecVec + 2], q3 = rec[(jb + j) * kRecVec + 3];
+#pragma unroll
+                for (int p = 0; p < RP; ++p) {
+                    bool c0, c1;
+                    filter_pair<RP, W>(fr, p, q0, q1, q2, q3, c0, c1);
+                    mask |= ((c0 ? 1u : 0u) << (2 * p) | (c1 ? 1u : 0u) << (2 * p + 1)) << (j * R);
+                }
+            }
+            mask &= live * REP;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const uint32_t mk = (mask >> k) & REP;
+                if (mk) {
+                    v3 O, D;
+                    fetch(k, O, D);
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        if ((mk & (1u << (j * R))) && (NEAREST || ((live >> k) & 1u))) {
+                            const int tri = (int)__float_as_uint(rec[(jb + j) * kRecVec + 3].y);   // triangle id of this record
+                            const float4 e = exact_eval_tri(triv, tri, O.x, O.y, O.z, D.x, D.y, D.z);
+                            ++n_exact;
+                            if (NEAREST) {
+                                // intersectMesh keeps the first (= lowest-index) triangle among equal distances (strict <,
+                                // raytracing.cpp:183); records are not visited in index order, so the index breaks ties here
+                                if (!(e.w < 0.0f) && (e.w < dist[k] || (e.w == dist[k] && tri < best[k]))) {
+                                    dist[k] = e.w;
+                                    best[k] = tri;
+                                    fr.rhi[k] = __float_as_uint(__fadd_ru(e.w, eps_r2));
+                                }
+                            } else {
+                                // isShadow ends with index != -1 iff some hit had distance < FLT_MAX
+                                // (raytracing.cpp:164,183); a NaN / inf distance never registers
+                                if (e.w >= 0.0f && e.w < FLT_MAX && (live & (1u << k))) {
+                                    live &= ~(1u << k);
+                                    best[k] = tri;
+                                    kill_slot<RP>(fr, k);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Scans the tiles [tile_begin, tile_begin + pipe.len) of one work item.  NEAREST: keeps (dist, best) like
+// intersectMesh; !NEAREST: any-hit, a ray dies at its first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
+// cls_end[0..1]: first tile of class 1 / class 2 (tiles are grouped by the dominant axis of their triangles).
 template <int RP, int J, bool NEAREST, class Fetch>
 __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
                                           const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact, int tile_begin,
-                                          const float4* __restrict__ tile_box) {
+                                          const float4* __restrict__ tile_box, int cls1, int cls2) {
     constexpr int R = 2 * RP;
-    constexpr uint32_t REP = BitLayout<RP, J>::kRep;
     for (int tile = tile_begin; tile < tile_begin + (int)pipe.len; ++tile) {
         const float4* rec = pipe_acquire(pipe);
         // does any live ray of this warp reach the tile?  (always, without tile culling)
@@ -422,69 +512,9 @@ __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&
         }
         // warp-level early exit: shadow rays that all found their occluder, or a tile no ray of the warp can reach
         if (__any_sync(0xffffffffu, need)) {
-            const int tri0 = tile * kTile;
-#pragma unroll 1
-            for (int jb = 0; jb < kTile; jb += J) {
-                // hot: only "is there any candidate in this block" (the predicate ORs fold into the compares)
-                bool any = false;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
-                    const float4 q2 = rec[(jb + j) * kRecVec + 2], q3 = rec[(jb + j) * kRecVec + 3];
-#pragma unroll
-                    for (int p = 0; p < RP; ++p) {
-                        bool c0, c1;
-                        filter_pair<RP>(fr, p, q0, q1, q2, q3, c0, c1);
-                        any = any || c0 || c1;
-                    }
-                }
-                if (any) {  // cold: redo the block's filter to find which pairs, then exact re-evaluation per ray in ascending triangle order
-                    uint32_t mask = 0;
-#pragma unroll 1
-                    for (int j = 0; j < J; ++j) {
-                        const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
-                        const float4 q2 = rec[(jb + j) * kRecVec + 2], q3 = rec[(jb + j) * kRecVec + 3];
-#pragma unroll
-                        for (int p = 0; p < RP; ++p) {
-                            bool c0, c1;
-                            filter_pair<RP>(fr, p, q0, q1, q2, q3, c0, c1);
-                            mask |= ((c0 ? 1u : 0u) << (2 * p) | (c1 ? 1u : 0u) << (2 * p + 1)) << (j * R);
-                        }
-                    }
-                    mask &= live * REP;
-#pragma unroll
-                    for (int k = 0; k < R; ++k) {
-                        const uint32_t mk = (mask >> k) & REP;
-                        if (mk) {
-                            v3 O, D;
-                            fetch(k, O, D);
-#pragma unroll
-                            for (int j = 0; j < J; ++j) {
-                                if ((mk & (1u << (j * R))) && (NEAREST || ((live >> k) & 1u))) {
-                                    const int tri = tri0 + jb + j;
-                                    const float4 e = exact_eval_tri(triv, tri, O.x, O.y, O.z, D.x, D.y, D.z);
-                                    ++n_exact;
-                                    if (NEAREST) {
-                                        if (!(e.w < 0.0f) && e.w < dist[k]) {  // raytracing.cpp:183 strict <
-                                            dist[k] = e.w;
-                                            best[k] = tri;
-                                            fr.rhi[k] = __float_as_uint(__fadd_ru(e.w, eps_r2));
-                                        }
-                                    } else {
-                                        // isShadow ends with index != -1 iff some hit had distance < FLT_MAX
-                                        // (raytracing.cpp:164,183); a NaN / inf distance never registers
-                                        if (e.w >= 0.0f && e.w < FLT_MAX && (live & (1u << k))) {
-                                            live &= ~(1u << k);
-                                            best[k] = tri;
-                                            kill_slot<RP>(fr, k);
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
+            if (tile < cls1) scan_tile<RP, J, NEAREST, 0>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+            else if (tile < cls2) scan_tile<RP, J, NEAREST, 1>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+            else scan_tile<RP, J, NEAREST, 2>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
         }
         pipe_release(pipe);
     }
@@ -604,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
             if (PRIMARY && !P.trace_api) { primary_ray(P, sid[k], O, D); }
             else { const float4 o = P.ray_o[sid[k]], d = P.ray_d[sid[k]]; O = mk3(o); D = mk3(d); }
         };
-        scan_pass<RP, J, true>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr);
+        scan_pass<RP, J, true>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr, P.cls1, P.cls2);
 
         // merge: (distance bits, triangle id) -- the smallest distance wins, equal distances go to the lowest
         // index, which is exactly the sequential rule of intersectMesh (strict <, raytracing.cpp:183)
@@ -722,7 +752,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
         }
         const uint32_t valid = live;
         FetchShadow fetch{P.hit, sid, light};
-        scan_pass<RP, J, NEAREST>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr);
+        scan_pass<RP, J, NEAREST>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr, P.cls1, P.cls2);
 
 #pragma unroll
         for (int k = 0; k < R; ++k) {

@@ -158,6 +158,41 @@ __device__ __forceinline__ bool block_vx(const Rays<RP>& f, const float4* rec, f
     return any;
 }
 
+// V6: 2-D projected barycentrics (dominant-axis classes): I needs 2 components, s/t are 2-term -> 16 packed ops
+template <int RP, int J>
+__device__ __forceinline__ bool block_v6(const Rays<RP>& f, const float4* rec) {
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const float4 q0 = rec[j * 4 + 0], q1 = rec[j * 4 + 1], q2 = rec[j * 4 + 2], q3 = rec[j * 4 + 3];
+#pragma unroll
+        for (int p = 0; p < RP; ++p) {
+            float2 b = __fmul2_rn(splat2(q0.x), f.dx[p]);
+            b = __ffma2_rn(splat2(q0.y), f.dy[p], b);
+            b = __ffma2_rn(splat2(q0.z), f.dz[p], b);
+            float2 a = __ffma2_rn(splat2(q0.x), f.ox[p], splat2(q0.w));
+            a = __ffma2_rn(splat2(q0.y), f.oy[p], a);
+            a = __ffma2_rn(splat2(q0.z), f.oz[p], a);
+            const float2 rc = make_float2(rcp_approx(-b.x), rcp_approx(-b.y));
+            const float2 r = __fmul2_rn(a, rc);
+            const float2 iu = __ffma2_rn(r, f.dx[p], f.ox[p]);
+            const float2 iv = __ffma2_rn(r, f.dy[p], f.oy[p]);
+            float2 s = __ffma2_rn(splat2(q1.x), iu, splat2(q1.z));
+            s = __ffma2_rn(splat2(q1.y), iv, s);
+            float2 t = __ffma2_rn(splat2(q2.x), iu, splat2(q2.z));
+            t = __ffma2_rn(splat2(q2.y), iv, t);
+            float2 q = __fadd2_rn(splat2(q1.w), make_float2(-s.x, -s.y));
+            q = __fadd2_rn(q, make_float2(-t.x, -t.y));
+            const float m0 = fminf(fminf(s.x, t.x), q.x), m1 = fminf(fminf(s.y, t.y), q.y);
+            const float2 e = __fmul2_rn(splat2(q2.w), rc);
+            const bool c0 = (!(m0 < -fabsf(e.x)) && (__float_as_uint(r.x) < f.rhi[2 * p])) || (fabsf(b.x) < q3.x);
+            const bool c1 = (!(m1 < -fabsf(e.y)) && (__float_as_uint(r.y) < f.rhi[2 * p + 1])) || (fabsf(b.y) < q3.x);
+            any = any || c0 || c1;
+        }
+    }
+    return any;
+}
+
 template <int RP, int J, int V, int MINB>
 __global__ void __launch_bounds__(256, MINB) k(const float4* rec_g, float* out, unsigned long long* cyc, float seed) {
     __shared__ float4 tile[kTile * 4];
@@ -178,7 +213,7 @@ __global__ void __launch_bounds__(256, MINB) k(const float4* rec_g, float* out, 
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll 1
         for (int jb = 0; jb < kTile; jb += J) {
-            const bool any = (V == 0) ? block_v0<RP, J>(f, tile + jb * 4) : (V == 1) ? block_v1<RP, J>(f, tile + jb * 4) : block_vx<RP, J, V>(f, tile + jb * 4, sink);
+            const bool any = (V == 0) ? block_v0<RP, J>(f, tile + jb * 4) : (V == 1) ? block_v1<RP, J>(f, tile + jb * 4) : (V == 6) ? block_v6<RP, J>(f, tile + jb * 4) : block_vx<RP, J, V>(f, tile + jb * 4, sink);
             if (any) { ++hits; f.rhi[0] ^= hits; }   // rare side effect so nothing is optimised away
         }
     }
@@ -216,6 +251,8 @@ int main() {
     }
     cudaMemcpy(rec, h, sizeof(h), cudaMemcpyHostToDevice);
     run<2, 8, 0, 2>("V0 rp2 j8 minb2 (shipped)", rec, out, cyc);
+    run<2, 8, 6, 2>("V6 2-D projected (16 packed)", rec, out, cyc);
+    run<1, 16, 6, 4>("V6 rp1 j16 minb4", rec, out, cyc);
     run<2, 8, 2, 2>("V2 FMA chain + MUFU, no compares", rec, out, cyc);
     run<2, 8, 3, 2>("V3 FMA chain only", rec, out, cyc);
     run<2, 8, 4, 2>("V4 V0 without |cos| clause", rec, out, cyc);
