@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="balls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-accelerated", action="store_true", help="skip the separately reported tile-culling frames (profiling runs)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -230,15 +231,17 @@ def main():
     e2e_steps = [frame_ms(e2e=True) for _ in range(max(3, min(args.steps, 5)))]
     fb_brute = fb_host.copy()
     # opt-in extra (not the contract path): conservative tile culling, same image bit for bit, reported separately
-    R.set_option(binding.RT_OPT_TILE_CULLING, 1)
-    for _ in range(3):
-        frame_ms()
-    barrier()
-    cull_steps = [frame_ms() for _ in range(max(3, min(args.steps, 10)))]
-    barrier()
-    R.download_into(fb_host)
-    cull_identical = bool(np.array_equal(fb_host.view(np.uint32), fb_brute.view(np.uint32)))
-    R.set_option(binding.RT_OPT_TILE_CULLING, 0)
+    cull_steps, cull_identical = [float("nan")], None
+    if not args.no_accelerated:
+        R.set_option(binding.RT_OPT_TILE_CULLING, 1)
+        for _ in range(3):
+            frame_ms()
+        barrier()
+        cull_steps = [frame_ms() for _ in range(max(3, min(args.steps, 10)))]
+        barrier()
+        R.download_into(fb_host)
+        cull_identical = bool(np.array_equal(fb_host.view(np.uint32), fb_brute.view(np.uint32)))
+        R.set_option(binding.RT_OPT_TILE_CULLING, 0)
 
     ms_dev = float(np.mean(per_step))
     ms_e2e = float(np.mean(e2e_steps))
@@ -266,8 +269,8 @@ def main():
         roof = {"bound": "fp32", "kernel": "k_trace (nearest-hit scan, all bounce levels)", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach / fp32_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the frame's largest k_trace launch (8.39 M primary rays), one
-                # `ncu --set full` capture of this command (profiles/r1b_k_trace_primary_full.txt); only meaningful for the default workload
-                "traffic": 592.2e6 if args.workload == "balls" and world == 1 else None, "traffic_unit": "B per launch (primary scan, chunk 0)", "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
+                # `ncu --set full` capture of this command (profiles/r1d_k_trace_primary_full.txt); only meaningful for the default workload
+                "traffic": 701.9e6 if args.workload == "balls" and world == 1 else None, "traffic_unit": "B per launch (primary scan, chunk 0)", "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
                 "frac_at_measured_clock": (ach / (fp32_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])) if clocks.get("sm_mhz") else None,
                 "frame_achieved": FLOPS_PER_TEST * rays * ntri / world / (ms_dev * 1e-3) / 1e12,
                 "ms_by_kernel": dict(zip(["k_trace", "k_shadow", "k_shade", "k_resolve", "gather"], [float(x) for x in kinds]))}
