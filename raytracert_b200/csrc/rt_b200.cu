@@ -82,6 +82,7 @@ struct RtDevice {
     float4* hit0 = nullptr;             // rt_trace: copy of the level-0 hit records
     uint32_t* counters = nullptr;      // kCntWords per chunk slot
     int counters_slots = 0;
+    int frame_chunks = 0;              // counter slots the last frame / trace call used
     int32_t* prim = nullptr; size_t cap_prim = 0;
     // framebuffers
     float *fb_local = nullptr, *fb_gather = nullptr, *fb_final = nullptr;
@@ -376,6 +377,7 @@ int render_enqueue(const rt_params* rp) {
             rc = ensure(d.fb_final, d.cap_final, (size_t)W * H * 3); if (rc) return rc;
         }
         CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords * std::max(1u, nchunks), d.stream));
+        d.frame_chunks = (int)std::max(1u, nchunks);
         if (my_rows < rows_per_rank) CU(cudaMemsetAsync(d.fb_local, 0, need_local * sizeof(float), d.stream));
         if (rp->want_prim_id) CU(cudaMemsetAsync(d.prim, 0xff, sizeof(int32_t) * rows_per_rank * row_samples, d.stream));
         CU(cudaEventRecord(d.ev_phase[0], d.stream));
@@ -392,7 +394,7 @@ int render_enqueue(const rt_params* rp) {
             P.nsamples = (uint32_t)(P.nrows * row_samples);
             P.tiles_x = (W + 7) / 8;
             P.nslots = P.tiles_x * ((P.nrows + 7) / 8) * 64u * spp;
-            P.sample_base = (uint32_t)(P.row0 * row_samples);
+            P.sample_base = (unsigned long long)P.row0 * row_samples;
             P.prim_out = rp->want_prim_id ? d.prim : nullptr;
             int levels = run_wavefront(d, P);
             if (levels < 0) return levels;
@@ -467,7 +469,7 @@ int collect_stats() {
         const uint32_t H = rp.height, G = (uint32_t)g.world;
         const uint32_t my_rows = (H > (uint32_t)d.rank) ? (H - d.rank + G - 1) / G : 0;
         st.primary_rays += (uint64_t)my_rows * rp.width * rp.pixelfactor_x * rp.pixelfactor_y;
-        for (int c = 0; c < d.counters_slots; ++c) {
+        for (int c = 0; c < d.frame_chunks; ++c) {
             const uint32_t* cw = &g.host_counters[(size_t)c * kCntWords];
             for (int l = 0; l < kMaxLevels; ++l) {
                 if (shadows) st.shadow_rays += (uint64_t)cw[kCntHit + l] * rp.n_lights;
@@ -756,6 +758,7 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     CU(cudaMemcpyAsync(d.thr, ht.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
     CU(cudaMemcpyAsync(d.acc, ha.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
     CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords, d.stream));
+    d.frame_chunks = 1;
     FrameParams P;
     fill_common(P, d, *rp, eps_r_for(M), d.counters);
     P.trace_api = 1;

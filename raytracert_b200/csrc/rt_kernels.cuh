@@ -76,7 +76,7 @@ struct FrameParams {
     uint32_t nsamples;          // samples in this chunk
     uint32_t nslots;            // primary work slots: samples in tiled order, padded to whole 8x8-pixel blocks (== nsamples for rt_trace)
     uint32_t tiles_x;           // 8x8-pixel blocks per row of blocks
-    uint32_t sample_base;       // local sample index of the chunk's first sample
+    unsigned long long sample_base;  // local sample index of the chunk's first sample (prim_out addressing)
     float eps_r;                // distance guard band of the filter
     float camera[3];
     int nlights;

@@ -309,3 +309,18 @@ def test_C4_one_million_triangles_reduced_frame(gpu, port):
     assert np.array_equal(prim, prim1) and np.array_equal(bits(rgb), bits(rgb1))
     hits = _lattice_check(gpu, port, s, cam, 2, 3, lights, 12, rgb, prim)
     assert hits > 50
+
+
+def test_stats_after_a_smaller_frame(gpu, port):
+    """Ray counters of a frame must not include chunks of an earlier, larger frame."""
+    from raytracert_b200 import binding, host, scenes
+    s = scenes.unit_cube()
+    gpu.upload_scene(s)
+    big = host.Camera(3000, 3000, (2.6, 2.4, 3.0), (.5, .5, .5))          # 9 M samples -> two chunks
+    gpu.render(binding.make_params(big.corners, 3000, 3000, 1, 1, 3, 63, big.eye, [big.eye]))
+    cam = host.Camera(64, 64, (2.6, 2.4, 3.0), (.5, .5, .5))
+    gpu.render(binding.make_params(cam.corners, 64, 64, 1, 1, 3, 63, cam.eye, [cam.eye]))
+    st = gpu.stats()
+    port.set_scene(s); port.configure(cam.eye, [cam.eye], 63, 3); port.reset_counts()
+    port.render(cam.corners, 64, 64, 1, 1)
+    assert (st["primary_rays"], st["shadow_rays"], st["bounce_rays"]) == port.ray_counts()
