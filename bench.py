@@ -211,6 +211,7 @@ def main():
         if not e2e:
             R.event_record(0); R.render(prm, sync=False); R.event_record(1); R.sync()
             return R.event_elapsed_ms(0, 1)
+        barrier()                                     # ranks start the step together (the all-gather would otherwise absorb their skew)
         t = time.perf_counter()
         R.upload_scene(scene); R.render(prm); R.download_into(fb_host)
         return (time.perf_counter() - t) * 1e3
@@ -285,7 +286,7 @@ def main():
                            "primary_mrays_per_s": counts[0] / ms_dev / 1e3, "parallelism": f"rows interleaved over {world} GPU(s)",
                            "l2": "flushed between timed iterations (256 MiB write)", "wall_s_timed_region": t_wall},
                 "clocks": clocks,
-                "e2e": {"value": rays / ms_e2e / 1e3, "unit": "Mrays/s", "ms_per_step": ms_e2e,
+                "e2e": {"value": rays / ms_e2e / 1e3, "unit": "Mrays/s", "ms_per_step": ms_e2e, "ms_steps_rank0": [round(x, 2) for x in e2e_steps],
                         "h2d_bytes_per_step": int(ntri * (4 * 16 + 4) + scene.materials.shape[0] * 64 + 432), "d2h_bytes_per_step": int(fb_host.nbytes),
                         "path": "rt_upload_scene + rt_render + rt_download_framebuffer with host buffers, every step"},
                 "gpu_launches": int(st["n_launches"]) * args.steps,
