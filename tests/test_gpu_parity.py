@@ -324,3 +324,57 @@ def test_stats_after_a_smaller_frame(gpu, port):
     port.set_scene(s); port.configure(cam.eye, [cam.eye], 63, 3); port.reset_counts()
     port.render(cam.corners, 64, 64, 1, 1)
     assert (st["primary_rays"], st["shadow_rays"], st["bounce_rays"]) == port.ray_counts()
+
+
+def test_scene_far_from_the_origin(gpu, port):
+    """Coordinates around 5000: float spacing is 5e-4 there, the filter tolerances scale with the magnitude bound M and
+    the reference's own rounding noise is large -- ids must still be the reference's (brute force and tile culling)."""
+    from raytracert_b200 import binding, host
+    base = load_scene("shadow_test")
+    off = np.array([5000.0, -3000.0, 4000.0], np.float32)
+    v = (base.vertices + off).astype(np.float32)
+    s = host.Scene(v, base.indices, base.tri_material, host.face_normals(v, base.indices), base.materials)
+    eye = (np.array([1, 5, 7], np.float32) + off).astype(np.float64)
+    cam = host.Camera(72, 72, tuple(eye), tuple(np.array([1, 1.2, .7]) + off))
+    lights = [tuple(eye), tuple(np.array([-2.0, 4.0, 1.0]) + off)]
+    c = dict(corners=cam.corners, W=72, H=72, pfx=2, pfy=2, max_lvl=4, features=63, eye=cam.eye, lights=lights)
+    port.set_scene(s); port.configure(cam.eye, lights, 63, 4); port.reset_counts()
+    rgb_o, _, prim_o = port.render(cam.corners, 72, 72, 2, 2, want_samples=True)
+    try:
+        for cull in (0, 1):
+            gpu.set_option(binding.RT_OPT_TILE_CULLING, cull)
+            rgb, prim = gpu_render(gpu, s, c)
+            assert np.array_equal(prim, prim_o)
+            assert np.abs(rgb - rgb_o).max() <= RGB_TOL
+            st = gpu.stats()
+            assert (st["primary_rays"], st["shadow_rays"], st["bounce_rays"]) == port.ray_counts()
+    finally:
+        gpu.set_option(binding.RT_OPT_TILE_CULLING, 0)
+    assert np.count_nonzero(prim_o >= 0) > 2000
+
+
+def test_axis_aligned_and_tied_normals(gpu, port):
+    """Dominant-axis classes: triangles whose normal is exactly an axis, and normals with two or three equal components."""
+    from raytracert_b200 import host
+    tris = []
+    for a in range(3):                      # unit squares perpendicular to each axis, both windings
+        e = np.eye(3)
+        u, w = e[(a + 1) % 3], e[(a + 2) % 3]
+        o = e[a] * (0.3 * (a + 1))
+        tris += [[o, o + u, o + w], [o + u + w, o + w, o + u]]
+    tris += [[[2, 0, 0], [0, 2, 0], [0, 0, 2]],          # normal (1,1,1)
+             [[2, 0, 0], [0, 2, 0], [2, 0, 1.5]],        # normal with nx == ny
+             [[-1, 0, 0.5], [0, -1, 0.5], [-1, -1, 1.5]]]
+    v = np.array(tris, np.float32).reshape(-1, 3)
+    idx = np.arange(len(v), dtype=np.uint32).reshape(-1, 3)
+    mats = load_scene("room").materials
+    s = host.Scene(v, idx, np.arange(len(idx), dtype=np.uint32) % len(mats), host.face_normals(v, idx), mats)
+    cam = host.Camera(96, 96, (3.1, 2.7, 3.6), (0.4, 0.4, 0.4))
+    lights = [(4, 5, 3)]
+    c = dict(corners=cam.corners, W=96, H=96, pfx=2, pfy=2, max_lvl=5, features=63, eye=cam.eye, lights=lights)
+    port.set_scene(s); port.configure(cam.eye, lights, 63, 5)
+    rgb_o, _, prim_o = port.render(cam.corners, 96, 96, 2, 2, want_samples=True)
+    rgb, prim = gpu_render(gpu, s, c)
+    assert len(np.unique(prim_o[prim_o >= 0])) >= 6
+    assert np.array_equal(prim, prim_o)
+    assert np.abs(rgb - rgb_o).max() <= RGB_TOL
