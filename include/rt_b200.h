@@ -149,7 +149,9 @@ int rt_trace(const rt_params* params, int n, const float* origins, const float* 
  *   option a warp skips a tile when none of its rays can reach the bounding box of the tile's (tolerance-dilated)
  *   triangles.  The image and the primitive ids are IDENTICAL to the brute-force scan (same filter + exact tiers on every
  *   tile that is not skipped) -- it only stops being the O(rays x triangles) loop of the reference
- *   (raytracing.cpp:174-189), which is why it is opt-in and reported separately by bench.py. */
+ *   (raytracing.cpp:174-189), which is why it is opt-in and reported separately by bench.py.  Set it BEFORE
+ *   rt_upload_scene to also get spatially sorted tiles (Morton order of the triangle centroids), which makes the boxes
+ *   compact; enabling it afterwards works on the tiles in file order. */
 #define RT_OPT_TILE_CULLING 1
 int rt_set_option(int option, int value);
 

@@ -617,6 +617,35 @@ int rt_upload_scene(const rt_scene* sc) {
         perm.assign(total + (size_t)kPadTiles * kTile, kNoTriangle);
         size_t fill[3] = {start[0], start[1], start[2]};
         for (uint32_t i = 0; i < n; ++i) perm[fill[cls[i]]++] = i;
+        if (g.tile_culling && n > 0) {
+            // tile culling wants spatially compact tiles: inside each class, order the triangles along a Morton curve
+            // of their centroids (the scan order is free: ties are broken by triangle id, results merge through keys)
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            std::vector<float> cen((size_t)3 * n);
+            for (uint32_t i = 0; i < n; ++i)
+                for (int a = 0; a < 3; ++a) {
+                    const float c = (sc->v0[4 * i + a] + sc->v1[4 * i + a] + sc->v2[4 * i + a]) * (1.0f / 3.0f);
+                    cen[3 * (size_t)i + a] = c;
+                    if (std::isfinite(c)) { lo[a] = std::min(lo[a], c); hi[a] = std::max(hi[a], c); }
+                }
+            auto spread = [](uint32_t v) {  // 10 bits -> every third bit
+                v &= 1023u; v = (v | (v << 16)) & 0x030000ffu; v = (v | (v << 8)) & 0x0300f00fu;
+                v = (v | (v << 4)) & 0x030c30c3u; v = (v | (v << 2)) & 0x09249249u; return v;
+            };
+            std::vector<uint32_t> code(n);
+            for (uint32_t i = 0; i < n; ++i) {
+                uint32_t m = 0;
+                for (int a = 0; a < 3; ++a) {
+                    const float ext = hi[a] - lo[a];
+                    float t = (ext > 0.f && std::isfinite(cen[3 * (size_t)i + a])) ? (cen[3 * (size_t)i + a] - lo[a]) / ext : 0.f;
+                    t = std::min(std::max(t, 0.f), 1.f);
+                    m |= spread((uint32_t)(t * 1023.f)) << a;
+                }
+                code[i] = m;
+            }
+            for (int c = 0; c < 3; ++c)
+                std::stable_sort(perm.begin() + start[c], perm.begin() + start[c] + cnt[c], [&](uint32_t x, uint32_t y) { return code[x] < code[y]; });
+        }
     }
     std::vector<float4> sph((size_t)2 * std::max(sc->n_spheres, 1u));
     for (uint32_t i = 0; i < sc->n_spheres; ++i) {

@@ -273,6 +273,14 @@ def test_tile_culling_is_invisible(gpu, port):
             for k in ("primary_rays", "shadow_rays", "bounce_rays"):
                 assert st0[k] == st1[k]
             assert st1["exact_evals"] <= st0["exact_evals"]
+            # the option enabled AFTER the upload (tiles stay in file order, not Morton-sorted): still the same frame
+            gpu.set_option(binding.RT_OPT_TILE_CULLING, 0)
+            gpu.upload_scene(s)
+            gpu.set_option(binding.RT_OPT_TILE_CULLING, 1)
+            gpu.render(binding.make_params(c["corners"], c["W"], c["H"], c["pfx"], c["pfy"], c["max_lvl"], c["features"], c["eye"], c["lights"],
+                                           want_prim_id=True))
+            rgb2, prim2 = gpu.download(want_prim_id=True)
+            assert np.array_equal(prim0, prim2) and np.array_equal(bits(rgb0), bits(rgb2))
     finally:
         gpu.set_option(binding.RT_OPT_TILE_CULLING, 0)
 

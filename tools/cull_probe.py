@@ -15,6 +15,7 @@ for name in ["balls", "dodge", "sphere200k"]:
     out = []
     for cull in (0, 1):
         R.set_option(binding.RT_OPT_TILE_CULLING, cull)
+        R.upload_scene(scene)
         R.render(prm); R.render(prm)
         st = R.stats(); out.append(R.download(want_prim_id=True))
         print(f"{name:10s} cull={cull} frame {st['ms_total']:8.2f} ms trace {st['ms_trace']:8.2f} shadow {st['ms_shadow']:8.2f} exact {st['exact_evals']:.3e}", flush=True)

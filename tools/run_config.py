@@ -29,6 +29,7 @@ out = {"workload": desc, "n_gpus": world}
 frames = {}
 for mode, cull in (("brute_force", 0), ("tile_culling", 1)):
     R.set_option(binding.RT_OPT_TILE_CULLING, cull)
+    R.upload_scene(scene)
     # warm-up (allocations, records, NCCL connections): the full frame when it is cheap, a tiny one otherwise
     R.render(prm if W * H * pf * pf * float(scene.n_triangles) < 2e11 else small)
     ms = []

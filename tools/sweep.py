@@ -20,6 +20,7 @@ for W in sizes:
         row = []
         for cull in (0, 1):
             R.set_option(binding.RT_OPT_TILE_CULLING, cull)
+            R.upload_scene(scene)
             R.render(prm)
             ms = []
             for _ in range(3):
