@@ -599,7 +599,29 @@ int rt_upload_scene(const rt_scene* sc) {
     int cls_tiles[3] = {0, 0, 0};
     {
         std::vector<uint8_t> cls(n);
-        size_t cnt[3] = {0, 0, 0};
+        size_t cnt[4] = {0, 0, 0, 0};
+        // with tile culling, triangles that will (probably) be "always exact" -- float D == 0 / NaN, extreme slivers --
+        // go to tiles of their own at the end (class 3, scanned with the W = z code path), so that they do not make the
+        // tiles of well-behaved triangles unbounded.  The test mirrors k_build_records loosely; a disagreement only
+        // costs speed (the record itself decides).
+        const float Mup = pow2_ceil(extent + 0.5f);
+        auto irregular = [&](const float* A, const float* B, const float* C) {
+            const float uf[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, vf[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+            const float uuf = uf[0] * uf[0] + uf[1] * uf[1] + uf[2] * uf[2], uvf = uf[0] * vf[0] + uf[1] * vf[1] + uf[2] * vf[2];
+            const float vvf = vf[0] * vf[0] + vf[1] * vf[1] + vf[2] * vf[2];
+            const float Df = uvf * uvf - uuf * vvf;
+            if (!(std::fabs(Df) > 0.0f) || !std::isfinite(Df)) return true;
+            const double u[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]};
+            const double v[3] = {(double)C[0] - A[0], (double)C[1] - A[1], (double)C[2] - A[2]};
+            const double nx = u[1] * v[2] - u[2] * v[1], ny = u[2] * v[0] - u[0] * v[2], nz = u[0] * v[1] - u[1] * v[0];
+            const double nn = std::sqrt(nx * nx + ny * ny + nz * nz), uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+            const double w[3] = {v[0] - u[0], v[1] - u[1], v[2] - u[2]};
+            const double ww = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+            if (!(nn > 0.0) || !std::isfinite(nn)) return true;
+            const double gmax = std::sqrt(std::max(uu, std::max(vv, ww))) / nn * 1.7320508;   // 1 / min altitude, stretched by the projection
+            const double kappa = std::max(1.0, 0.25 * std::sqrt(uu * vv) / nn);
+            return !(256.0 * (double)kU32 * Mup * gmax * kappa < 16.0);
+        };
         for (uint32_t i = 0; i < n; ++i) {
             const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i;
             const double u[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]};
@@ -608,14 +630,17 @@ int rt_upload_scene(const rt_scene* sc) {
             int w = 0;
             if (ny > nx) w = 1;
             if (nz > (w == 1 ? ny : nx)) w = 2;   // NaN compares false: non-finite triangles land in class 0 (and are "always exact")
+            if (g.tile_culling && irregular(A, B, C)) w = 3;
             cls[i] = (uint8_t)w;
             ++cnt[w];
         }
-        size_t start[3], total = 0;
-        for (int c = 0; c < 3; ++c) { start[c] = total; cls_tiles[c] = (int)((cnt[c] + kTile - 1) / kTile); total += (size_t)cls_tiles[c] * kTile; }
+        size_t start[4], total = 0;
+        int tiles4[4];
+        for (int c = 0; c < 4; ++c) { start[c] = total; tiles4[c] = (int)((cnt[c] + kTile - 1) / kTile); total += (size_t)tiles4[c] * kTile; }
+        cls_tiles[0] = tiles4[0]; cls_tiles[1] = tiles4[1]; cls_tiles[2] = tiles4[2] + tiles4[3];   // class 3 rides on the W = z path
         if (total == 0) { cls_tiles[0] = 1; total = kTile; }   // an empty scene still has one (padding) tile
         perm.assign(total + (size_t)kPadTiles * kTile, kNoTriangle);
-        size_t fill[3] = {start[0], start[1], start[2]};
+        size_t fill[4] = {start[0], start[1], start[2], start[3]};
         for (uint32_t i = 0; i < n; ++i) perm[fill[cls[i]]++] = i;
         if (g.tile_culling && n > 0) {
             // tile culling wants spatially compact tiles: inside each class, order the triangles along a Morton curve
