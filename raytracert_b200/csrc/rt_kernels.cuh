@@ -1,21 +1,28 @@
 // rt_kernels.cuh -- the sm_100a kernels of the render hot path.
 //
 // Reference functions replaced (paths under /root/reference/CG_Project):
-//   k_build_records   -- (new) per-triangle filter records; uses u,v,n,uu,uv,vv,D of raytracing.cpp:106-140
+//   k_build_records / k_build_tile_boxes -- (new) per-triangle filter records, built from u,v,n,uu,uv,vv,D of
+//                        raytracing.cpp:106-140, and per-tile bounds for the opt-in tile culling
 //   k_trace           -- main.cpp:377-388 ray generation (PRIMARY) + intersectMesh raytracing.cpp:161-192
+//   k_finish          -- tail of intersectMesh / head of trace (raytracing.cpp:183-191, 387-396): winner's hit point,
+//                        analytic spheres, hit record
 //   k_shadow          -- isShadow raytracing.cpp:241-261
 //   k_shade           -- shade/diffuseOnly/blinnPhongSpecularOnly/reflection/refraction/addOffset/trace
 //                        raytracing.cpp:197-232, 266-330, 335-406
 //   k_resolve         -- main.cpp:391-393 + RGBValue clamp main.cpp:24-42
-//   k_deinterleave / k_quantise -- row gather after the all-gather; Image::writeImage's quantiser main.cpp:117
+//   k_deinterleave / k_place_rows / k_quantise -- row gather after the all-gather; Image::writeImage's quantiser main.cpp:117
 //
 // How parity and speed coexist (DESIGN.md "filter + exact"):
 //   every (ray, triangle) pair first goes through a CONSERVATIVE FILTER evaluated with packed FP32 FMAs
-//   (FFMA2, two rays per instruction) on a precomputed 64-byte plane record; the filter may only say
+//   (FFMA2, two rays per instruction) on a precomputed 64-byte record; the filter may only say
 //   "certainly not a hit / certainly not nearer than the current best".  Pairs it cannot rule out are
 //   re-evaluated by exact_ray_triangle(), the reference's expression order with non-contracted IEEE
 //   operations, and only that exact result ever updates the nearest hit -- so primitive ids and hit
 //   points are the reference's, bit for bit, while ~all the work runs at FMA-pipe speed.
+//
+// Work decomposition: a scan launch is cut into items = (chunk of kThreads*R rays) x (range of triangle tiles);
+// persistent CTAs stride over the items, tiles stream through a TMA-filled shared-memory ring, per-ray results of
+// the parts are merged with atomics (make_split / Pipe / scan_pass below).
 #pragma once
 #include "rt_common.cuh"
 #include "../../include/rt_b200.h"
@@ -39,7 +46,7 @@ constexpr float kCosMinDefault = 1.0e-5f;  // |cos(ray, plane normal)| below thi
 
 // counters[] layout (uint32 unless noted)
 constexpr int kMaxLevels = 40;
-constexpr int kCntHit = 0;                 // [level] hits found by k_trace at that level
+constexpr int kCntHit = 0;                 // [level] hits recorded by k_finish at that level
 constexpr int kCntRay = kMaxLevels;        // [level] rays queued for k_trace at that level
 constexpr int kCntExact = 2 * kMaxLevels;  // 64-bit: exact re-evaluations (2 words)
 constexpr int kCntWords = 2 * kMaxLevels + 4;
