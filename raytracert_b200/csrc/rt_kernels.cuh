@@ -106,7 +106,7 @@ struct FrameParams {
 //   q0 = ( nx, ny, nz, dn )     unit plane normal, dn = -n.T0        -> h = n.O' + dn, cos = n.d
 //   q1 = ( su, sv, cs', c1 )    s(P) = su*Pu + sv*Pv + cs, cs' = cs + E0   (first barycentric of raytracing.cpp:144), c1 = 1 + 3*E0
 //   q2 = ( tu, tv, ct', -E1 )   t(P) = tu*Pu + tv*Pv + ct, ct' = ct + E0   (second barycentric, :148)
-//   q3 = ( bmin, id, 0, 0 )     id = triangle index (bits)
+//   q3 = ( bmin, id, nv, 0 )    id = triangle index (bits); nv (first record of a tile only) = records in use in the tile
 // A pair is a CANDIDATE (goes to the exact path) iff
 //   ( min(s', t', c1 - s' - t') >= -E1*|1/cos|  and  0 <= r' < rhi' )  or  |cos| < bmin
 // with r' = h/(-cos) (distance along the unit direction from the shifted origin O' = O - eps_r*d).
@@ -168,6 +168,13 @@ __global__ void k_build_records(const float4* __restrict__ triv, const uint32_t*
             }
             if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3.x = __int_as_float(0x7f800000); }
         }
+    }
+    if ((pos % kTile) == 0) {
+        // first record of a tile: q3.z = number of records up to the tile's last triangle (padding sits at the end of a
+        // class, so a partially filled tile -- every tile of a tiny scene -- is scanned only that far)
+        int last = -1;
+        for (int j = 0; j < kTile; ++j) if (perm[pos + j] != kNoTriangle) last = j;
+        q3.z = __int_as_float(last + 1);
     }
     rec[4 * pos] = q0; rec[4 * pos + 1] = q1; rec[4 * pos + 2] = q2; rec[4 * pos + 3] = q3;
 }
@@ -426,8 +433,9 @@ __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, f
                                           const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact) {
     constexpr int R = 2 * RP;
     constexpr uint32_t REP = BitLayout<RP, J>::kRep;
+    const int nvalid = __float_as_int(rec[3].z);   // records in use in this tile (warp-uniform); the rest is padding
 #pragma unroll 1
-    for (int jb = 0; jb < kTile; jb += J) {
+    for (int jb = 0; jb < nvalid; jb += J) {
         // hot: only "is there any candidate in this block" (the predicate ORs fold into the compares)
         bool any = false;
 #pragma unroll
