@@ -361,7 +361,11 @@ template <int RP, int K>
 __device__ __forceinline__ void fast_set(FastRays<RP>& f, v3 O, v3 D, float eps_r, bool live) {
     // d = normalize(D - O) only has to be accurate to a few ulp: it feeds the filter, never a result.
     float dx = D.x - O.x, dy = D.y - O.y, dz = D.z - O.z;
-    float inv = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-37f));
+    const float len2 = dx * dx + dy * dy + dz * dz;
+    float inv = rsqrtf(len2);
+    // a (near-)zero or overflowing direction cannot be normalised: d = 0 makes cos = 0 for every triangle, i.e. every
+    // pair goes to the exact path (|cos| < bmin), which is always sound
+    if (!(len2 > 1e-30f) || !(len2 < 1e30f)) inv = 0.0f;
     dx *= inv; dy *= inv; dz *= inv;
     // an unused / finished slot gets a NaN direction: cos = NaN fails every clause of the candidate test
     if (!live) { dx = dy = dz = __int_as_float(0x7fc00000); O = mk3(0.f, 0.f, 0.f); }

@@ -386,3 +386,21 @@ def test_axis_aligned_and_tied_normals(gpu, port):
     assert len(np.unique(prim_o[prim_o >= 0])) >= 6
     assert np.array_equal(prim, prim_o)
     assert np.abs(rgb - rgb_o).max() <= RGB_TOL
+
+
+def test_degenerate_rays_through_rt_trace(gpu, port):
+    """performRayTracing on rays the frame loop never makes: zero-length (origin == dest), NaN and huge directions.
+    The filter cannot normalise them, so every pair takes the exact path; results must be the reference's."""
+    from raytracert_b200 import binding
+    s = load_scene("shadow_test")
+    eye = np.array([1, 5, 7], np.float32)
+    o = np.array([[1, 5, 7], [1, 5, 7], [1, 5, 7], [0.5, 3.0, 0.5], [1, 5, 7], [2, 4, 6]], np.float32)
+    d = np.array([[1, 5, 7], [1, 5 - 1e-20, 7], [np.nan, 0, 0], [0.5, -1e30, 0.5], [1, 1.2, 0.7], [2 + 1e-25, 4, 6]], np.float32)
+    port.set_scene(s); port.configure(eye, [eye], 63, 4)
+    rgb_o, prim_o, hit_o = port.trace(o, d)
+    gpu.upload_scene(s)
+    rgb, prim, hit = gpu.trace(binding.make_params([0] * 24, 1, 1, 1, 1, 4, 63, eye, [eye]), o, d)
+    assert np.array_equal(prim, prim_o)
+    ok = np.isfinite(rgb_o)
+    assert np.array_equal(np.isfinite(rgb), ok) and np.abs(rgb[ok] - rgb_o[ok]).max() <= RGB_TOL
+    assert prim_o[4] >= 0
