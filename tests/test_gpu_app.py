@@ -53,3 +53,17 @@ def test_app_key_replay_toggles(built, tmp_path, port):
     rgb, _, _ = port.render(cam.corners, 64, 48, 1, 1)
     d = np.abs(img.astype(int) - port.quantise(rgb).astype(int))
     assert d.max() <= 1
+
+
+def test_app_light_and_sample_keys(built, tmp_path, port):
+    """'L' adds a light at the camera (main.cpp:334-336), '+' raises pixelfactorX/Y (raytracing.cpp:474-477); no --light:
+    init() puts the first light at the start-up camera position (raytracing.cpp:72)."""
+    from conftest import load_scene
+    from raytracert_b200 import host
+    img, _ = run_app(tmp_path, "--size", "48x40", "--pf", "1", "--lvl", "3", "--eye", "3.4,3.0,4.6", "--center", "0.4,0.2,0.2", "--keys", "L+r")
+    cam = host.Camera(48, 40, (3.4, 3.0, 4.6), (0.4, 0.2, 0.2))
+    port.set_scene(load_scene("quirks"))
+    port.configure(cam.eye, [cam.eye, cam.eye], 63, 3)
+    rgb, _, _ = port.render(cam.corners, 48, 40, 2, 2)
+    d = np.abs(img.astype(int) - port.quantise(rgb).astype(int))
+    assert d.max() <= 1
