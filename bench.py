@@ -228,6 +228,7 @@ def main():
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.summary()
     st = R.stats()
+    fp32_probe = R.probe_fp32_peak()   # measured packed-FMA ceiling of this device, for context beside the nominal peak
     # end-to-end through the public API with host buffers (scene H2D + frame + framebuffer D2H every step)
     e2e_steps = [frame_ms(e2e=True) for _ in range(max(3, min(args.steps, 5)))]
     fb_brute = fb_host.copy()
@@ -271,6 +272,8 @@ def main():
         ach = FLOPS_PER_TEST * trace_rays * ntri / (kinds[0] * 1e-3) / 1e12 if kinds[0] > 0 else 0.0
         roof = {"bound": "fp32", "kernel": "k_trace (nearest-hit scan, all bounce levels)", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach / fp32_peak,
+                # rt_probe_fp32_peak(): what a register-resident FFMA/FFMA2 loop sustains on this device right now (TFLOP/s)
+                "peak_fma_loop_measured": fp32_probe, "frac_of_measured_fma_loop": ach / fp32_probe if fp32_probe > 0 else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the frame's largest k_trace launch (8.39 M primary rays), one
                 # `ncu --set full` capture of this command (profiles/r1d_k_trace_primary_full.txt); only meaningful for the default workload
                 "traffic": 701.9e6 if args.workload == "balls" and world == 1 else None, "traffic_unit": "B per launch (primary scan, chunk 0)", "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",

@@ -157,6 +157,10 @@ int rt_set_option(int option, int value);
 
 int rt_get_stats(rt_stats* out);
 
+/* Measurement aid, not on the render path: the FP32 rate (TFLOP/s, FMA = 2) device 0 sustains on a register-resident
+ * packed-FMA loop -- the practical ceiling the roofline fraction of the intersection kernels can be read against. */
+int rt_probe_fp32_peak(float* tflops);
+
 /* Device-side timing on the library's own stream (CUDA events): slots 0..15. */
 int rt_event_record(int slot);
 int rt_event_elapsed_ms(int slot_begin, int slot_end, float* ms);

@@ -48,7 +48,7 @@ class RtStats(C.Structure):
 
 
 EXPORTS = ["rt_init", "rt_init_rank", "rt_nccl_unique_id", "rt_upload_scene", "rt_render", "rt_render_async",
-           "rt_sync", "rt_download_framebuffer", "rt_download_framebuffer_u8", "rt_trace", "rt_get_stats", "rt_set_option",
+           "rt_sync", "rt_download_framebuffer", "rt_download_framebuffer_u8", "rt_trace", "rt_get_stats", "rt_set_option", "rt_probe_fp32_peak",
            "rt_event_record", "rt_event_elapsed_ms", "rt_last_error", "rt_shutdown"]
 
 _LIB = None
@@ -78,6 +78,7 @@ def lib():
         L.rt_trace.argtypes = [C.POINTER(RtParams), C.c_int] + [C.c_void_p] * 5
         L.rt_get_stats.argtypes = [C.POINTER(RtStats)]
         L.rt_set_option.argtypes = [C.c_int, C.c_int]
+        L.rt_probe_fp32_peak.argtypes = [C.POINTER(C.c_float)]
         L.rt_event_record.argtypes = [C.c_int]
         L.rt_event_elapsed_ms.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.rt_shutdown.restype = None
@@ -202,6 +203,11 @@ class Renderer:
 
     def set_option(self, option, value):
         _check(self.L.rt_set_option(int(option), int(value)))
+
+    def probe_fp32_peak(self):
+        v = C.c_float(0)
+        _check(self.L.rt_probe_fp32_peak(C.byref(v)))
+        return v.value
 
     def stats(self):
         st = RtStats()

@@ -847,6 +847,35 @@ int rt_set_option(int option, int value) {
     return fail(RT_ERR_INVALID, "unknown option %d", option);
 }
 
+int rt_probe_fp32_peak(float* tflops) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (!tflops) return fail(RT_ERR_INVALID, "tflops is NULL");
+    RtDevice& d = g.devs[0];
+    CU(cudaSetDevice(d.device));
+    const int grid = d.num_sms * 8, iters = 8192;
+    float2* buf = nullptr;
+    CU(cudaMalloc(&buf, sizeof(float2) * (size_t)grid * 256));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    k_fp32_peak_probe<true><<<grid, 256, 0, d.stream>>>(buf, 1.0f, iters / 8);   // warm-up (clock ramp)
+    float best = 0.f;
+    for (int rep = 0; rep < 6; ++rep) {   // packed and scalar FMAs, best of three each
+        CU(cudaEventRecord(e0, d.stream));
+        if (rep & 1) k_fp32_peak_probe<true><<<grid, 256, 0, d.stream>>>(buf, 1.0f, iters);
+        else k_fp32_peak_probe<false><<<grid, 256, 0, d.stream>>>(buf, 1.0f, iters);
+        CU(cudaEventRecord(e1, d.stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = (double)grid * 256 * (double)iters * 16 * 4;   // 16 FFMA2 per iteration, 4 flop each
+        best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    *tflops = best;
+    return RT_OK;
+}
+
 int rt_get_stats(rt_stats* out) {
     int rc = check_ready();
     if (rc) return rc;

@@ -1008,6 +1008,29 @@ __global__ void k_place_rows(const float* __restrict__ local, float* __restrict_
     }
 }
 
+// Measured FP32 ceiling of the device (rt_probe_fp32_peak): 16 independent packed-FMA chains per thread whose
+// multiplier and addend stay in the operand-reuse cache, i.e. the most the FMA pipe can retire (2 x 2 flop per
+// FFMA2 per lane).  Not part of the render path.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) k_fp32_peak_probe(float2* __restrict__ out, float seed, int iters) {
+    float2 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float2(seed + i, seed - i + threadIdx.x * 1e-3f);
+    const float2 m = make_float2(0.9999f, 1.0001f), c = make_float2(1e-4f, -1e-4f);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (PACKED) acc[i] = __ffma2_rn(acc[i], m, c);                                   // 1 FFMA2
+            else { acc[i].x = fmaf(acc[i].x, m.x, c.x); acc[i].y = fmaf(acc[i].y, m.y, c.y); }  // 2 FFMA
+        }
+    }
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { s.x += acc[i].x; s.y += acc[i].y; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // Image::writeImage's quantiser (main.cpp:117): (unsigned char)(v * 255.0f), truncation toward zero.
 __global__ void k_quantise(const float* __restrict__ fb, uint8_t* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
