@@ -13,38 +13,40 @@
 #include "mesh.h"
 
 class Sphere {
-    Vec3Df center;
-    float radius;
-    Material material;
-
 public:
-    Sphere() : center(0, 0, 0), radius(1) {}
-    Sphere(Vec3Df _center, float _radius, Material _material) : center(_center), radius(_radius), material(_material) {}
+    Sphere() : c_(0, 0, 0), r_(1) {}
+    Sphere(Vec3Df _center, float _radius, Material _material) : c_(_center), r_(_radius), m_(_material) {}
     virtual ~Sphere() {}
 
-    const Vec3Df& getCenter() const { return center; }
-    float getRadius() const { return radius; }
-    const Material& getMaterial() const { return material; }
+    const Vec3Df& getCenter() const { return c_; }
+    float getRadius() const { return r_; }
+    const Material& getMaterial() const { return m_; }
 
+    // Unit outward normal at a surface point.
     virtual Vec3Df getNormalAt(Vec3Df& intersection) {
-        Vec3Df result = intersection - center;
-        result.normalize();
-        return result;
+        Vec3Df n = intersection - c_;
+        n.normalize();
+        return n;
     }
 
-    // Distance along the unit direction origin -> destination to the nearest intersection, 0 on a miss.
+    // Distance along the unit direction origin -> destination to the nearest intersection, 0 on a miss
+    // (float arithmetic in this exact order: it is the definition the oracle and the GPU share).
     virtual float findIntersection(Vec3Df& origin, Vec3Df& destination) {
         Vec3Df d = destination - origin;
         d.normalize();
-        Vec3Df oc = origin - center;
-        float bq = Vec3Df::dotProduct(oc, d);
-        float cq = Vec3Df::dotProduct(oc, oc) - radius * radius;
-        float disc = bq * bq - cq;
+        const Vec3Df oc = origin - c_;
+        const float half_b = Vec3Df::dotProduct(oc, d);
+        const float c = Vec3Df::dotProduct(oc, oc) - r_ * r_;
+        const float disc = half_b * half_b - c;
         if (disc < 0) return 0;
-        float sq = (float)std::sqrt((double)disc);
-        float t = -bq - sq;
-        if (!(t > 1e-4f)) t = -bq + sq;
-        if (!(t > 1e-4f)) return 0;
-        return t;
+        const float root = (float)std::sqrt((double)disc);
+        float t = -half_b - root;
+        if (!(t > 1e-4f)) t = -half_b + root;
+        return (t > 1e-4f) ? t : 0;
     }
+
+private:
+    Vec3Df c_;
+    float r_;
+    Material m_;
 };

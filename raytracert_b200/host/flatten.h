@@ -40,8 +40,9 @@ inline rt_material flatten_material(const Material& m) {
     rt_material r;
     for (int c = 0; c < 3; ++c) { r.Kd[c] = m.Kd()[c]; r.Ka[c] = m.Ka()[c]; r.Ks[c] = m.Ks()[c]; }
     r.Ns = m.Ns(); r.Ni = m.Ni(); r.Tr = m.Tr();
-    r.flags = (m.has_Kd() ? RT_HAS_KD : 0) | (m.has_Ka() ? RT_HAS_KA : 0) | (m.has_Ks() ? RT_HAS_KS : 0) |
-              (m.has_Ns() ? RT_HAS_NS : 0) | (m.has_Ni() ? RT_HAS_NI : 0) | (m.has_Tr() ? RT_HAS_TR : 0);
+    static_assert(Material::kKd == RT_HAS_KD && Material::kKa == RT_HAS_KA && Material::kKs == RT_HAS_KS && Material::kNs == RT_HAS_NS &&
+                  Material::kNi == RT_HAS_NI && Material::kTr == RT_HAS_TR, "Material::Field must match the RT_HAS_* bits");
+    r.flags = m.seen() & (RT_HAS_KD | RT_HAS_KA | RT_HAS_KS | RT_HAS_NS | RT_HAS_NI | RT_HAS_TR);
     r.pad[0] = r.pad[1] = r.pad[2] = 0;
     return r;
 }

@@ -15,49 +15,51 @@
 
 class Material {
 public:
-    Material() : Ns_(0.f), Ni_(1.f), illum_(0), Tr_(1.f) { cleanup(); }
+    // which statements of the MTL block were seen; the bit values are the RT_HAS_* flags of include/rt_b200.h
+    enum Field : unsigned { kKd = 1u, kKa = 2u, kKs = 4u, kNs = 8u, kNi = 16u, kTr = 32u, kIllum = 64u };
 
-    void cleanup() {
-        Kd_set_ = Ka_set_ = Ks_set_ = Ns_set_ = Ni_set_ = Tr_set_ = illum_set_ = false;
-        name_ = "empty";
-    }
-    bool is_valid() const { return Kd_set_ || Ka_set_ || Ks_set_ || Tr_set_; }
+    Material() : seen_(0u), scalar_{0.f, 1.f, 1.f}, illum_(0), name_("empty") {}   // Ns = 0, Ni = 1, Tr = 1 (pinned)
 
-    bool has_Kd() const { return Kd_set_; }
-    bool has_Ka() const { return Ka_set_; }
-    bool has_Ks() const { return Ks_set_; }
-    bool has_Ns() const { return Ns_set_; }
-    bool has_Ni() const { return Ni_set_; }
-    bool has_illum() const { return illum_set_; }
-    bool has_Tr() const { return Tr_set_; }
+    // Forget which fields were set (and the name); the VALUES stay -- see the note above.
+    void cleanup() { seen_ = 0u; name_ = "empty"; }
+    bool is_valid() const { return (seen_ & (kKd | kKa | kKs | kTr)) != 0u; }
+    unsigned seen() const { return seen_; }
 
-    void set_Kd(float r, float g, float b) { Kd_ = Vec3Df(r, g, b); Kd_set_ = true; }
-    void set_Ka(float r, float g, float b) { Ka_ = Vec3Df(r, g, b); Ka_set_ = true; }
-    void set_Ks(float r, float g, float b) { Ks_ = Vec3Df(r, g, b); Ks_set_ = true; }
-    void set_Ns(float v) { Ns_ = v; Ns_set_ = true; }
-    void set_Ni(float v) { Ni_ = v; Ni_set_ = true; }
-    void set_illum(int v) { illum_ = v; illum_set_ = true; }
-    void set_Tr(float v) { Tr_ = v; Tr_set_ = true; }
-    void set_textureName(const std::string& s) { textureName_ = s; }
+    bool has_Kd() const { return has(kKd); }
+    bool has_Ka() const { return has(kKa); }
+    bool has_Ks() const { return has(kKs); }
+    bool has_Ns() const { return has(kNs); }
+    bool has_Ni() const { return has(kNi); }
+    bool has_illum() const { return has(kIllum); }
+    bool has_Tr() const { return has(kTr); }
+
+    void set_Kd(float r, float g, float b) { colour_[0] = Vec3Df(r, g, b); seen_ |= kKd; }
+    void set_Ka(float r, float g, float b) { colour_[1] = Vec3Df(r, g, b); seen_ |= kKa; }
+    void set_Ks(float r, float g, float b) { colour_[2] = Vec3Df(r, g, b); seen_ |= kKs; }
+    void set_Ns(float v) { scalar_[0] = v; seen_ |= kNs; }
+    void set_Ni(float v) { scalar_[1] = v; seen_ |= kNi; }
+    void set_Tr(float v) { scalar_[2] = v; seen_ |= kTr; }
+    void set_illum(int v) { illum_ = v; seen_ |= kIllum; }
+    void set_textureName(const std::string& s) { texture_ = s; }
     void set_name(const std::string& s) { name_ = s; }
 
-    const Vec3Df& Kd() const { return Kd_; }
-    const Vec3Df& Ka() const { return Ka_; }
-    const Vec3Df& Ks() const { return Ks_; }
-    float Ns() const { return Ns_; }
-    float Ni() const { return Ni_; }
+    const Vec3Df& Kd() const { return colour_[0]; }   // diffuse
+    const Vec3Df& Ka() const { return colour_[1]; }   // ambient
+    const Vec3Df& Ks() const { return colour_[2]; }   // specular (also the reflection weight, flag or not)
+    float Ns() const { return scalar_[0]; }           // shininess
+    float Ni() const { return scalar_[1]; }           // index of refraction
+    float Tr() const { return scalar_[2]; }           // "d" / "Tr": 1 = opaque
     int illum() const { return illum_; }
-    float Tr() const { return Tr_; }
-    const std::string& textureName() const { return textureName_; }
+    const std::string& textureName() const { return texture_; }
     const std::string& name() const { return name_; }
 
 private:
-    Vec3Df Kd_, Ka_, Ks_;
-    float Ns_, Ni_;
+    bool has(unsigned f) const { return (seen_ & f) != 0u; }
+    unsigned seen_;
+    Vec3Df colour_[3];   // Kd, Ka, Ks
+    float scalar_[3];    // Ns, Ni, Tr
     int illum_;
-    float Tr_;
-    bool Kd_set_, Ka_set_, Ks_set_, Ns_set_, Ni_set_, illum_set_, Tr_set_;
-    std::string name_, textureName_;
+    std::string name_, texture_;
 };
 
 // Vertex ids v[3] and texture-coordinate ids t[3] of one face.
