@@ -107,7 +107,7 @@ typedef struct rt_stats {
     float ms_total, ms_trace, ms_shadow, ms_shade, ms_resolve, ms_gather;
     uint32_t n_gpus, rank, n_triangles, n_levels;
     uint32_t n_launches;                              /* kernels launched for the frame (per GPU)      */
-    uint32_t pad;
+    uint32_t variant;                                 /* bit 0: scan kernels without the grazing clause (fine mesh) */
 } rt_stats;
 
 /* Single-process mode: use devices 0..n_gpus-1 of this box (n_gpus >= 1); rows are interleaved over

