@@ -76,6 +76,9 @@ struct RtDevice {
     float M_built = 0.f, dir_built = 0.f;   // magnitude bound / longest ray the records were built for
     bool no_grazing = false;                // the records carry no grazing clause (see build_records)
     unsigned int* n_always = nullptr;       // device counter written by k_build_records
+    uint32_t* always_list = nullptr;        // triangles outside the filter (see k_build_records)
+    size_t cap_always = 0;
+    int n_always_host = 0;
     // per-chunk state
     size_t cap_samples = 0;
     float4 *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *acc = nullptr, *hit = nullptr;
@@ -170,7 +173,7 @@ int create_device(RtDevice& d, int device, int rank) {
 void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
-    void* ptrs[] = {d.rec, d.perm, d.n_always, d.tile_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+    void* ptrs[] = {d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
                     d.q_hit, d.key, d.hit0, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -259,9 +262,9 @@ float pow2_ceil(float v) {
 // 7u|u||v| of u x v (rounded edges and cross product), its dot product adds 3u|n||dir|, and |n| <= |u||v|:
 //     |b_ref| < |dir| |u||v| (1.05e-5 + 7u + 3u) < 1.11e-5 |dir||u||v|.
 // So if  max_triangles(|u||v|) * max_rays(|dir|) <= 0.85  every such pair is a certain miss in the reference and the
-// clause can be compiled out (kernel variants with GRAZ = false) -- provided no triangle is "always exact" (those reach
-// the exact path through the same clause) and the face normals handed in are not longer than 1 (they bound the
-// reflected / refracted directions in direction_bound()).  Fine meshes (the Balls stand-in, the 1 M-triangle sphere)
+// clause can be compiled out (kernel variants with GRAZ = false) -- provided the face normals handed in are not longer
+// than 1 (they bound the reflected / refracted directions in direction_bound()).  ("Always exact" triangles do not go
+// through the filter at all: always_list.)  Fine meshes (the Balls stand-in, the 1 M-triangle sphere)
 // qualify; scenes with large triangles (cube, ground quads) or far lights keep the clause.
 int build_records(RtDevice& d, float M, float dir_max) {
     dir_max = pow2_ceil(dir_max);   // coarse steps: a moving camera does not rebuild every frame
@@ -272,16 +275,16 @@ int build_records(RtDevice& d, float M, float dir_max) {
     const int npad = (d.ntiles + kPadTiles) * kTile;
     if (!d.n_always) CU(cudaMalloc(&d.n_always, sizeof(unsigned int)));
     CU(cudaMemsetAsync(d.n_always, 0, sizeof(unsigned int), d.stream));
-    k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.perm, npad, d.cls1 * kTile, d.cls2 * kTile, M, g.cos_min, d.rec, d.n_always);
+    int rc = ensure(d.always_list, d.cap_always, (size_t)std::max(d.ntri, 1));
+    if (rc) return rc;
+    d.no_grazing = g.allow_no_grazing && g.cos_min <= 1.0e-5f && g.unit_normals && (double)g.max_uv * (double)dir_max <= 0.85;
+    k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.perm, npad, d.cls1 * kTile, d.cls2 * kTile, M,
+                                                           d.no_grazing ? kBminNoGrazing : g.cos_min, d.rec, d.n_always, d.always_list);
     CU(cudaGetLastError());
-    unsigned int n_always = 1;
+    unsigned int n_always = 0;
     CU(cudaMemcpyAsync(&n_always, d.n_always, sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
-    d.no_grazing = g.allow_no_grazing && n_always == 0 && g.cos_min <= 1.0e-5f && g.unit_normals && (double)g.max_uv * (double)dir_max <= 0.85;
-    if (d.no_grazing) {
-        k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.perm, npad, d.cls1 * kTile, d.cls2 * kTile, M, kBminNoGrazing, d.rec, d.n_always);
-        CU(cudaGetLastError());
-    }
+    d.n_always_host = (int)n_always;
     const int tiles_padded = d.ntiles + kPadTiles;
     k_build_tile_boxes<<<(tiles_padded + 127) / 128, 128, 0, d.stream>>>(d.triv, d.rec, tiles_padded, M, d.tile_box);
     CU(cudaGetLastError());
@@ -324,6 +327,7 @@ void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float e
     P.ray_o = d.ray_o; P.ray_d = d.ray_d; P.thr = d.thr; P.acc = d.acc; P.hit = d.hit; P.lit = d.lit;
     P.q_ray = d.q_ray; P.q_hit = d.q_hit; P.counters = counters; P.key = d.key;
     P.tile_box = d.tile_box; P.cull = g.tile_culling ? 1 : 0;
+    P.always_list = d.always_list; P.n_always = d.n_always_host;
     P.eps_r = eps_r;
     memcpy(P.camera, rp.camera, sizeof(P.camera));
     P.nlights = (int)rp.n_lights;
@@ -670,28 +674,6 @@ int rt_upload_scene(const rt_scene* sc) {
     {
         std::vector<uint8_t> cls(n);
         size_t cnt[4] = {0, 0, 0, 0};
-        // with tile culling, triangles that will (probably) be "always exact" -- float D == 0 / NaN, extreme slivers --
-        // go to tiles of their own at the end (class 3, scanned with the W = z code path), so that they do not make the
-        // tiles of well-behaved triangles unbounded.  The test mirrors k_build_records loosely; a disagreement only
-        // costs speed (the record itself decides).
-        const float Mup = pow2_ceil(extent + 0.5f);
-        auto irregular = [&](const float* A, const float* B, const float* C) {
-            const float uf[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, vf[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
-            const float uuf = uf[0] * uf[0] + uf[1] * uf[1] + uf[2] * uf[2], uvf = uf[0] * vf[0] + uf[1] * vf[1] + uf[2] * vf[2];
-            const float vvf = vf[0] * vf[0] + vf[1] * vf[1] + vf[2] * vf[2];
-            const float Df = uvf * uvf - uuf * vvf;
-            if (!(std::fabs(Df) > 0.0f) || !std::isfinite(Df)) return true;
-            const double u[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]};
-            const double v[3] = {(double)C[0] - A[0], (double)C[1] - A[1], (double)C[2] - A[2]};
-            const double nx = u[1] * v[2] - u[2] * v[1], ny = u[2] * v[0] - u[0] * v[2], nz = u[0] * v[1] - u[1] * v[0];
-            const double nn = std::sqrt(nx * nx + ny * ny + nz * nz), uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-            const double w[3] = {v[0] - u[0], v[1] - u[1], v[2] - u[2]};
-            const double ww = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
-            if (!(nn > 0.0) || !std::isfinite(nn)) return true;
-            const double gmax = std::sqrt(std::max(uu, std::max(vv, ww))) / nn * 1.7320508;   // 1 / min altitude, stretched by the projection
-            const double kappa = std::max(1.0, 0.25 * std::sqrt(uu * vv) / nn);
-            return !(256.0 * (double)kU32 * Mup * gmax * kappa < 16.0);
-        };
         for (uint32_t i = 0; i < n; ++i) {
             const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i;
             const double u[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]};
@@ -700,7 +682,6 @@ int rt_upload_scene(const rt_scene* sc) {
             int w = 0;
             if (ny > nx) w = 1;
             if (nz > (w == 1 ? ny : nx)) w = 2;   // NaN compares false: non-finite triangles land in class 0 (and are "always exact")
-            if (g.tile_culling && irregular(A, B, C)) w = 3;
             cls[i] = (uint8_t)w;
             ++cnt[w];
         }

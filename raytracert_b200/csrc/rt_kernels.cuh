@@ -71,6 +71,8 @@ struct FrameParams {
     uint32_t* q_hit;
     uint32_t* counters;
     unsigned long long* key;    // per sample: nearest (distance, triangle) found by the scan parts, merged with atomicMin
+    const uint32_t* always_list;  // triangles the filter cannot bound ("always exact"): evaluated per ray outside the scan
+    int n_always;
     const float4* tile_box;     // 2 float4 per tile: conservative AABB (lo, hi) of the tile's candidate region
     int cull;                   // RT_OPT_TILE_CULLING: warps skip tiles whose box none of their rays can reach
     int32_t* prim_out;          // optional: primary primitive id per local sample
@@ -111,16 +113,18 @@ struct FrameParams {
 //   ( min(s', t', c1 - s' - t') >= -E1*|1/cos|  and  0 <= r' < rhi' )  or  |cos| < bmin
 // with r' = h/(-cos) (distance along the unit direction from the shifted origin O' = O - eps_r*d).
 //   bmin = cos_min : normal triangle;   bmin = -1 : never a candidate (degenerate n == 0, padding);
-//   bmin = +inf    : always a candidate (ill-conditioned triangle, or one whose D is 0/NaN so that the
-//                    reference's NaN barycentrics pass its tests).
+//   (triangles the filter cannot bound are not in the records at all: see always_list below)
 // E0/E1 bound the difference between this evaluation and the reference's own rounding.
 constexpr uint32_t kNoTriangle = 0xffffffffu;
 
 // bmin_regular: cos_min, or kBminNoGrazing (< 0, never true) when the grazing clause is provably unnecessary.
-// n_always counts the triangles that depend on the clause (bmin = +inf).
+// Triangles the filter cannot bound (float D == 0 / NaN so that the reference's NaN barycentrics pass its tests,
+// non-finite vertices, slivers with E0 >= 64) get a "never" record and are appended to always_list instead: k_finish /
+// k_shadow evaluate those exactly for every ray.  Nearest hits merge by (distance, id) and shadow rays only ask
+// "any hit", so where a triangle is evaluated does not matter.
 constexpr float kBminNever = -1.0f, kBminNoGrazing = -0.5f;
 __global__ void k_build_records(const float4* __restrict__ triv, const uint32_t* __restrict__ perm, int npos, int c1_end, int c2_end, float M,
-                                float bmin_regular, float4* __restrict__ rec, unsigned int* __restrict__ n_always) {
+                                float bmin_regular, float4* __restrict__ rec, unsigned int* __restrict__ n_always, uint32_t* __restrict__ always_list) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= npos) return;
     const uint32_t i = perm[pos];
@@ -169,7 +173,7 @@ __global__ void k_build_records(const float4* __restrict__ triv, const uint32_t*
                     q3.x = bmin_regular;
                 }
             }
-            if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3.x = __int_as_float(0x7f800000); atomicAdd(n_always, 1u); }
+            if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3.x = kBminNever; always_list[atomicAdd(n_always, 1u)] = i; }
         }
     }
     if ((pos % kTile) == 0) {
@@ -703,6 +707,11 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FramePar
                 const float4 e = exact_eval_tri(P.triv, idx, O.x, O.y, O.z, D.x, D.y, D.z);
                 I = mk3(e);
             }
+            for (int a = 0; a < P.n_always; ++a) {   // triangles outside the filter: same (distance, id) rule as the scan
+                const int tri = (int)P.always_list[a];
+                const float4 e = exact_eval_tri(P.triv, tri, O.x, O.y, O.z, D.x, D.y, D.z);
+                if (!(e.w < 0.0f) && (e.w < dbest || (e.w == dbest && tri < idx))) { dbest = e.w; idx = tri; I = mk3(e); }
+            }
             for (int sp = 0; sp < P.nspheres; ++sp) {  // spheres come after the triangles, strict <
                 const float4 c = P.spheres[2 * sp];
                 v3 Is;
@@ -717,6 +726,10 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FramePar
             hit_any = idx >= 0;
         }
         warp_append(hit_any, s, P.q_hit, &P.counters[kCntHit + level]);
+        if (P.n_always > 0) {
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if ((threadIdx.x & 31) == 0 && m) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)__popc(m) * (unsigned long long)P.n_always);
+        }
     }
 }
 
@@ -791,6 +804,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
             if (NEAREST) {
                 int idx = best[k];
                 float dbest = dist[k];
+                for (int a = 0; a < P.n_always; ++a) {
+                    const int tri = (int)P.always_list[a];
+                    const float4 e = exact_eval_tri(P.triv, tri, O.x, O.y, O.z, D.x, D.y, D.z);
+                    if (!(e.w < 0.0f) && (e.w < dbest || (e.w == dbest && tri < idx))) { dbest = e.w; idx = tri; }
+                }
                 for (int sph = 0; sph < P.nspheres; ++sph) {
                     const float4 c = P.spheres[2 * sph];
                     v3 Is;
@@ -809,12 +827,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
                 }
             } else {
                 lit = (live >> k) & 1u;  // still alive after every triangle of this part: no occluder found here
-                if (part == 0)
+                if (part == 0) {
+                    for (int a = 0; lit && a < P.n_always; ++a) {
+                        const float4 e = exact_eval_tri(P.triv, (int)P.always_list[a], O.x, O.y, O.z, D.x, D.y, D.z);
+                        if (e.w >= 0.0f && e.w < FLT_MAX) lit = false;
+                    }
                     for (int sph = 0; lit && sph < P.nspheres; ++sph) {
                         const float4 c = P.spheres[2 * sph];
                         v3 Is;
                         if (exact_ray_sphere(O, D, mk3(c), c.w, Is) && e_distance(O, Is) < FLT_MAX) lit = false;
                     }
+                }
             }
             if (!lit) atomicAnd(&P.lit[sid[k]], ~(1u << lid[k]));
         }
