@@ -111,7 +111,7 @@ def make_params(corners, W, H, pfx=1, pfy=None, max_lvl=10, features=RT_ALL_FEAT
     cam = np.asarray(camera, np.float32)
     for i in range(3):
         p.camera[i] = float(cam[i])
-    lights = np.asarray([cam] if lights is None else lights, np.float32).reshape(-1, 3)
+    lights = np.asarray([cam] if lights is None else lights, np.float32).reshape(-1, 3)   # None: one light at the camera
     if len(lights) > RT_MAX_LIGHTS:
         raise ValueError("too many lights")
     p.n_lights = len(lights)

@@ -433,3 +433,73 @@ def test_fine_mesh_uses_the_clause_free_kernels(gpu, port):
     # large triangles: never
     gpu_render(gpu, load_scene("cube"), load_case("cube_default_64"))
     assert not (gpu.stats()["variant"] & 1)
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("RT_FUZZ_SEEDS", "24"))))
+def test_fuzz_random_scenes(gpu, port, seed):
+    """Seeded random scenes / cameras / lights / feature masks / materials (incl. transparent ones and analytic
+    spheres), brute force or tile culling: primary ids and ray counts identical to the oracle, colours within tolerance."""
+    import ctypes as C
+    from raytracert_b200 import binding, host
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 500))
+    kind = seed % 4
+    ctr = rng.uniform(-1.5, 1.5, (n, 1, 3))
+    size = 10 ** rng.uniform(-2.0, 0.2, (n, 1, 1)) if kind != 1 else np.full((n, 1, 1), 0.08)   # kind 1: fine mesh (clause-free kernels)
+    tri = ctr + size * rng.normal(size=(n, 3, 3))
+    if kind == 2:   # axis-aligned boxes of triangles + exact duplicates (distance ties between different ids)
+        tri = np.round(tri * 4) / 4
+        tri = np.concatenate([tri, tri[: max(1, n // 5)]])
+    if kind == 3 and n > 4:   # degenerate / sliver / NaN members
+        tri[0, 2] = tri[0, 1]
+        tri[1, 2] = tri[1, 0] + (tri[1, 1] - tri[1, 0]) * 0.5
+        tri[2, 2] = tri[2, 1] + 1e-6 * (tri[2, 0] - tri[2, 1])
+        tri[3, 0, 0] = np.nan
+    v = tri.reshape(-1, 3).astype(np.float32)
+    idx = np.arange(len(v), dtype=np.uint32).reshape(-1, 3)
+    nm = int(rng.integers(1, 5))
+    mats = np.zeros((nm, 16), np.float32)
+    for m in mats:
+        m[0:3] = rng.uniform(0, 1, 3); m[3] = rng.choice([0.0, 5.0, 40.0, 96.0]); m[4:7] = rng.uniform(0, 0.1, 3)
+        m[7] = rng.choice([1.0, 1.3, 1.5]); m[8:11] = rng.uniform(0, 0.9, 3)
+        m[11] = rng.choice([1.0, 1.0, 0.5, 0.0]); m[12] = float(rng.choice([63, 63, 63, 15, 13, 47, 1]))
+    s = host.Scene(v, idx, rng.integers(0, nm, len(idx)).astype(np.uint32), host.face_normals(v, idx), mats)
+    nsph = int(rng.integers(0, 3)) if seed % 3 == 0 else 0
+    sph = np.zeros((nsph, 5), np.float32)
+    for r in sph:
+        r[0:3] = rng.uniform(-1, 1, 3); r[3] = rng.uniform(0.1, 0.5); r[4] = rng.integers(0, nm)
+    s.spheres = sph
+    W, H = int(rng.integers(8, 72)), int(rng.integers(8, 60))
+    pfx, pfy = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    eye = rng.uniform(-1, 1, 3) + np.array([0, 0, 5.0]) if seed % 5 else rng.uniform(-0.5, 0.5, 3)   # sometimes inside the soup
+    cam = host.Camera(W, H, tuple(eye), tuple(rng.uniform(-0.5, 0.5, 3)))
+    lights = rng.uniform(-6, 6, (int(rng.integers(0, 4)), 3)).astype(np.float32)
+    if seed == 7:
+        lights = np.array([[300.0, 500.0, 200.0]], np.float32)     # far light
+    feats = int(rng.integers(0, 64)) if seed % 2 else 63
+    lvl = int(rng.integers(0, 7))
+    port.set_scene(s)
+    port.L.orc_set_spheres.argtypes = [C.c_int, C.c_void_p]
+    port.L.orc_set_spheres(nsph, sph.ctypes.data)
+    try:
+        port.configure(cam.eye, lights.reshape(-1, 3) if len(lights) else np.zeros((0, 3), np.float32), feats, lvl)
+        port.reset_counts()
+        rgb_o, _, prim_o = port.render(cam.corners, W, H, pfx, pfy, want_samples=True)
+        counts = port.ray_counts()
+    finally:
+        port.L.orc_set_spheres(0, sph.ctypes.data)
+    c = dict(corners=cam.corners, W=W, H=H, pfx=pfx, pfy=pfy, max_lvl=lvl, features=feats, eye=cam.eye, lights=lights)
+    try:
+        gpu.set_option(binding.RT_OPT_TILE_CULLING, seed & 1)
+        gpu.upload_scene(s)
+        p = binding.make_params(cam.corners, W, H, pfx, pfy, lvl, feats, cam.eye, lights if len(lights) else np.zeros((0, 3), np.float32), want_prim_id=True)
+        gpu.render(p)
+        rgb, prim = gpu.download(want_prim_id=True)
+        st = gpu.stats()
+    finally:
+        gpu.set_option(binding.RT_OPT_TILE_CULLING, 0)
+    assert np.array_equal(prim, prim_o), f"{np.count_nonzero(prim != prim_o)} ids differ"
+    ok = np.isfinite(rgb_o)
+    assert np.array_equal(np.isfinite(rgb), ok)
+    assert np.abs(rgb[ok] - rgb_o[ok]).max() <= 5e-5
+    assert (st["primary_rays"], st["shadow_rays"], st["bounce_rays"]) == counts
