@@ -22,7 +22,7 @@ using namespace rt;
 // Scan-kernel shapes compiled into the library: (ray pairs per thread, triangles per filter block,
 // resident CTAs per SM).  The first entry is the default; RT_B200_TUNE="rp,j,minb" selects another
 // (tools/tune.py sweeps them on the GPU).
-#define RT_SCAN_CONFIGS(X) X(2, 8, 2) X(2, 4, 2) X(1, 16, 4)
+#define RT_SCAN_CONFIGS(X) X(2, 8, 2) X(1, 16, 4)
 struct ScanConfig { int rp, j, minb; };
 constexpr uint32_t kMaxChunkSamples = 1u << 23;  // 8 Mi samples per wavefront chunk (84 B of state each)
 
@@ -66,8 +66,8 @@ struct RtDevice {
     cudaStream_t stream = nullptr;
     ncclComm_t comm = nullptr;
     // scene
-    float4 *rec = nullptr, *triv = nullptr, *normal_mat = nullptr, *materials = nullptr, *spheres = nullptr, *tile_box = nullptr;
-    size_t cap_box = 0;
+    float4 *rec = nullptr, *triv = nullptr, *normal_mat = nullptr, *materials = nullptr, *spheres = nullptr, *tile_box = nullptr, *super_box = nullptr;
+    size_t cap_box = 0, cap_super = 0;
     size_t cap_rec = 0, cap_triv = 0, cap_nm = 0, cap_mat = 0, cap_sph = 0;  // in float4; buffers are reused across uploads
     int ntri = 0, ntiles = 0, nmat = 0, nspheres = 0;
     int cls1 = 0, cls2 = 0;             // first tile of dominant-axis class 1 / 2
@@ -173,7 +173,7 @@ int create_device(RtDevice& d, int device, int rank) {
 void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
-    void* ptrs[] = {d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+    void* ptrs[] = {d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
                     d.q_hit, d.key, d.hit0, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -198,19 +198,24 @@ struct LaunchTimer {
     ~LaunchTimer() { if (timed) cudaEventRecord(d.kev[2 * (d.kev_kind.size() - 1) + 1], d.stream); }
 };
 
-template <int RP, int J, int MINB, bool GRAZ>
-void launch_scan_g(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
+template <int RP, int J, int MINB, bool GRAZ, bool CULL>
+void launch_scan_gc(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
     switch (which) {
-        case 0: k_trace<RP, J, MINB, true, GRAZ><<<grid, kThreads, 0, st>>>(P, level); break;
-        case 1: k_trace<RP, J, MINB, false, GRAZ><<<grid, kThreads, 0, st>>>(P, level); break;
-        case 2: k_shadow<RP, J, MINB, false, GRAZ><<<grid, kThreads, 0, st>>>(P, level); break;
-        default: k_shadow<RP, J, MINB, true, GRAZ><<<grid, kThreads, 0, st>>>(P, level); break;
+        case 0: k_trace<RP, J, MINB, true, GRAZ, CULL><<<grid, kThreads, 0, st>>>(P, level); break;
+        case 1: k_trace<RP, J, MINB, false, GRAZ, CULL><<<grid, kThreads, 0, st>>>(P, level); break;
+        case 2: k_shadow<RP, J, MINB, false, GRAZ, CULL><<<grid, kThreads, 0, st>>>(P, level); break;
+        default: k_shadow<RP, J, MINB, true, GRAZ, CULL><<<grid, kThreads, 0, st>>>(P, level); break;
     }
 }
 template <int RP, int J, int MINB>
 void launch_scan(int which, int grid, cudaStream_t st, const FrameParams& P, int level, bool grazing_clause) {
-    if (grazing_clause) launch_scan_g<RP, J, MINB, true>(which, grid, st, P, level);
-    else launch_scan_g<RP, J, MINB, false>(which, grid, st, P, level);
+    if (P.cull) {
+        if (grazing_clause) launch_scan_gc<RP, J, MINB, true, true>(which, grid, st, P, level);
+        else launch_scan_gc<RP, J, MINB, false, true>(which, grid, st, P, level);
+    } else {
+        if (grazing_clause) launch_scan_gc<RP, J, MINB, true, false>(which, grid, st, P, level);
+        else launch_scan_gc<RP, J, MINB, false, false>(which, grid, st, P, level);
+    }
 }
 enum { kScanPrimary = 0, kScanBounce = 1, kScanShadowAny = 2, kScanShadowNearest = 3 };
 
@@ -288,6 +293,11 @@ int build_records(RtDevice& d, float M, float dir_max) {
     const int tiles_padded = d.ntiles + kPadTiles;
     k_build_tile_boxes<<<(tiles_padded + 127) / 128, 128, 0, d.stream>>>(d.triv, d.rec, tiles_padded, M, d.tile_box);
     CU(cudaGetLastError());
+    const int nsuper = (tiles_padded + kSuper - 1) / kSuper;
+    rc = ensure(d.super_box, d.cap_super, (size_t)nsuper * 2);
+    if (rc) return rc;
+    k_build_super_boxes<<<(nsuper + 127) / 128, 128, 0, d.stream>>>(d.tile_box, tiles_padded, nsuper, d.super_box);
+    CU(cudaGetLastError());
     d.M_built = M;
     d.dir_built = dir_max;
     return RT_OK;
@@ -326,7 +336,8 @@ void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float e
     P.ntri = d.ntri; P.ntiles = d.ntiles; P.nspheres = d.nspheres; P.cls1 = d.cls1; P.cls2 = d.cls2;
     P.ray_o = d.ray_o; P.ray_d = d.ray_d; P.thr = d.thr; P.acc = d.acc; P.hit = d.hit; P.lit = d.lit;
     P.q_ray = d.q_ray; P.q_hit = d.q_hit; P.counters = counters; P.key = d.key;
-    P.tile_box = d.tile_box; P.cull = g.tile_culling ? 1 : 0;
+    P.tile_box = d.tile_box; P.super_box = d.super_box;
+    P.cull = (g.tile_culling && d.ntiles <= kCullMaxTiles) ? 1 : 0;   // beyond the bitmap's reach: brute force
     P.always_list = d.always_list; P.n_always = d.n_always_host;
     P.eps_r = eps_r;
     memcpy(P.camera, rp.camera, sizeof(P.camera));

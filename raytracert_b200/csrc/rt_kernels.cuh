@@ -39,6 +39,9 @@ constexpr int kMaxParts = 64;      // a launch with few rays splits the triangle
 constexpr uint32_t kItemsPerCta = 24;   // load-balance target of make_split
 constexpr uint32_t kMinPartTiles = 8;   // >= 1024 triangles per part unless the launch is tiny
 constexpr int kPadTiles = kMaxParts;  // "never" tiles appended to the record array so that every part has the same length
+constexpr int kSuper = 32;              // tiles per super-tile (hierarchical tile culling)
+constexpr int kCullMaxTiles = 16384;    // the CTA-level "needed tiles" bitmap covers this many tiles (2.1 M triangles)
+constexpr int kCullList = 4096;         // needed tiles streamed per batch
 constexpr unsigned long long kKeyEmpty = ~0ull;  // (distance bits << 32 | primitive id); all ones = no hit yet
 
 constexpr float kU32 = 5.9604645e-8f;  // 2^-24
@@ -74,7 +77,8 @@ struct FrameParams {
     const uint32_t* always_list;  // triangles the filter cannot bound ("always exact"): evaluated per ray outside the scan
     int n_always;
     const float4* tile_box;     // 2 float4 per tile: conservative AABB (lo, hi) of the tile's candidate region
-    int cull;                   // RT_OPT_TILE_CULLING: warps skip tiles whose box none of their rays can reach
+    int cull;                   // RT_OPT_TILE_CULLING in effect for this launch (the CULL = true kernel instantiations)
+    const float4* super_box;    // 2 float4 per super-tile (kSuper tiles)
     int32_t* prim_out;          // optional: primary primitive id per local sample
     // frame
     float corners[24];
@@ -224,6 +228,20 @@ __global__ void k_build_tile_boxes(const float4* __restrict__ triv, const float4
     tile_box[2 * tile + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
 }
 
+// Super-tile boxes: union of kSuper consecutive tile boxes (tiles are Morton-sorted when the option was set before the upload).
+__global__ void k_build_super_boxes(const float4* __restrict__ tile_box, int ntiles_padded, int nsuper, float4* __restrict__ super_box) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nsuper) return;
+    const float inf = __int_as_float(0x7f800000);
+    float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
+    for (int t = g * kSuper; t < min((g + 1) * kSuper, ntiles_padded); ++t) {
+        const float4 a = tile_box[2 * t], b = tile_box[2 * t + 1];
+        lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+        hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
+    }
+    super_box[2 * g] = lo; super_box[2 * g + 1] = hi;
+}
+
 // Slab test of the half-line O' + t d, 0 <= t < rhi, against a box.  NaN-safe in the conservative direction:
 // fminf/fmaxf drop NaN operands (0 * inf on a slab boundary), and a ray whose direction is NaN (dead slot) is
 // filtered by the caller's live mask.
@@ -260,6 +278,17 @@ struct __align__(128) ScanSmem {
     unsigned long long full[kStages];
     unsigned int done[kStages];
 };
+// tile culling only (CULL = true kernels): tiles some ray of this CTA can reach (bitmap), and the batch being streamed
+struct CullSmem {
+    unsigned int need[kCullMaxTiles / 32];
+    unsigned short list[kCullList];
+    unsigned int list_n, list_next;
+};
+
+
+// Shared-memory block of the culling path, present only in the CULL = true kernel instantiations.
+template <bool CULL> struct CullStorage { CullSmem s; __device__ CullSmem& get() { return s; } __device__ const unsigned short* list() { return s.list; } };
+template <> struct CullStorage<false> { __device__ CullSmem& get() { return *reinterpret_cast<CullSmem*>(this); } __device__ const unsigned short* list() { return nullptr; } };
 
 // Work decomposition of one scan launch.  count rays -> nchunks chunks of kThreads*R rays; when there are fewer chunks
 // than CTAs the triangle tiles are split into `parts` ranges of `len` tiles each (the record array carries kPadTiles
@@ -294,16 +323,24 @@ struct Pipe {
     const float4* tiles_ptr;
     const float4* rec;
     uint32_t parts, len;   // see Split
-    uint32_t total_iters;  // tiles this CTA will consume over its whole life
+    uint32_t total_iters;  // tiles this CTA will consume over its whole life (range mode) / end of the current batch (list mode)
     uint32_t it;           // next iteration
+    const unsigned short* list;  // list mode (hierarchical culling): tile of iteration i is list[i - base]; nullptr = range mode
+    uint32_t base;
 };
 
+template <bool LIST>
 __device__ __forceinline__ void pipe_issue(const Pipe& p, uint32_t iter) {
     const uint32_t stage = iter % kStages;
     const uint32_t bar = p.full_addr + stage * 8u;
-    const uint32_t q = iter / p.len;                                   // this CTA's q-th work item
-    const uint32_t item = blockIdx.x + q * gridDim.x;
-    const uint32_t tile = (item % p.parts) * p.len + (iter - q * p.len);
+    uint32_t tile;
+    if (LIST) {
+        tile = p.list[iter - p.base];
+    } else {
+        const uint32_t q = iter / p.len;                               // this CTA's q-th work item
+        const uint32_t item = blockIdx.x + q * gridDim.x;
+        tile = (item % p.parts) * p.len + (iter - q * p.len);
+    }
     // generic-proxy reads of this stage (all warps are past it) are ordered before the async-proxy write
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive_expect_tx(bar, kTileBytes);
@@ -314,7 +351,9 @@ __device__ __forceinline__ uint32_t cta_items(uint32_t nitems) {
     return (nitems > blockIdx.x) ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 }
 
-__device__ __forceinline__ void pipe_init(Pipe& p, ScanSmem& sm, const float4* rec, const Split& sp) {
+// list_mode: nothing is prefetched here; every batch is started by pipe_begin_batch().
+template <bool LIST>
+__device__ __forceinline__ void pipe_init(Pipe& p, ScanSmem& sm, const float4* rec, const Split& sp, const unsigned short* list) {
     p.tiles_addr = smem_u32(&sm.tiles[0][0]);
     p.full_addr = smem_u32(&sm.full[0]);
     p.done = sm.done;
@@ -322,8 +361,10 @@ __device__ __forceinline__ void pipe_init(Pipe& p, ScanSmem& sm, const float4* r
     p.rec = rec;
     p.parts = sp.parts;
     p.len = sp.len;
-    p.total_iters = cta_items(sp.nitems) * sp.len;
+    p.total_iters = LIST ? 0u : cta_items(sp.nitems) * sp.len;
     p.it = 0;
+    p.list = list;
+    p.base = 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(p.full_addr + s * 8u, 1); sm.done[s] = 0; }
         mbar_fence_init();
@@ -331,7 +372,18 @@ __device__ __forceinline__ void pipe_init(Pipe& p, ScanSmem& sm, const float4* r
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t n = p.total_iters < (uint32_t)kStages ? p.total_iters : (uint32_t)kStages;
-        for (uint32_t i = 0; i < n; ++i) pipe_issue(p, i);
+        for (uint32_t i = 0; i < n; ++i) pipe_issue<LIST>(p, i);
+    }
+}
+
+// List mode: the n tiles of the list are the next n iterations.  Call from all threads after a __syncthreads() that
+// follows both the list construction and every warp's release of the previous batch.
+__device__ __forceinline__ void pipe_begin_batch(Pipe& p, uint32_t n) {
+    p.base = p.it;
+    p.total_iters = p.it + n;
+    if (threadIdx.x == 0) {
+        const uint32_t m = n < (uint32_t)kStages ? n : (uint32_t)kStages;
+        for (uint32_t i = 0; i < m; ++i) pipe_issue<true>(p, p.it + i);
     }
 }
 
@@ -341,6 +393,7 @@ __device__ __forceinline__ const float4* pipe_acquire(const Pipe& p) {
     return p.tiles_ptr + stage * (kTile * kRecVec);
 }
 
+template <bool LIST>
 __device__ __forceinline__ void pipe_release(Pipe& p) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
@@ -348,7 +401,7 @@ __device__ __forceinline__ void pipe_release(Pipe& p) {
         const unsigned int prev = atomicAdd(&p.done[stage], 1u);
         if ((prev % kWarps) == kWarps - 1) {  // every warp has finished reading this stage
             const uint32_t nxt = p.it + kStages;
-            if (nxt < p.total_iters) pipe_issue(p, nxt);
+            if (nxt < p.total_iters) pipe_issue<LIST>(p, nxt);
         }
     }
     ++p.it;
@@ -517,38 +570,102 @@ __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, f
     }
 }
 
-// Scans the tiles [tile_begin, tile_begin + pipe.len) of one work item.  NEAREST: keeps (dist, best) like
-// intersectMesh; !NEAREST: any-hit, a ray dies at its first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
-// cls_end[0..1]: first tile of class 1 / class 2 (tiles are grouped by the dominant axis of their triangles).
+// Does any live ray of this thread reach the box?
+template <int RP>
+__device__ __forceinline__ bool thread_reaches_box(const FastRays<RP>& fr, uint32_t live, const float4& lo, const float4& hi) {
+    bool need = false;
+#pragma unroll
+    for (int k = 0; k < 2 * RP; ++k) {
+        const int p = k / 2;
+        const bool odd = k & 1;
+        const bool reach = ray_reaches_box(odd ? fr.ox[p].y : fr.ox[p].x, odd ? fr.oy[p].y : fr.oy[p].x, odd ? fr.oz[p].y : fr.oz[p].x,
+                                           odd ? fr.dx[p].y : fr.dx[p].x, odd ? fr.dy[p].y : fr.dy[p].x, odd ? fr.dz[p].y : fr.dz[p].x,
+                                           __uint_as_float(fr.rhi[k]), lo, hi);
+        need = need || (reach && ((live >> k) & 1u));
+    }
+    return need;
+}
+
+// Tile culling (RT_OPT_TILE_CULLING, scenes of <= kCullMaxTiles tiles; larger scenes are scanned brute force) for one work item:
+//   1. every warp walks the super-tile boxes (kSuper tiles each) of the item's tile range and, inside the super-tiles
+//      one of its rays reaches, the tile boxes; reached tiles are marked in a CTA-wide bitmap;
+//   2. the bitmap is compacted into batches of <= kCullList tile ids;
+//   3. only those tiles are streamed through the TMA ring; a warp still re-tests a tile's box against its own rays
+//      (with the nearest-hit bound as it is by then) before scanning it.
+// Same filter + exact tiers as scan_pass on every tile that is not skipped, so the results are identical.
+template <int RP, int J, bool NEAREST, bool GRAZ, class Fetch>
+__device__ __forceinline__ void scan_item_culled(Pipe& pipe, CullSmem& sm, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
+                                                 const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact, int tile_begin,
+                                                 int tile_end, const float4* __restrict__ tile_box, const float4* __restrict__ super_box, int cls1, int cls2) {
+    const int lane = threadIdx.x & 31;
+    const int w0 = tile_begin / 32, w1 = (tile_end + 31) / 32;   // bitmap words of the range
+    __syncthreads();   // every warp is done with the previous item's bitmap / list / ring
+    for (int w = w0 + (int)threadIdx.x; w < w1; w += kThreads) sm.need[w] = 0u;
+    if (threadIdx.x == 0) sm.list_next = (unsigned int)w0;
+    __syncthreads();
+    // 1. mark
+    for (int g = tile_begin / kSuper; g * kSuper < tile_end; ++g) {
+        const float4 slo = __ldg(&super_box[2 * g]), shi = __ldg(&super_box[2 * g + 1]);
+        if (!__any_sync(0xffffffffu, thread_reaches_box<RP>(fr, live, slo, shi))) continue;
+        const int t0 = max(g * kSuper, tile_begin), t1 = min((g + 1) * kSuper, tile_end);
+        unsigned int bits = 0u;
+        for (int t = t0; t < t1; ++t) {
+            const float4 lo = __ldg(&tile_box[2 * t]), hi = __ldg(&tile_box[2 * t + 1]);
+            if (__any_sync(0xffffffffu, thread_reaches_box<RP>(fr, live, lo, hi))) bits |= 1u << (t & 31);
+        }
+        if (lane == 0 && bits) atomicOr(&sm.need[g * kSuper / 32], bits);   // kSuper == 32: one word per super-tile
+    }
+    // 2. + 3. batches
+    for (;;) {
+        __syncthreads();   // marks complete (first round) / previous batch fully consumed and released
+        if (threadIdx.x < 32) {   // warp 0 compacts the next batch, word by word
+            unsigned int n = 0;
+            int w = (int)sm.list_next;
+            while (w < w1 && n + 32 <= (unsigned int)kCullList) {
+                unsigned int word = sm.need[w];
+                const bool mine = (word >> lane) & 1u;
+                const unsigned int pos = n + __popc(word & ((1u << lane) - 1u));
+                if (mine) sm.list[pos] = (unsigned short)(w * 32 + lane);
+                n += __popc(word);
+                ++w;
+            }
+            if (lane == 0) { sm.list_n = n; sm.list_next = (unsigned int)w; }
+        }
+        __syncthreads();
+        const uint32_t n = sm.list_n;
+        if (n == 0 && (int)sm.list_next >= w1) break;
+        pipe_begin_batch(pipe, n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const float4* rec = pipe_acquire(pipe);
+            const int tile = (int)sm.list[i];
+            const float4 lo = __ldg(&tile_box[2 * tile]), hi = __ldg(&tile_box[2 * tile + 1]);
+            if (__any_sync(0xffffffffu, thread_reaches_box<RP>(fr, live, lo, hi))) {
+                if (tile < cls1) scan_tile<RP, J, NEAREST, 0, GRAZ>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+                else if (tile < cls2) scan_tile<RP, J, NEAREST, 1, GRAZ>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+                else scan_tile<RP, J, NEAREST, 2, GRAZ>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+            }
+            pipe_release<true>(pipe);
+        }
+        if ((int)sm.list_next >= w1) break;
+    }
+}
+
+// Scans the tiles [tile_begin, tile_begin + pipe.len) of one work item (brute force: every tile).  NEAREST: keeps
+// (dist, best) like intersectMesh; !NEAREST: any-hit, a ray dies at its first exact hit.  fetch(k, O, D) returns the
+// exact ray of slot k.  cls1 / cls2: first tile of class 1 / class 2 (tiles are grouped by the dominant axis of their triangles).
 template <int RP, int J, bool NEAREST, bool GRAZ, class Fetch>
 __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
                                           const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact, int tile_begin,
-                                          const float4* __restrict__ tile_box, int cls1, int cls2) {
-    constexpr int R = 2 * RP;
+                                          int cls1, int cls2) {
     for (int tile = tile_begin; tile < tile_begin + (int)pipe.len; ++tile) {
         const float4* rec = pipe_acquire(pipe);
-        // does any live ray of this warp reach the tile?  (always, without tile culling)
-        bool need = live != 0u;
-        if (tile_box != nullptr && need) {
-            const float4 lo = __ldg(&tile_box[2 * tile]), hi = __ldg(&tile_box[2 * tile + 1]);
-            need = false;
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-                const int p = k / 2;
-                const bool odd = k & 1;
-                const bool reach = ray_reaches_box(odd ? fr.ox[p].y : fr.ox[p].x, odd ? fr.oy[p].y : fr.oy[p].x, odd ? fr.oz[p].y : fr.oz[p].x,
-                                                   odd ? fr.dx[p].y : fr.dx[p].x, odd ? fr.dy[p].y : fr.dy[p].x, odd ? fr.dz[p].y : fr.dz[p].x,
-                                                   __uint_as_float(fr.rhi[k]), lo, hi);
-                need = need || (reach && ((live >> k) & 1u));
-            }
-        }
-        // warp-level early exit: shadow rays that all found their occluder, or a tile no ray of the warp can reach
-        if (__any_sync(0xffffffffu, need)) {
+        // warp-level early exit: shadow rays that all found their occluder
+        if (__any_sync(0xffffffffu, live != 0u)) {
             if (tile < cls1) scan_tile<RP, J, NEAREST, 0, GRAZ>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
             else if (tile < cls2) scan_tile<RP, J, NEAREST, 1, GRAZ>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
             else scan_tile<RP, J, NEAREST, 2, GRAZ>(rec, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
         }
-        pipe_release(pipe);
+        pipe_release<false>(pipe);
     }
 }
 
@@ -613,15 +730,16 @@ __device__ __forceinline__ void fast_set_slot(FastRays<RP>& fr, int k, v3 O, v3 
     if (k == 7) fast_set<RP, (R > 6 ? 7 : 0)>(fr, O, D, eps_r, ok);
 }
 
-template <int RP, int J, int MINB, bool PRIMARY, bool GRAZ>
+template <int RP, int J, int MINB, bool PRIMARY, bool GRAZ, bool CULL>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant__ FrameParams P, int level) {
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
+    __shared__ CullStorage<CULL> csm;
     const uint32_t count = PRIMARY ? P.nslots : P.counters[kCntRay + level];
     const uint32_t per_chunk = kThreads * R;
     const Split sp = make_split(count, per_chunk, P.ntiles, true);
     Pipe pipe;
-    pipe_init(pipe, sm, P.rec, sp);
+    pipe_init<CULL>(pipe, sm, P.rec, sp, csm.list());
     uint32_t n_exact = 0;
     const float eps_r2 = 2.0f * P.eps_r;
 
@@ -666,7 +784,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
             if (PRIMARY && !P.trace_api) { primary_ray(P, sid[k], O, D); }
             else { const float4 o = P.ray_o[sid[k]], d = P.ray_d[sid[k]]; O = mk3(o); D = mk3(d); }
         };
-        scan_pass<RP, J, true, GRAZ>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr, P.cls1, P.cls2);
+        if (CULL)
+            scan_item_culled<RP, J, true, GRAZ>(pipe, csm.get(), fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len),
+                                                min((int)((part + 1) * sp.len), P.ntiles), P.tile_box, P.super_box, P.cls1, P.cls2);
+        else
+            scan_pass<RP, J, true, GRAZ>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cls1, P.cls2);
 
         // merge: (distance bits, triangle id) -- the smallest distance wins, equal distances go to the lowest
         // index, which is exactly the sequential rule of intersectMesh (strict <, raytracing.cpp:183)
@@ -751,16 +873,17 @@ struct FetchShadow {
     }
 };
 
-template <int RP, int J, int MINB, bool NEAREST, bool GRAZ>
+template <int RP, int J, int MINB, bool NEAREST, bool GRAZ, bool CULL>
 __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant__ FrameParams P, int level) {
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
+    __shared__ CullStorage<CULL> csm;
     const uint32_t nl = (uint32_t)P.nlights;
     const uint32_t count = P.counters[kCntHit + level] * nl;
     const uint32_t per_chunk = kThreads * R;
     const Split sp = make_split(count, per_chunk, P.ntiles, !NEAREST);
     Pipe pipe;
-    pipe_init(pipe, sm, P.rec, sp);
+    pipe_init<CULL>(pipe, sm, P.rec, sp, csm.list());
     uint32_t n_exact = 0;
     const float eps_r2 = 2.0f * P.eps_r;
 
@@ -793,7 +916,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
         }
         const uint32_t valid = live;
         FetchShadow fetch{P.hit, sid, light};
-        scan_pass<RP, J, NEAREST, GRAZ>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cull ? P.tile_box : nullptr, P.cls1, P.cls2);
+        if (CULL)
+            scan_item_culled<RP, J, NEAREST, GRAZ>(pipe, csm.get(), fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len),
+                                                   min((int)((part + 1) * sp.len), P.ntiles), P.tile_box, P.super_box, P.cls1, P.cls2);
+        else
+            scan_pass<RP, J, NEAREST, GRAZ>(pipe, fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len), P.cls1, P.cls2);
 
 #pragma unroll
         for (int k = 0; k < R; ++k) {
