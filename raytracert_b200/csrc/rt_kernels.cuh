@@ -286,6 +286,31 @@ struct CullSmem {
 };
 
 
+// Per-ray state that only the cold path and the epilogues touch (nearest distance, nearest triangle, sample id).
+// In the brute-force kernels it lives in shared memory, one column per thread, which frees 3*R registers for the
+// filter loop; the culling kernels (whose shared memory is taken by the tile list) keep it in registers.
+template <int R> struct ColdSmem { float dist[R][kThreads]; int best[R][kThreads]; uint32_t sid[R][kThreads]; };
+template <class T> struct SmemCol {
+    T (*col)[kThreads];
+    __device__ __forceinline__ T& operator[](int k) const { return col[k][threadIdx.x]; }
+};
+template <class T, int R> struct RegCol {
+    T v[R];
+    __device__ __forceinline__ T& operator[](int k) { return v[k]; }
+    __device__ __forceinline__ const T& operator[](int k) const { return v[k]; }
+};
+template <int R, bool IN_SMEM> struct ColdState;
+template <int R> struct ColdState<R, true> {
+    SmemCol<float> dist; SmemCol<int> best; SmemCol<uint32_t> sid;
+    __device__ __forceinline__ explicit ColdState(ColdSmem<R>* s) : dist{s->dist}, best{s->best}, sid{s->sid} {}
+};
+template <int R> struct ColdState<R, false> {
+    RegCol<float, R> dist; RegCol<int, R> best; RegCol<uint32_t, R> sid;
+    __device__ __forceinline__ explicit ColdState(ColdSmem<R>*) {}
+};
+template <int R, bool PRESENT> struct ColdStorage { ColdSmem<R> s; __device__ ColdSmem<R>* get() { return &s; } };
+template <int R> struct ColdStorage<R, false> { __device__ ColdSmem<R>* get() { return nullptr; } };
+
 // Shared-memory block of the culling path, present only in the CULL = true kernel instantiations.
 template <bool CULL> struct CullStorage { CullSmem s; __device__ CullSmem& get() { return s; } __device__ const unsigned short* list() { return s.list; } };
 template <> struct CullStorage<false> { __device__ CullSmem& get() { return *reinterpret_cast<CullSmem*>(this); } __device__ const unsigned short* list() { return nullptr; } };
@@ -498,8 +523,8 @@ struct BitLayout {
 // Scans all tiles of one pass.  NEAREST: keeps (dist, best) exactly like intersectMesh; !NEAREST: any-hit,
 // clears the ray's live bit on the first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
 // One tile (kTile records of dominant-axis class W) against this thread's R rays.
-template <int RP, int J, bool NEAREST, int W, bool GRAZ, class Fetch>
-__device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
+template <int RP, int J, bool NEAREST, int W, bool GRAZ, class DistT, class BestT, class Fetch>
+__device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, DistT& dist, BestT& best, uint32_t& live,
                                           const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact) {
     constexpr int R = 2 * RP;
     constexpr uint32_t REP = BitLayout<RP, J>::kRep;
@@ -593,8 +618,8 @@ __device__ __forceinline__ bool thread_reaches_box(const FastRays<RP>& fr, uint3
 //   3. only those tiles are streamed through the TMA ring; a warp still re-tests a tile's box against its own rays
 //      (with the nearest-hit bound as it is by then) before scanning it.
 // Same filter + exact tiers as scan_pass on every tile that is not skipped, so the results are identical.
-template <int RP, int J, bool NEAREST, bool GRAZ, class Fetch>
-__device__ __forceinline__ void scan_item_culled(Pipe& pipe, CullSmem& sm, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
+template <int RP, int J, bool NEAREST, bool GRAZ, class DistT, class BestT, class Fetch>
+__device__ __forceinline__ void scan_item_culled(Pipe& pipe, CullSmem& sm, FastRays<RP>& fr, DistT& dist, BestT& best, uint32_t& live,
                                                  const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact, int tile_begin,
                                                  int tile_end, const float4* __restrict__ tile_box, const float4* __restrict__ super_box, int cls1, int cls2) {
     const int lane = threadIdx.x & 31;
@@ -653,8 +678,8 @@ __device__ __forceinline__ void scan_item_culled(Pipe& pipe, CullSmem& sm, FastR
 // Scans the tiles [tile_begin, tile_begin + pipe.len) of one work item (brute force: every tile).  NEAREST: keeps
 // (dist, best) like intersectMesh; !NEAREST: any-hit, a ray dies at its first exact hit.  fetch(k, O, D) returns the
 // exact ray of slot k.  cls1 / cls2: first tile of class 1 / class 2 (tiles are grouped by the dominant axis of their triangles).
-template <int RP, int J, bool NEAREST, bool GRAZ, class Fetch>
-__device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, float (&dist)[2 * RP], int (&best)[2 * RP], uint32_t& live,
+template <int RP, int J, bool NEAREST, bool GRAZ, class DistT, class BestT, class Fetch>
+__device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, DistT& dist, BestT& best, uint32_t& live,
                                           const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact, int tile_begin,
                                           int cls1, int cls2) {
     for (int tile = tile_begin; tile < tile_begin + (int)pipe.len; ++tile) {
@@ -735,6 +760,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
     __shared__ CullStorage<CULL> csm;
+    __shared__ ColdStorage<R, !CULL> cold;
     const uint32_t count = PRIMARY ? P.nslots : P.counters[kCntRay + level];
     const uint32_t per_chunk = kThreads * R;
     const Split sp = make_split(count, per_chunk, P.ntiles, true);
@@ -746,9 +772,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
     for (uint32_t item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
         const uint32_t chunk = item / sp.parts, part = item - chunk * sp.parts;
         FastRays<RP> fr;
-        float dist[R];
-        int best[R];
-        uint32_t sid[R];
+        ColdState<R, !CULL> st(cold.get());
+        auto& dist = st.dist; auto& best = st.best; auto& sid = st.sid;
         uint32_t live = 0;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
@@ -862,22 +887,12 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FramePar
 //   NEAREST : the nearest occluder's material decides (transparent -> lit); never split.
 // lit[] arrives with every light's bit set (k_finish); occluded lights are cleared here.
 // ------------------------------------------------------------------------------------------------
-struct FetchShadow {
-    const float4* hit;
-    const uint32_t* sid;
-    const v3* light;
-    __device__ __forceinline__ void operator()(int k, v3& O, v3& D) const {
-        const float4 h = hit[sid[k]];
-        O = e_add(mk3(h), mk3(0.1f, 0.1f, 0.1f));  // raytracing.cpp:246
-        D = light[k];
-    }
-};
-
 template <int RP, int J, int MINB, bool NEAREST, bool GRAZ, bool CULL>
 __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant__ FrameParams P, int level) {
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
     __shared__ CullStorage<CULL> csm;
+    __shared__ ColdStorage<R, !CULL> cold;
     const uint32_t nl = (uint32_t)P.nlights;
     const uint32_t count = P.counters[kCntHit + level] * nl;
     const uint32_t per_chunk = kThreads * R;
@@ -890,24 +905,20 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
     for (uint32_t item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
         const uint32_t chunk = item / sp.parts, part = item - chunk * sp.parts;
         FastRays<RP> fr;
-        float dist[R];
-        int best[R];
-        uint32_t sid[R], lid[R];
-        v3 light[R];
+        ColdState<R, !CULL> st(cold.get());
+        auto& dist = st.dist; auto& best = st.best; auto& sid = st.sid;
         uint32_t live = 0;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const uint32_t ray = chunk * per_chunk + threadIdx.x * R + k;
             const bool ok = ray < count;
             v3 O = mk3(0, 0, 0), D = mk3(0, 0, 1);
-            sid[k] = 0; lid[k] = 0; light[k] = D;
+            sid[k] = 0;
             if (ok) {
-                const uint32_t h = ray / nl;
-                lid[k] = ray - h * nl;
+                const uint32_t h = ray / nl, l = ray - h * nl;
                 sid[k] = P.q_hit[h];
-                light[k] = mk3(P.lights[lid[k]][0], P.lights[lid[k]][1], P.lights[lid[k]][2]);
                 O = e_add(mk3(P.hit[sid[k]]), mk3(0.1f, 0.1f, 0.1f));
-                D = light[k];
+                D = mk3(P.lights[l][0], P.lights[l][1], P.lights[l][2]);
                 live |= 1u << k;
             }
             dist[k] = FLT_MAX;
@@ -915,7 +926,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
             fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
         }
         const uint32_t valid = live;
-        FetchShadow fetch{P.hit, sid, light};
+        const uint32_t ray0 = chunk * per_chunk + threadIdx.x * R;   // slot k of this thread is work item ray0 + k
+        auto fetch = [&](int k, v3& O, v3& D) {   // the exact shadow ray of slot k: hit + (0.1, 0.1, 0.1) -> light (raytracing.cpp:246-248)
+            const uint32_t l = (ray0 + k) % nl;
+            O = e_add(mk3(P.hit[sid[k]]), mk3(0.1f, 0.1f, 0.1f));
+            D = mk3(P.lights[l][0], P.lights[l][1], P.lights[l][2]);
+        };
         if (CULL)
             scan_item_culled<RP, J, NEAREST, GRAZ>(pipe, csm.get(), fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len),
                                                    min((int)((part + 1) * sp.len), P.ntiles), P.tile_box, P.super_box, P.cls1, P.cls2);
@@ -966,7 +982,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
                     }
                 }
             }
-            if (!lit) atomicAnd(&P.lit[sid[k]], ~(1u << lid[k]));
+            if (!lit) atomicAnd(&P.lit[sid[k]], ~(1u << ((ray0 + k) % nl)));
         }
     }
     if (n_exact) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)n_exact);
