@@ -146,8 +146,9 @@ int rt_trace(const rt_params* params, int n, const float* origins, const float* 
 
 /* Options (rt_set_option; they persist until rt_shutdown).
  * RT_OPT_TILE_CULLING (default 0): 1 = conservative tile culling.  Triangles are scanned in tiles of 128; with this
- *   option a warp skips a tile when none of its rays can reach the bounding box of the tile's (tolerance-dilated)
- *   triangles.  The image and the primitive ids are IDENTICAL to the brute-force scan (same filter + exact tiers on every
+ *   option only tiles (found through a two-level hierarchy of bounding boxes) that some ray of a thread block can reach
+ *   are streamed, and a warp skips a tile when none of its own rays can reach the box of the tile's (tolerance-dilated)
+ *   triangles.  Scenes of more than 2.1 M triangles are scanned brute force.  The image and the primitive ids are IDENTICAL to the brute-force scan (same filter + exact tiers on every
  *   tile that is not skipped) -- it only stops being the O(rays x triangles) loop of the reference
  *   (raytracing.cpp:174-189), which is why it is opt-in and reported separately by bench.py.  Set it BEFORE
  *   rt_upload_scene to also get spatially sorted tiles (Morton order of the triangle centroids), which makes the boxes
