@@ -41,6 +41,11 @@ def workload(name):
         return s, 800, 800, 4, 3, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0), [(2.5, 4.0, 3.0)], \
             "Balls stand-in (Balls.obj is missing from the reference checkout): island height field + 3 tessellated spheres, " \
             f"{s.n_triangles} triangles, Balls.mtl materials, 800x800, 4x4 rays/pixel, 1 light, shadows + reflection, max_lvl 3"
+    if name == "balls_spheres":   # configs[1] read literally: "Balls.obj + Sphere primitives"
+        s = scenes.balls_with_sphere_primitives()
+        return s, 800, 800, 4, 3, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0), [(2.5, 4.0, 3.0)], \
+            f"Balls stand-in terrain ({s.n_triangles} triangles) + 3 analytic Sphere primitives (own semantics: the reference's Sphere.h is " \
+            "orphaned), 800x800, 4x4 rays/pixel, 1 light, shadows + reflection, max_lvl 3"
     if name == "dodge":      # configs[2]
         s = host.Scene.load(os.path.join(ROOT, "tests", "golden", "scenes", "dodge.npz"))
         return s, 1920, 1080, 4, 10, (.75, .55, 1.1), (.07, 0, .23), None, \

@@ -88,6 +88,17 @@ def balls_standin(grid=128, slices=64, stacks=32):
     return _finish(np.concatenate(verts), np.concatenate(tris), np.concatenate(mats), materials, names)
 
 
+def balls_with_sphere_primitives(grid=128):
+    """The Balls stand-in with its three balls as analytic `Sphere` primitives (Sphere.h of the reference; own
+    semantics) instead of tessellated meshes: island height field (2*grid^2 triangles) + 3 spheres."""
+    full = balls_standin(grid=grid, slices=8, stacks=4)
+    nt = 2 * grid * grid                       # the terrain comes first in balls_standin
+    nv = (grid + 1) ** 2
+    s = Scene(full.vertices[:nv], full.indices[:nt], full.tri_material[:nt], full.normals[:nt], full.materials, full.names)
+    s.spheres = np.array([[-0.95, 1.25, 0.35, 0.42, 1], [0.15, 1.45, -0.55, 0.42, 2], [1.05, 1.15, 0.55, 0.42, 3]], np.float32)
+    return s
+
+
 def tessellated_sphere(slices=1000, stacks=501, ground=False):
     """BASELINE C4: UV sphere of radius 1 at the origin; slices=1000, stacks=501 -> exactly 1,000,000 triangles."""
     v, t = uv_sphere((0.0, 0.0, 0.0), 1.0, slices, stacks)

@@ -503,3 +503,29 @@ def test_fuzz_random_scenes(gpu, port, seed):
     assert np.array_equal(np.isfinite(rgb), ok)
     assert np.abs(rgb[ok] - rgb_o[ok]).max() <= 5e-5
     assert (st["primary_rays"], st["shadow_rays"], st["bounce_rays"]) == counts
+
+
+def test_balls_with_sphere_primitives(gpu, port):
+    """BASELINE configs[1] read literally ("Balls.obj + Sphere primitives"): terrain mesh + three analytic spheres that
+    reflect each other and cast shadows on the terrain.  Oracle = this repo's sphere semantics."""
+    import ctypes as C
+    from raytracert_b200 import host, scenes
+    s = scenes.balls_with_sphere_primitives(grid=48)
+    cam = host.Camera(96, 80, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0))
+    lights = [(2.5, 4.0, 3.0)]
+    port.set_scene(s)
+    port.L.orc_set_spheres.argtypes = [C.c_int, C.c_void_p]
+    port.L.orc_set_spheres(len(s.spheres), s.spheres.ctypes.data)
+    try:
+        port.configure(cam.eye, lights, 63, 3); port.reset_counts()
+        rgb_o, _, prim_o = port.render(cam.corners, 96, 80, 2, 2, want_samples=True)
+        counts = port.ray_counts()
+    finally:
+        port.L.orc_set_spheres(0, s.spheres.ctypes.data)
+    c = dict(corners=cam.corners, W=96, H=80, pfx=2, pfy=2, max_lvl=3, features=63, eye=cam.eye, lights=lights)
+    rgb, prim = gpu_render(gpu, s, c)
+    st = gpu.stats()
+    assert np.count_nonzero(prim_o >= s.n_triangles) > 500      # sphere pixels
+    assert np.array_equal(prim, prim_o)
+    assert np.abs(rgb - rgb_o).max() <= RGB_TOL
+    assert (st["primary_rays"], st["shadow_rays"], st["bounce_rays"]) == counts
