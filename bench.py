@@ -280,12 +280,12 @@ def main():
                 # rt_probe_fp32_peak(): what a register-resident FFMA/FFMA2 loop sustains on this device right now (TFLOP/s)
                 "peak_fma_loop_measured": fp32_probe, "frac_of_measured_fma_loop": ach / fp32_probe if fp32_probe > 0 else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the frame's largest k_trace launch (8.39 M primary rays), one
-                # `ncu --set full` capture of this command (profiles/r1f_k_trace_primary_full.txt); only meaningful for the default workload
-                "traffic": 594.4e6 if args.workload == "balls" and world == 1 else None, "traffic_unit": "B per launch (primary scan, chunk 0)", "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
+                # `ncu --set full` capture of this command (profiles/r1g_k_trace_primary_full.txt); only meaningful for the default workload
+                "traffic": 590.9e6 if args.workload == "balls" and world == 1 else None, "traffic_unit": "B per launch (primary scan, chunk 0)", "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
                 "frac_at_measured_clock": (ach / (fp32_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])) if clocks.get("sm_mhz") else None,
                 "frame_achieved": FLOPS_PER_TEST * rays * ntri / world / (ms_dev * 1e-3) / 1e12,
                 # what the filter actually executes per test (11 FFMA2 + 3 FMUL2 + 2 FADD2 per ray pair = 27 flop per ray),
-                # i.e. the executed-FP32 fraction; ncu sm__pipe_fma_cycles_active for the same launch: 62.6 % (profiles/r1f_*)
+                # i.e. the executed-FP32 fraction; ncu sm__pipe_fma_cycles_active for the same launch: 62.9 % (profiles/r1g_*)
                 "executed_flops_per_test": 27, "executed_frac": ach * 27.0 / FLOPS_PER_TEST / fp32_peak,
                 "ms_by_kernel": dict(zip(["k_trace", "k_shadow", "k_shade", "k_resolve", "gather"], [float(x) for x in kinds]))}
         line = {"metric": METRIC, "value": rays / ms_dev / 1e3, "unit": "Mrays/s",
