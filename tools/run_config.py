@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="sphere1m")
 ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--lattice", type=int, default=0, help="oracle check on every k-th pixel of every k-th row (0 = ~150 pixels)")
+ap.add_argument("--modes", default="brute_force,tile_culling", help="comma list of brute_force, tile_culling")
 args = ap.parse_args()
 R, rank, world = dist.make_renderer()
 scene, W, H, pf, lvl, eye, center, lights, desc = bench.workload(args.workload)
@@ -27,7 +28,10 @@ small = binding.make_params(host.Camera(64, 36, eye, center).corners, 64, 36, 1,
 prm = binding.make_params(cam.corners, W, H, pf, pf, lvl, 63, cam.eye, lights, want_prim_id=(world == 1))
 out = {"workload": desc, "n_gpus": world}
 frames = {}
+modes = args.modes.split(",")
 for mode, cull in (("brute_force", 0), ("tile_culling", 1)):
+    if mode not in modes:
+        continue
     R.set_option(binding.RT_OPT_TILE_CULLING, cull)
     R.upload_scene(scene)
     # warm-up (allocations, records, NCCL connections): the full frame when it is cheap, a tiny one otherwise
@@ -49,10 +53,12 @@ for mode, cull in (("brute_force", 0), ("tile_culling", 1)):
     out[mode] = {"ms_per_frame": m, "Mrays_per_s": rays / m / 1e3, "rays": rays, "tests_per_s": rays * scene.n_triangles / (m * 1e-3),
                  "fp32_algorithmic_tflops_per_gpu": 42 * rays * scene.n_triangles / (m * 1e-3) / 1e12 / world}
 if rank == 0:
-    a, b = frames["brute_force"], frames["tile_culling"]
+    a = frames[modes[0]]
     rgb = a[0] if world == 1 else a
-    rgb_c = b[0] if world == 1 else b
-    out["culling_bit_identical"] = bool(np.array_equal(rgb.view(np.uint32), rgb_c.view(np.uint32)))
+    if len(frames) == 2:
+        b = frames["tile_culling"]
+        rgb_c = b[0] if world == 1 else b
+        out["culling_bit_identical"] = bool(np.array_equal(rgb.view(np.uint32), rgb_c.view(np.uint32)))
     from oracle import pyoracle
     k = args.lattice or max(1, int(round((W * H / 150.0) ** 0.5)))
     P = pyoracle.PortOracle(); P.set_scene(scene); P.configure(cam.eye, lights, 63, lvl)
