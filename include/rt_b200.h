@@ -102,8 +102,8 @@ typedef struct rt_stats {
     uint64_t tri_tests;                               /* rays * triangles, the reference's count     */
     uint64_t exact_evals;                             /* (ray,triangle) pairs re-done in exact order */
     /* device time (CUDA events on the library's stream; max over this process's GPUs): the whole frame, and the
-     * sum over launches of each kernel kind: nearest-hit scans (k_trace), shadow scans (k_shadow), shading
-     * (k_shade), resolve, and the all-gather + de-interleave */
+     * sum over launches of each kernel kind: nearest-hit scans (k_trace), shadow scans (k_shadow), hit records +
+     * shading (k_finish, k_shade), resolve, and the all-gather + de-interleave */
     float ms_total, ms_trace, ms_shadow, ms_shade, ms_resolve, ms_gather;
     uint32_t n_gpus, rank, n_triangles, n_levels;
     uint32_t n_launches;                              /* kernels launched for the frame (per GPU)      */
