@@ -221,7 +221,8 @@ def main():
         R.upload_scene(scene); R.render(prm); R.download_into(fb_host)
         return (time.perf_counter() - t) * 1e3
 
-    fb_host = np.zeros((H, W, 3), np.float32)
+    fb_pinned = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory()   # the D2H target of the e2e steps is pinned host memory
+    fb_host = fb_pinned.numpy()
     for _ in range(args.warmup):
         frame_ms()
     sampler = ClockSampler(local)

@@ -126,6 +126,34 @@ struct Global {
     std::string error;
 } g;
 
+// Host staging for rt_upload_scene: page-locked, grow-only, reused across uploads, so the H2D copies are true DMA
+// transfers from pinned memory.  Falls back to pageable memory if pinning fails.
+template <class T>
+struct PinnedStage {
+    T* p = nullptr;
+    size_t cap = 0, n = 0;
+    bool pinned = false;
+    void resize(size_t count) {
+        if (count > cap) {
+            release();
+            const size_t want = count + count / 8 + 16;
+            if (cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault) == cudaSuccess) pinned = true;
+            else { cudaGetLastError(); p = (T*)malloc(want * sizeof(T)); pinned = false; }
+            cap = p ? want : 0;
+        }
+        n = count;
+    }
+    void assign(size_t count, const T& v) { resize(count); for (size_t i = 0; i < n; ++i) p[i] = v; }
+    void release() { if (p) { if (pinned) cudaFreeHost(p); else free(p); } p = nullptr; cap = n = 0; }
+    T* data() { return p; }
+    size_t size() const { return n; }
+    T& operator[](size_t i) { return p[i]; }
+    T* begin() { return p; }
+};
+PinnedStage<float4> g_stage_triv, g_stage_nm, g_stage_sph;
+PinnedStage<uint32_t> g_stage_perm;
+PinnedStage<rt_material> g_stage_mat;
+
 int fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -590,6 +618,7 @@ void rt_shutdown(void) {
     g.world = 0;
     g.scene_ready = g.frame_ready = false;
     g.tile_culling = false;
+    g_stage_triv.release(); g_stage_nm.release(); g_stage_sph.release(); g_stage_perm.release(); g_stage_mat.release();
 }
 
 int rt_init(int n_gpus) {
@@ -666,7 +695,10 @@ int rt_upload_scene(const rt_scene* sc) {
         if (sc->spheres[i].material >= sc->n_materials) return fail(RT_ERR_INVALID, "sphere %u uses material %u of %u", i, sc->spheres[i].material, sc->n_materials);
 
     // host-side packing: exact corners (3 float4 per triangle), normal+material, bounds
-    std::vector<float4> triv((size_t)3 * std::max(n, 1u)), nm(std::max(n, 1u));
+    PinnedStage<float4>&triv = g_stage_triv, &nm = g_stage_nm;
+    triv.resize((size_t)3 * std::max(n, 1u));
+    nm.resize(std::max(n, 1u));
+    if (!triv.data() || !nm.data()) return fail(RT_ERR_CUDA, "out of host memory for the scene staging buffers");
     float extent = 0.f;
     for (uint32_t i = 0; i < n; ++i) {
         const float* c[3] = {sc->v0 + 4 * i, sc->v1 + 4 * i, sc->v2 + 4 * i};
@@ -680,7 +712,7 @@ int rt_upload_scene(const rt_scene* sc) {
     }
     // group the triangles by the dominant axis of their plane normal (rt_kernels.cuh: 2-D projected filter); stable
     // inside a class, every class padded to whole tiles
-    std::vector<uint32_t> perm;
+    PinnedStage<uint32_t>& perm = g_stage_perm;
     int cls_tiles[3] = {0, 0, 0};
     {
         std::vector<uint8_t> cls(n);
@@ -734,7 +766,12 @@ int rt_upload_scene(const rt_scene* sc) {
                 std::stable_sort(perm.begin() + start[c], perm.begin() + start[c] + cnt[c], [&](uint32_t x, uint32_t y) { return code[x] < code[y]; });
         }
     }
-    std::vector<float4> sph((size_t)2 * std::max(sc->n_spheres, 1u));
+    PinnedStage<float4>& sph = g_stage_sph;
+    sph.resize((size_t)2 * std::max(sc->n_spheres, 1u));
+    PinnedStage<rt_material>& mats = g_stage_mat;
+    mats.resize(sc->n_materials);
+    if (!perm.data() || !sph.data() || !mats.data()) return fail(RT_ERR_CUDA, "out of host memory for the scene staging buffers");
+    memcpy(mats.data(), sc->materials, sizeof(rt_material) * sc->n_materials);
     for (uint32_t i = 0; i < sc->n_spheres; ++i) {
         const rt_sphere& s = sc->spheres[i];
         sph[2 * i] = make_float4(s.center[0], s.center[1], s.center[2], s.radius);
@@ -791,7 +828,7 @@ int rt_upload_scene(const rt_scene* sc) {
         rc = ensure(d.spheres, d.cap_sph, sph.size()); if (rc) return rc;
         CU(cudaMemcpyAsync(d.triv, triv.data(), sizeof(float4) * triv.size(), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.normal_mat, nm.data(), sizeof(float4) * nm.size(), cudaMemcpyHostToDevice, d.stream));
-        CU(cudaMemcpyAsync(d.materials, sc->materials, sizeof(rt_material) * sc->n_materials, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemcpyAsync(d.materials, mats.data(), sizeof(rt_material) * sc->n_materials, cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.spheres, sph.data(), sizeof(float4) * sph.size(), cudaMemcpyHostToDevice, d.stream));
         CU(cudaStreamSynchronize(d.stream));  // host staging vectors die at return
     }
