@@ -195,8 +195,8 @@ __global__ void k_build_records(const float4* __restrict__ triv, const uint32_t*
 // because the reference's own barycentrics are off by at most E0 (DESIGN.md "filter soundness"), inside the triangle
 // dilated by E0 in barycentric units, i.e. by <= 3*E0*diameter.  So a ray that misses the box of the dilated
 // triangles (+ rounding slack) cannot hit any of them.  E0 is read back from the record (c1 = 1 + 3*E0).
-// A tile holding an "always exact" triangle (bmin = +inf: the bound does not exist) is unbounded and never skipped;
-// "never" records (degenerate, padding) contribute nothing.
+// "never" records (degenerate, padding, and the triangles that went to always_list) contribute nothing; a record
+// with a non-finite bmin (not produced any more) would make its tile unbounded, i.e. never skipped.
 __global__ void k_build_tile_boxes(const float4* __restrict__ triv, const float4* __restrict__ rec, int ntiles_padded, float M,
                                    float4* __restrict__ tile_box) {
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,7 +208,7 @@ __global__ void k_build_tile_boxes(const float4* __restrict__ triv, const float4
         const int pos = tile * kTile + j;
         const float4 q3 = rec[4 * pos + 3];
         if (q3.x == kBminNever) continue;                   // never a candidate
-        if (!(q3.x < inf)) { unbounded = true; break; }     // always exact
+        if (!(q3.x < inf)) { unbounded = true; break; }     // defensive: no bound
         const uint32_t i = __float_as_uint(q3.y);
         const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
         const float e0 = fmaxf(rec[4 * pos + 1].w - 1.0f, 0.0f) * (1.0f / 3.0f) + 1e-6f;
