@@ -107,7 +107,8 @@ typedef struct rt_stats {
     float ms_total, ms_trace, ms_shadow, ms_shade, ms_resolve, ms_gather;
     uint32_t n_gpus, rank, n_triangles, n_levels;
     uint32_t n_launches;                              /* kernels launched for the frame (per GPU)      */
-    uint32_t variant;                                 /* bit 0: scan kernels without the grazing clause (fine mesh) */
+    uint32_t variant;                                 /* bit 0: scan kernels without the grazing clause (fine mesh);
+                                                       * bit 1: pencil filter on the primary rays; bit 2: on shadow rays */
 } rt_stats;
 
 /* Single-process mode: use devices 0..n_gpus-1 of this box (n_gpus >= 1); rows are interleaved over
@@ -154,6 +155,12 @@ int rt_trace(const rt_params* params, int n, const float* origins, const float* 
  *   rt_upload_scene to also get spatially sorted tiles (Morton order of the triangle centroids), which makes the boxes
  *   compact; enabling it afterwards works on the tiles in file order. */
 #define RT_OPT_TILE_CULLING 1
+/* RT_OPT_PENCIL (default 1): 1 = primary rays (all lines pass through the eye) and the shadow rays of a light (all end at
+ * the light) are filtered with the common-point ("pencil") form of the ray-triangle test -- 12 instead of 16 packed FP32
+ * instructions per (ray pair, triangle) -- whenever the frame qualifies (brute-force scan, clause-free scene, perspective
+ * camera / light outside the scene box; rt_stats.variant says what was used).  Same filter + exact tiers, identical
+ * image and ids.  0 = always the generic filter. */
+#define RT_OPT_PENCIL 2
 int rt_set_option(int option, int value);
 
 int rt_get_stats(rt_stats* out);

@@ -409,6 +409,16 @@ void orc_trace(int n, const float* origins, const float* dests, float* rgb, int3
     }
 }
 
+/* One (ray, triangle) pair: rayIntersectTriangle + the distance intersectMesh compares (raytracing.cpp:179-183).
+ * Returns 1 on a hit and writes Vec3Df::distance(origin, I).  Used by the filter soundness tests. */
+int orc_ray_triangle(const float* R0, const float* R1, const float* T0, const float* T1, const float* T2, float* dist) {
+    v3 I;
+    v3 o = V(R0[0], R0[1], R0[2]);
+    if (!ray_intersect_triangle(o, V(R1[0], R1[1], R1[2]), V(T0[0], T0[1], T0[2]), V(T1[0], T1[1], T1[2]), V(T2[0], T2[1], T2[2]), &I)) return 0;
+    *dist = vdistance(o, I);
+    return 1;
+}
+
 /* Image::writeImage quantiser, main.cpp:116-117 */
 void orc_quantise(const float* rgb, int n, unsigned char* out) {
     for (int i = 0; i < n; i++) out[i] = (unsigned char)(rgb[i] * 255.0f);

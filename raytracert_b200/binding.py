@@ -15,6 +15,7 @@ RT_AMBIENT, RT_DIFFUSE, RT_SPECULAR, RT_REFLECTION, RT_SHADOWS, RT_REFRACTION = 
 RT_ALL_FEATURES = 63
 RT_MAX_LIGHTS = 16
 RT_OPT_TILE_CULLING = 1
+RT_OPT_PENCIL = 2
 
 
 class RtMaterial(C.Structure):

@@ -79,6 +79,11 @@ struct RtDevice {
     uint32_t* always_list = nullptr;        // triangles outside the filter (see k_build_records)
     size_t cap_always = 0;
     int n_always_host = 0;
+    uint32_t pencil_used = 0;               // rt_stats.variant bits of the last frame (2: primary rays, 4: shadow rays)
+    // pencil filter (rt_pencil.h): slot 0 = records around the eye, slot 1 + l = around light l; rebuilt every frame
+    float4* prec = nullptr; size_t cap_prec = 0;
+    float4* scene_box = nullptr;            // device: union of the tile boxes (k_scene_box)
+    float box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0};   // host copy, valid while the generic records are
     // per-chunk state
     size_t cap_samples = 0;
     float4 *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *acc = nullptr, *hit = nullptr;
@@ -112,6 +117,7 @@ struct Global {
     NcclApi nccl;
     ScanConfig scan = {2, 8, 2};
     bool tile_culling = false;       // RT_OPT_TILE_CULLING
+    bool pencil = true;              // RT_OPT_PENCIL: common-point filter for primary / shadow rays where it applies
     bool allow_no_grazing = true;    // RT_B200_GRAZING=1 forces the grazing clause on (experiments)
     float max_uv = 0.f;              // max over the triangles of |v1-v0| * |v2-v0| (see build_records)
     float max_ni = 1.f;              // max over the materials of max(Ni, 1/Ni): bounds the refracted direction
@@ -201,7 +207,7 @@ int create_device(RtDevice& d, int device, int rank) {
 void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
-    void* ptrs[] = {d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+    void* ptrs[] = {d.prec, d.scene_box, d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
                     d.q_hit, d.key, d.hit0, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -226,6 +232,8 @@ struct LaunchTimer {
     ~LaunchTimer() { if (timed) cudaEventRecord(d.kev[2 * (d.kev_kind.size() - 1) + 1], d.stream); }
 };
 
+enum { kScanPrimary = 0, kScanBounce = 1, kScanShadowAny = 2, kScanShadowNearest = 3, kScanPrimaryPencil = 4, kScanShadowPencil = 5 };
+
 template <int RP, int J, int MINB, bool GRAZ, bool CULL>
 void launch_scan_gc(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
     switch (which) {
@@ -237,6 +245,8 @@ void launch_scan_gc(int which, int grid, cudaStream_t st, const FrameParams& P, 
 }
 template <int RP, int J, int MINB>
 void launch_scan(int which, int grid, cudaStream_t st, const FrameParams& P, int level, bool grazing_clause) {
+    if (which == kScanPrimaryPencil) { k_trace<RP, J, MINB, true, false, false, true><<<grid, kThreads, 0, st>>>(P, level); return; }
+    if (which == kScanShadowPencil) { k_shadow<RP, J, MINB, false, false, false, true><<<grid, kThreads, 0, st>>>(P, level); return; }
     if (P.cull) {
         if (grazing_clause) launch_scan_gc<RP, J, MINB, true, true>(which, grid, st, P, level);
         else launch_scan_gc<RP, J, MINB, false, true>(which, grid, st, P, level);
@@ -245,7 +255,6 @@ void launch_scan(int which, int grid, cudaStream_t st, const FrameParams& P, int
         else launch_scan_gc<RP, J, MINB, false, false>(which, grid, st, P, level);
     }
 }
-enum { kScanPrimary = 0, kScanBounce = 1, kScanShadowAny = 2, kScanShadowNearest = 3 };
 
 // which: kScan*; the grid is one CTA per resident slot (persistent CTAs stride over ray chunks)
 void dispatch_scan(const ScanConfig& c, int which, int num_sms, cudaStream_t st, const FrameParams& P, int level, bool grazing_clause) {
@@ -268,6 +277,7 @@ void read_tuning_env() {
     }
     if (const char* c = getenv("RT_B200_GRAZING")) g.allow_no_grazing = atoi(c) == 0;
     if (const char* c = getenv("RT_B200_CULL")) g.tile_culling = atoi(c) != 0;   // same as rt_set_option(RT_OPT_TILE_CULLING, ..)
+    if (const char* c = getenv("RT_B200_PENCIL")) g.pencil = atoi(c) != 0;       // same as rt_set_option(RT_OPT_PENCIL, ..)
     const char* e = getenv("RT_B200_TUNE");
     if (!e) return;
     ScanConfig c = g.scan;
@@ -326,6 +336,14 @@ int build_records(RtDevice& d, float M, float dir_max) {
     if (rc) return rc;
     k_build_super_boxes<<<(nsuper + 127) / 128, 128, 0, d.stream>>>(d.tile_box, tiles_padded, nsuper, d.super_box);
     CU(cudaGetLastError());
+    if (!d.scene_box) CU(cudaMalloc(&d.scene_box, 2 * sizeof(float4)));
+    k_scene_box<<<1, 32, 0, d.stream>>>(d.super_box, nsuper, d.scene_box);
+    CU(cudaGetLastError());
+    float4 hb[2];
+    CU(cudaMemcpyAsync(hb, d.scene_box, sizeof(hb), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaStreamSynchronize(d.stream));
+    d.box_lo[0] = hb[0].x; d.box_lo[1] = hb[0].y; d.box_lo[2] = hb[0].z;
+    d.box_hi[0] = hb[1].x; d.box_hi[1] = hb[1].y; d.box_hi[2] = hb[1].z;
     d.M_built = M;
     d.dir_built = dir_max;
     return RT_OK;
@@ -373,10 +391,65 @@ void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float e
     memcpy(P.lights, rp.lights, sizeof(P.lights));
     P.features = rp.features;
     P.max_lvl = rp.max_lvl;
+    P.light_sel = -1;
+}
+
+// Pencil launches of one frame on one device (rt_pencil.h).  cam: the primary rays; light[l]: the shadow rays of light l.
+struct PencilPlan {
+    bool cam = false, any_light = false;
+    bool light[RT_MAX_LIGHTS] = {};
+    PencilSetup cam_setup, light_setup[RT_MAX_LIGHTS];
+    int axis[RT_MAX_LIGHTS] = {};
+    float sign[RT_MAX_LIGHTS] = {};
+    size_t slot_vec = 0;   // float4 per record slot
+};
+
+void apply_pencil(FrameParams& P, const RtDevice& d, const PencilPlan& plan, int slot, const PencilSetup& S) {
+    P.prec = d.prec + (size_t)slot * plan.slot_vec;
+    P.pE[0] = S.Ef[0]; P.pE[1] = S.Ef[1]; P.pE[2] = S.Ef[2];
+    P.p_lam_slack = S.lam_slack;
+}
+
+// Decide which launches of this frame can use the pencil filter and build their records.  Conditions: brute force
+// (no tile culling), the clause-free proof holds (pairs with |cos| < cos_min are certain misses in the reference), and
+// the geometric launch conditions of pencil_camera_setup / pencil_light_setup.
+int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
+    plan = PencilPlan();
+    if (!g.pencil || cull || !d.no_grazing || d.ntri == 0) return RT_OK;
+    const int npad = (d.ntiles + kPadTiles) * kTile;
+    plan.slot_vec = (size_t)npad * kRecVec;
+    const bool shadows = (rp.features & RT_SHADOWS) && rp.n_lights > 0 && !g.any_transparent;
+    plan.cam = pencil_camera_setup(rp.corners, (double)d.M_built, plan.cam_setup);
+    if (plan.cam && plan.cam_setup.cos_g > kPencilCosMin) {
+        // the camera pencil answers only for |cos| >= cos_g (> the generic 1.05e-5): the clause-free proof of build_records
+        // must hold at that threshold for the primary rays, |b_ref| < |dir||u||v| (cos_g + 10u) < 1e-5
+        double dir_cam = 0.0;
+        for (int c = 0; c < 4; ++c) {
+            double l2 = 0.0;
+            for (int k = 0; k < 3; ++k) { const double t = (double)rp.corners[c * 6 + 3 + k] - rp.corners[c * 6 + k]; l2 += t * t; }
+            dir_cam = std::max(dir_cam, std::sqrt(l2));
+        }
+        if (!((plan.cam_setup.cos_g + 6e-7) * (double)g.max_uv * dir_cam * 1.01 <= 0.95e-5)) plan.cam = false;
+    }
+    if (shadows)
+        for (uint32_t l = 0; l < rp.n_lights; ++l) {
+            plan.light[l] = pencil_light_setup(rp.lights[l], d.box_lo, d.box_hi, (double)d.M_built, plan.light_setup[l], plan.axis[l], plan.sign[l]);
+            plan.any_light = plan.any_light || plan.light[l];
+        }
+    if (!plan.cam && !plan.any_light) return RT_OK;
+    int rc = ensure(d.prec, d.cap_prec, plan.slot_vec * (1 + (shadows ? rp.n_lights : 0)));
+    if (rc) return rc;
+    const int grid = (npad + 127) / 128;
+    if (plan.cam) k_build_pencil<<<grid, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.cam_setup, d.prec);
+    for (uint32_t l = 0; shadows && l < rp.n_lights; ++l)
+        if (plan.light[l])
+            k_build_pencil<<<grid, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.light_setup[l], d.prec + (size_t)(1 + l) * plan.slot_vec);
+    CU(cudaGetLastError());
+    return RT_OK;
 }
 
 // Wavefront for one chunk whose rays are either generated (primary) or already in ray_o/ray_d (trace API).
-int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullptr) {
+int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullptr, const PencilPlan* plan = nullptr) {
     const bool shadows = (P.features & RT_SHADOWS) && P.nlights > 0;
     const bool bounces = (P.features & (RT_REFLECTION | RT_REFRACTION)) != 0;
     const int levels = bounces ? std::min(P.max_lvl + 1, kMaxLevels - 2) : 1;
@@ -384,7 +457,13 @@ int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullp
     for (int level = 0; level < levels; ++level) {
         {
             LaunchTimer t(d, kKindTrace);
-            dispatch_scan(g.scan, level == 0 ? kScanPrimary : kScanBounce, d.num_sms, d.stream, P, level, !d.no_grazing);
+            if (level == 0 && plan && plan->cam && !P.trace_api) {
+                FrameParams Pp = P;
+                apply_pencil(Pp, d, *plan, 0, plan->cam_setup);
+                dispatch_scan(g.scan, kScanPrimaryPencil, d.num_sms, d.stream, Pp, level, false);
+            } else {
+                dispatch_scan(g.scan, level == 0 ? kScanPrimary : kScanBounce, d.num_sms, d.stream, P, level, !d.no_grazing);
+            }
         }
         {
             LaunchTimer t(d, kKindShade);
@@ -392,7 +471,21 @@ int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullp
             else k_finish<false><<<grid_small, 256, 0, d.stream>>>(P, level);
         }
         if (level == 0 && level0_hits) CU(cudaMemcpyAsync(level0_hits, d.hit, sizeof(float4) * P.nsamples, cudaMemcpyDeviceToDevice, d.stream));
-        if (shadows) {
+        if (shadows && plan && plan->any_light) {
+            // one launch per light: the pencil filter around the lights that qualify, the generic any-hit scan for the others
+            for (int l = 0; l < P.nlights; ++l) {
+                LaunchTimer t(d, kKindShadow);
+                FrameParams Pl = P;
+                Pl.light_sel = l;
+                if (plan->light[l]) {
+                    apply_pencil(Pl, d, *plan, 1 + l, plan->light_setup[l]);
+                    Pl.p_axis = plan->axis[l]; Pl.p_sign = plan->sign[l];
+                    dispatch_scan(g.scan, kScanShadowPencil, d.num_sms, d.stream, Pl, level, false);
+                } else {
+                    dispatch_scan(g.scan, kScanShadowAny, d.num_sms, d.stream, Pl, level, !d.no_grazing);
+                }
+            }
+        } else if (shadows) {
             LaunchTimer t(d, kKindShadow);
             dispatch_scan(g.scan, g.any_transparent ? kScanShadowNearest : kScanShadowAny, d.num_sms, d.stream, P, level, !d.no_grazing);
         }
@@ -480,6 +573,9 @@ int render_enqueue(const rt_params* rp) {
         const uint32_t nchunks = (my_rows + rows_per_chunk - 1) / rows_per_chunk;
         const size_t chunk_cap = (size_t)std::min(rows_per_chunk, std::max(my_rows, 1u)) * row_samples;
         rc = build_records(d, M, direction_bound(*rp, true, nullptr, nullptr, 0)); if (rc) return rc;
+        PencilPlan plan;
+        rc = plan_pencil(d, *rp, g.tile_culling && d.ntiles <= kCullMaxTiles, plan); if (rc) return rc;
+        d.pencil_used = (plan.cam ? 2u : 0u) | (plan.any_light ? 4u : 0u);
         rc = ensure_chunk_state(d, chunk_cap, rp->want_prim_id != 0, (size_t)rows_per_rank * row_samples); if (rc) return rc;
         rc = ensure_counters(d, std::max(1u, nchunks)); if (rc) return rc;
         size_t need_local = (size_t)rows_per_rank * W * 3;
@@ -508,7 +604,7 @@ int render_enqueue(const rt_params* rp) {
             P.nslots = P.tiles_x * ((P.nrows + 7) / 8) * 64u * spp;
             P.sample_base = (unsigned long long)P.row0 * row_samples;
             P.prim_out = rp->want_prim_id ? d.prim : nullptr;
-            int levels = run_wavefront(d, P);
+            int levels = run_wavefront(d, P, nullptr, &plan);
             if (levels < 0) return levels;
             g.stats.n_levels = (uint32_t)levels;
             {
@@ -600,7 +696,7 @@ int collect_stats() {
         st.ms_resolve = std::max(st.ms_resolve, by_kind[kKindResolve]);
         if (cudaEventElapsedTime(&ms, d.ev_phase[1], d.ev_phase[2]) == cudaSuccess) st.ms_gather = std::max(st.ms_gather, ms);
         st.n_launches = std::max(st.n_launches, (uint32_t)d.kev_kind.size());
-        st.variant |= d.no_grazing ? 1u : 0u;
+        st.variant |= (d.no_grazing ? 1u : 0u) | d.pencil_used;
     }
     st.tri_tests = (st.primary_rays + st.shadow_rays + st.bounce_rays) * (uint64_t)st.n_triangles;
     return RT_OK;
@@ -618,6 +714,7 @@ void rt_shutdown(void) {
     g.world = 0;
     g.scene_ready = g.frame_ready = false;
     g.tile_culling = false;
+    g.pencil = true;
     g_stage_triv.release(); g_stage_nm.release(); g_stage_sph.release(); g_stage_perm.release(); g_stage_mat.release();
 }
 
@@ -934,6 +1031,7 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     CU(cudaMemcpyAsync(d.acc, ha.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
     CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords, d.stream));
     d.frame_chunks = 1;
+    d.pencil_used = 0;
     FrameParams P;
     fill_common(P, d, *rp, eps_r_for(M), d.counters);
     P.trace_api = 1;
@@ -965,6 +1063,7 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
 
 int rt_set_option(int option, int value) {
     if (option == RT_OPT_TILE_CULLING) { g.tile_culling = value != 0; return RT_OK; }
+    if (option == RT_OPT_PENCIL) { g.pencil = value != 0; return RT_OK; }
     return fail(RT_ERR_INVALID, "unknown option %d", option);
 }
 

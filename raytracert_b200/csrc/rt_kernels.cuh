@@ -25,6 +25,7 @@
 // the parts are merged with atomics (make_split / Pipe / scan_pass below).
 #pragma once
 #include "rt_common.cuh"
+#include "rt_pencil.h"
 #include "../../include/rt_b200.h"
 
 namespace rt {
@@ -97,6 +98,13 @@ struct FrameParams {
     uint32_t features;
     int max_lvl;
     int trace_api;              // 1: rays come from ray_o/ray_d (rt_trace), not from the camera
+    // pencil launches (rt_pencil.h): every ray's line passes through the common point pE
+    const float4* prec;         // pencil records of this launch (same positions / tiles as rec); nullptr: generic filter
+    float pE[3];                // the common point, float
+    float p_lam_slack;          // s_lam: ray-side guard band of the distance clause
+    int light_sel;              // k_shadow: >= 0 -> this launch handles only that light; -1 -> all lights (ray = hit * nlights + light)
+    int p_axis;                 // shadow pencil: a ray with origin O is "safe" (no occluder beyond the light can exist)
+    float p_sign;               //                iff p_sign * (L[p_axis] - O[p_axis]) >= 0
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -144,38 +152,17 @@ __global__ void k_build_records(const float4* __restrict__ triv, const uint32_t*
         float Df = __fsub_rn(__fmul_rn(uvf, uvf), __fmul_rn(uuf, vvf));
         if (!null_n) {
             bool always = !(fabsf(Df) > 0.0f) || !isfinite(Df);
-            const double a3[3] = {A.x, A.y, A.z};
-            const double u3[3] = {(double)B.x - A.x, (double)B.y - A.y, (double)B.z - A.z};
-            const double v3d[3] = {(double)C.x - A.x, (double)C.y - A.y, (double)C.z - A.z};
-            double n3[3] = {u3[1] * v3d[2] - u3[2] * v3d[1], u3[2] * v3d[0] - u3[0] * v3d[2], u3[0] * v3d[1] - u3[1] * v3d[0]};
-            const double nn = sqrt(n3[0] * n3[0] + n3[1] * n3[1] + n3[2] * n3[2]);
-            const double uu = u3[0] * u3[0] + u3[1] * u3[1] + u3[2] * u3[2], vv = v3d[0] * v3d[0] + v3d[1] * v3d[1] + v3d[2] * v3d[2];
-            const int U = (W + 1) % 3, V = (W + 2) % 3;
-            const double det = u3[U] * v3d[V] - u3[V] * v3d[U];   // == n3[W]
-            if (!(nn > 0.0) || !isfinite(nn) || !(uu > 0.0) || !(vv > 0.0) || !(fabs(det) > 0.0) || !isfinite(det)) always = true;
+            const float a3f[3] = {A.x, A.y, A.z}, b3f[3] = {B.x, B.y, B.z}, c3f[3] = {C.x, C.y, C.z};
+            const FilterTol t = filter_tolerances(a3f, b3f, c3f, W, (double)M);   // rt_pencil.h: shared with the pencil records
+            if (t.always) always = true;
             if (!always) {
-                // s = 1 at B, t = 1 at C, both 0 at A, as functions of the (U, V) coordinates
-                const double su = v3d[V] / det, sv = -v3d[U] / det, tu = -u3[V] / det, tv = u3[U] / det;
-                const double gs = sqrt(su * su + sv * sv), gt = sqrt(tu * tu + tv * tv);
-                const double gq = sqrt((su + tu) * (su + tu) + (sv + tv) * (sv + tv));
-                const double gmax = fmax(gs, fmax(gt, gq));   // >= the in-plane gradients (the projection only stretches them)
-                const double sinphi = nn / sqrt(uu * vv);
-                const double kappa = fmax(1.0, 0.25 / sinphi);
-                // DESIGN.md "filter soundness": E0 covers the rounding of the reference's own dot-product
-                // barycentrics (<= 28uM*gmax/sin(phi) + 8u/sin^2(phi)) plus this filter's arithmetic (<= 16uM*gmax),
-                // E1*|1/cos| the shift of (Pu, Pv) caused by the two sides' error along the ray (<= 34uM/|cos|)
-                const double E0 = 256.0 * (double)kU32 * (double)M * gmax * kappa + 1e-6;
-                const double E1 = 64.0 * (double)kU32 * (double)M * gmax * kappa;
-                if (!(E0 < 64.0) || !isfinite(E0)) {  // beyond this the dilated triangle is so large that "always exact" is cheaper
-                    always = true;
-                } else {
-                    const double inv = 1.0 / nn;
-                    n3[0] *= inv; n3[1] *= inv; n3[2] *= inv;
-                    q0 = make_float4((float)n3[0], (float)n3[1], (float)n3[2], (float)(-(n3[0] * a3[0] + n3[1] * a3[1] + n3[2] * a3[2])));
-                    q1 = make_float4((float)su, (float)sv, (float)(-(su * a3[U] + sv * a3[V]) + E0), (float)(1.0 + 3.0 * E0));
-                    q2 = make_float4((float)tu, (float)tv, (float)(-(tu * a3[U] + tv * a3[V]) + E0), (float)(-E1));
-                    q3.x = bmin_regular;
-                }
+                const double a3[3] = {A.x, A.y, A.z};
+                const double inv = 1.0 / t.nn;
+                const double n3[3] = {t.n3[0] * inv, t.n3[1] * inv, t.n3[2] * inv};
+                q0 = make_float4((float)n3[0], (float)n3[1], (float)n3[2], (float)(-(n3[0] * a3[0] + n3[1] * a3[1] + n3[2] * a3[2])));
+                q1 = make_float4((float)t.su, (float)t.sv, (float)(-(t.su * a3[t.U] + t.sv * a3[t.V]) + t.E0), (float)(1.0 + 3.0 * t.E0));
+                q2 = make_float4((float)t.tu, (float)t.tv, (float)(-(t.tu * a3[t.U] + t.tv * a3[t.V]) + t.E0), (float)(-t.E1));
+                q3.x = bmin_regular;
             }
             if (always) { q0 = q1 = q2 = make_float4(0, 0, 0, 0); q3.x = kBminNever; always_list[atomicAdd(n_always, 1u)] = i; }
         }
@@ -240,6 +227,43 @@ __global__ void k_build_super_boxes(const float4* __restrict__ tile_box, int nti
         hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
     }
     super_box[2 * g] = lo; super_box[2 * g + 1] = hi;
+}
+
+// Union of the tile boxes = bounding box of everything a filter record can make a hit of (pencil_light_setup).
+__global__ void k_scene_box(const float4* __restrict__ super_box, int nsuper, float4* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const float inf = __int_as_float(0x7f800000);
+    float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
+    for (int g = 0; g < nsuper; ++g) {
+        const float4 a = super_box[2 * g], b = super_box[2 * g + 1];
+        lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+        hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
+    }
+    out[0] = lo; out[1] = hi;
+}
+
+// Pencil records around the common point S.E (rt_pencil.h), position by position next to the generic records: a
+// position that is "never" there (padding, degenerate, always-exact triangle) is "never" here; id and the tile's
+// record count are copied.  M is the magnitude bound the generic records were built with (same E0 / E1).
+__global__ void k_build_pencil(const float4* __restrict__ triv, const float4* __restrict__ rec, int npos, int c1_end, int c2_end, float M,
+                               const PencilSetup S, float4* __restrict__ prec) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const float4 g3 = rec[4 * pos + 3];
+    float q[16];
+    pencil_never(q);
+    if (g3.x != kBminNever) {
+        const uint32_t i = __float_as_uint(g3.y);
+        const int W = pos < c1_end ? 0 : (pos < c2_end ? 1 : 2);
+        const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
+        const float a3f[3] = {A.x, A.y, A.z}, b3f[3] = {B.x, B.y, B.z}, c3f[3] = {C.x, C.y, C.z};
+        const FilterTol t = filter_tolerances(a3f, b3f, c3f, W, (double)M);
+        if (!t.always) pencil_record(a3f, b3f, c3f, t.E0, t.E1, S, q);
+    }
+    prec[4 * pos] = make_float4(q[0], q[1], q[2], q[3]);
+    prec[4 * pos + 1] = make_float4(q[4], q[5], q[6], q[7]);
+    prec[4 * pos + 2] = make_float4(q[8], q[9], q[10], q[11]);
+    prec[4 * pos + 3] = make_float4(q[12], g3.y, g3.z, 0.f);
 }
 
 // Slab test of the half-line O' + t d, 0 <= t < rhi, against a box.  NaN-safe in the conservative direction:
@@ -512,6 +536,87 @@ __device__ __forceinline__ void kill_slot(FastRays<RP>& f, int k) {
     f.rhi[k] = 0u;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pencil filter (rt_pencil.h): rays through a common point.  8 registers per ray pair, 12 packed FP32 instructions
+// and 4 LOP3 per (ray pair, triangle); the hot loop ANDs the sign words, "any candidate" = sign bit of the AND clear.
+// ------------------------------------------------------------------------------------------------
+template <int RP>
+struct PencilRays {
+    float2 wx[RP], wy[RP], wz[RP];  // direction away from the common point (+-unit ray direction); 0 = finished / unused / degenerate
+    float2 lhi[RP];                 // lambda_hi = lambda_O + nearest distance so far + s_lam; -inf = finished / unused; +inf = degenerate ray (always exact)
+    float ex, ey, ez, slack;        // common point, s_lam (uniform)
+};
+__device__ __forceinline__ float& pair_elem(float2& v, int odd) { return odd ? v.y : v.x; }
+
+// flip: w = -(dest - origin)/|..| (shadow rays: the pencil's centre is the ray's DEST).  nearest0: initial nearest distance
+// (FLT_MAX for a nearest-hit ray that has found nothing yet, 0 for an any-hit shadow ray: r >= 0 <=> lambda <= lambda_O).
+template <int RP>
+__device__ __forceinline__ void pencil_set_slot(PencilRays<RP>& f, int k, v3 O, v3 D, bool flip, float nearest0, bool live) {
+    float dx = D.x - O.x, dy = D.y - O.y, dz = D.z - O.z;
+    const float len2 = dx * dx + dy * dy + dz * dz;
+    float inv = rsqrtf(len2);
+    const bool degenerate = !(len2 > 1e-30f) || !(len2 < 1e30f);   // cannot be normalised: every triangle goes to the exact path
+    if (flip) inv = -inv;
+    dx *= inv; dy *= inv; dz *= inv;
+    float lam = fmaf(dx, O.x - f.ex, fmaf(dy, O.y - f.ey, (dz * (O.z - f.ez))));
+    lam = __fadd_ru(__fadd_ru(lam, nearest0), f.slack);
+    if (!(lam < FLT_MAX)) lam = FLT_MAX;                            // also a NaN (non-finite ray): candidates everywhere, the exact path decides
+    if (degenerate) { dx = dy = dz = 0.0f; lam = __int_as_float(0x7f800000); }
+    if (!live) { dx = dy = dz = 0.0f; lam = __int_as_float(0xff800000); }
+#pragma unroll
+    for (int kk = 0; kk < 2 * RP; ++kk)
+        if (kk == k) {
+            pair_elem(f.wx[kk / 2], kk & 1) = dx; pair_elem(f.wy[kk / 2], kk & 1) = dy; pair_elem(f.wz[kk / 2], kk & 1) = dz;
+            pair_elem(f.lhi[kk / 2], kk & 1) = lam;
+        }
+}
+
+// sign words of one ray pair against one pencil record: bit 31 of s0 / s1 set <=> certainly not a candidate
+template <int RP>
+__device__ __forceinline__ void pencil_pair(const PencilRays<RP>& f, int p, const float4& q0, const float4& q1, const float4& q2, const float4& q3,
+                                            uint32_t& s0, uint32_t& s1) {
+    float2 a = __ffma2_rn(splat2(q0.z), f.wz[p], splat2(q0.w));
+    float2 b = __ffma2_rn(splat2(q1.z), f.wz[p], splat2(q1.w));
+    float2 c = __ffma2_rn(splat2(q2.z), f.wz[p], splat2(q2.w));
+    a = __ffma2_rn(splat2(q0.y), f.wy[p], a);
+    b = __ffma2_rn(splat2(q1.y), f.wy[p], b);
+    c = __ffma2_rn(splat2(q2.y), f.wy[p], c);
+    a = __ffma2_rn(splat2(q0.x), f.wx[p], a);
+    b = __ffma2_rn(splat2(q1.x), f.wx[p], b);
+    c = __ffma2_rn(splat2(q2.x), f.wx[p], c);
+    float2 sg = __fadd2_rn(a, b);
+    sg = __fadd2_rn(sg, c);
+    const float2 e = __ffma2_rn(sg, f.lhi[p], splat2(q3.x));
+    s0 = __float_as_uint(a.x) | __float_as_uint(b.x) | __float_as_uint(c.x) | __float_as_uint(e.x);
+    s1 = __float_as_uint(a.y) | __float_as_uint(b.y) | __float_as_uint(c.y) | __float_as_uint(e.y);
+}
+
+// Ray-side hooks of the cold path, one overload per filter.
+template <int RP>
+__device__ __forceinline__ void ray_nearer(FastRays<RP>& f, int k, float dist, float band, v3) { f.rhi[k] = __float_as_uint(__fadd_ru(dist, band)); }
+template <int RP>
+__device__ __forceinline__ void ray_nearer(PencilRays<RP>& f, int k, float dist, float, v3 O) {
+#pragma unroll
+    for (int kk = 0; kk < 2 * RP; ++kk)
+        if (kk == k) {
+            float& lhi = pair_elem(f.lhi[kk / 2], kk & 1);
+            const float lam = fmaf(pair_elem(f.wx[kk / 2], kk & 1), O.x - f.ex, fmaf(pair_elem(f.wy[kk / 2], kk & 1), O.y - f.ey, pair_elem(f.wz[kk / 2], kk & 1) * (O.z - f.ez)));
+            const float v = __fadd_ru(__fadd_ru(lam, dist), f.slack);
+            if (lhi < __int_as_float(0x7f800000) && v < lhi) lhi = v;   // a degenerate ray (+inf) stays "always exact"; NaN keeps the old bound
+        }
+}
+template <int RP>
+__device__ __forceinline__ void ray_kill(FastRays<RP>& f, int k) { kill_slot<RP>(f, k); }
+template <int RP>
+__device__ __forceinline__ void ray_kill(PencilRays<RP>& f, int k) {
+#pragma unroll
+    for (int kk = 0; kk < 2 * RP; ++kk)
+        if (kk == k) {
+            pair_elem(f.wx[kk / 2], kk & 1) = 0.0f; pair_elem(f.wy[kk / 2], kk & 1) = 0.0f; pair_elem(f.wz[kk / 2], kk & 1) = 0.0f;
+            pair_elem(f.lhi[kk / 2], kk & 1) = __int_as_float(0xff800000);
+        }
+}
+
 template <int RP, int J>
 struct BitLayout {
     static constexpr int R = 2 * RP;
@@ -520,14 +625,55 @@ struct BitLayout {
     static constexpr uint32_t kRep = (uint32_t)((((uint64_t)1 << (R * J)) - 1) / (((uint64_t)1 << R) - 1));
 };
 
-// Scans all tiles of one pass.  NEAREST: keeps (dist, best) exactly like intersectMesh; !NEAREST: any-hit,
-// clears the ray's live bit on the first exact hit.  fetch(k, O, D) returns the exact ray of slot k.
-// One tile (kTile records of dominant-axis class W) against this thread's R rays.
+// Cold path of one filter block: exact re-evaluation of every (ray, triangle) pair in `mask` (bit j*R + k).
+// NEAREST: keeps (dist, best) exactly like intersectMesh; !NEAREST: any-hit, clears the ray's live bit on the first
+// exact hit.  fetch(k, O, D) returns the exact ray of slot k.
+template <int RP, int J, bool NEAREST, class Rays, class DistT, class BestT, class Fetch>
+__device__ __forceinline__ void exact_block(uint32_t mask, const float4* rec, int jb, Rays& fr, DistT& dist, BestT& best, uint32_t& live,
+                                            const float4* __restrict__ triv, float band, const Fetch& fetch, uint32_t& n_exact) {
+    constexpr int R = 2 * RP;
+    constexpr uint32_t REP = BitLayout<RP, J>::kRep;
+    mask &= live * REP;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const uint32_t mk = (mask >> k) & REP;
+        if (mk) {
+            v3 O, D;
+            fetch(k, O, D);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                if ((mk & (1u << (j * R))) && (NEAREST || ((live >> k) & 1u))) {
+                    const int tri = (int)__float_as_uint(rec[(jb + j) * kRecVec + 3].y);   // triangle id of this record
+                    const float4 e = exact_eval_tri(triv, tri, O.x, O.y, O.z, D.x, D.y, D.z);
+                    ++n_exact;
+                    if (NEAREST) {
+                        // intersectMesh keeps the first (= lowest-index) triangle among equal distances (strict <,
+                        // raytracing.cpp:183); records are not visited in index order, so the index breaks ties here
+                        if (!(e.w < 0.0f) && (e.w < dist[k] || (e.w == dist[k] && tri < best[k]))) {
+                            dist[k] = e.w;
+                            best[k] = tri;
+                            ray_nearer<RP>(fr, k, e.w, band, O);
+                        }
+                    } else {
+                        // isShadow ends with index != -1 iff some hit had distance < FLT_MAX
+                        // (raytracing.cpp:164,183); a NaN / inf distance never registers
+                        if (e.w >= 0.0f && e.w < FLT_MAX && (live & (1u << k))) {
+                            live &= ~(1u << k);
+                            best[k] = tri;
+                            ray_kill<RP>(fr, k);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One tile (kTile records of dominant-axis class W) against this thread's R rays, generic filter.
 template <int RP, int J, bool NEAREST, int W, bool GRAZ, class DistT, class BestT, class Fetch>
 __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, DistT& dist, BestT& best, uint32_t& live,
                                           const float4* __restrict__ triv, float eps_r2, const Fetch& fetch, uint32_t& n_exact) {
     constexpr int R = 2 * RP;
-    constexpr uint32_t REP = BitLayout<RP, J>::kRep;
     const int nvalid = __float_as_int(rec[3].z);   // records in use in this tile (warp-uniform); the rest is padding
 #pragma unroll 1
     for (int jb = 0; jb < nvalid; jb += J) {
@@ -557,40 +703,45 @@ __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, D
                     mask |= ((c0 ? 1u : 0u) << (2 * p) | (c1 ? 1u : 0u) << (2 * p + 1)) << (j * R);
                 }
             }
-            mask &= live * REP;
+            exact_block<RP, J, NEAREST>(mask, rec, jb, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+        }
+    }
+}
+
+// The same against a tile of PENCIL records (no axis classes).
+template <int RP, int J, bool NEAREST, class DistT, class BestT, class Fetch>
+__device__ __forceinline__ void scan_tile_pencil(const float4* rec, PencilRays<RP>& fr, DistT& dist, BestT& best, uint32_t& live,
+                                                 const float4* __restrict__ triv, const Fetch& fetch, uint32_t& n_exact) {
+    constexpr int R = 2 * RP;
+    const int nvalid = __float_as_int(rec[3].z);
+#pragma unroll 1
+    for (int jb = 0; jb < nvalid; jb += J) {
+        uint32_t acc = 0xffffffffu;   // AND of the sign words: bit 31 survives iff every pair of the block is rejected
 #pragma unroll
-            for (int k = 0; k < R; ++k) {
-                const uint32_t mk = (mask >> k) & REP;
-                if (mk) {
-                    v3 O, D;
-                    fetch(k, O, D);
+        for (int j = 0; j < J; ++j) {
+            const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
+            const float4 q2 = rec[(jb + j) * kRecVec + 2], q3 = rec[(jb + j) * kRecVec + 3];
 #pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        if ((mk & (1u << (j * R))) && (NEAREST || ((live >> k) & 1u))) {
-                            const int tri = (int)__float_as_uint(rec[(jb + j) * kRecVec + 3].y);   // triangle id of this record
-                            const float4 e = exact_eval_tri(triv, tri, O.x, O.y, O.z, D.x, D.y, D.z);
-                            ++n_exact;
-                            if (NEAREST) {
-                                // intersectMesh keeps the first (= lowest-index) triangle among equal distances (strict <,
-                                // raytracing.cpp:183); records are not visited in index order, so the index breaks ties here
-                                if (!(e.w < 0.0f) && (e.w < dist[k] || (e.w == dist[k] && tri < best[k]))) {
-                                    dist[k] = e.w;
-                                    best[k] = tri;
-                                    fr.rhi[k] = __float_as_uint(__fadd_ru(e.w, eps_r2));
-                                }
-                            } else {
-                                // isShadow ends with index != -1 iff some hit had distance < FLT_MAX
-                                // (raytracing.cpp:164,183); a NaN / inf distance never registers
-                                if (e.w >= 0.0f && e.w < FLT_MAX && (live & (1u << k))) {
-                                    live &= ~(1u << k);
-                                    best[k] = tri;
-                                    kill_slot<RP>(fr, k);
-                                }
-                            }
-                        }
-                    }
+            for (int p = 0; p < RP; ++p) {
+                uint32_t s0, s1;
+                pencil_pair<RP>(fr, p, q0, q1, q2, q3, s0, s1);
+                acc &= s0 & s1;
+            }
+        }
+        if ((int)acc >= 0) {
+            uint32_t mask = 0;
+#pragma unroll 1
+            for (int j = 0; j < J; ++j) {
+                const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
+                const float4 q2 = rec[(jb + j) * kRecVec + 2], q3 = rec[(jb + j) * kRecVec + 3];
+#pragma unroll
+                for (int p = 0; p < RP; ++p) {
+                    uint32_t s0, s1;
+                    pencil_pair<RP>(fr, p, q0, q1, q2, q3, s0, s1);
+                    mask |= ((~s0 >> 31) << (2 * p) | (~s1 >> 31) << (2 * p + 1)) << (j * R);
                 }
             }
+            exact_block<RP, J, NEAREST>(mask, rec, jb, fr, dist, best, live, triv, 0.0f, fetch, n_exact);
         }
     }
 }
@@ -694,6 +845,16 @@ __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, DistT& d
     }
 }
 
+template <int RP, int J, bool NEAREST, class DistT, class BestT, class Fetch>
+__device__ __forceinline__ void scan_pass_pencil(Pipe& pipe, PencilRays<RP>& fr, DistT& dist, BestT& best, uint32_t& live,
+                                                 const float4* __restrict__ triv, const Fetch& fetch, uint32_t& n_exact, int tile_begin) {
+    for (int tile = tile_begin; tile < tile_begin + (int)pipe.len; ++tile) {
+        const float4* rec = pipe_acquire(pipe);
+        if (__any_sync(0xffffffffu, live != 0u)) scan_tile_pencil<RP, J, NEAREST>(rec, fr, dist, best, live, triv, fetch, n_exact);
+        pipe_release<false>(pipe);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Ray generation, main.cpp:380-386 (exact)
 // ------------------------------------------------------------------------------------------------
@@ -755,8 +916,13 @@ __device__ __forceinline__ void fast_set_slot(FastRays<RP>& fr, int k, v3 O, v3 
     if (k == 7) fast_set<RP, (R > 6 ? 7 : 0)>(fr, O, D, eps_r, ok);
 }
 
-template <int RP, int J, int MINB, bool PRIMARY, bool GRAZ, bool CULL>
+template <bool B, class X, class Y> struct SelectT { using type = X; };
+template <class X, class Y> struct SelectT<false, X, Y> { using type = Y; };
+
+// PENCIL (primary rays of a frame only, brute force): the pencil filter around the eye (P.prec, P.pE).
+template <int RP, int J, int MINB, bool PRIMARY, bool GRAZ, bool CULL, bool PENCIL = false>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant__ FrameParams P, int level) {
+    static_assert(!PENCIL || (PRIMARY && !CULL), "the pencil filter serves primary rays in the brute-force scan");
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
     __shared__ CullStorage<CULL> csm;
@@ -765,13 +931,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
     const uint32_t per_chunk = kThreads * R;
     const Split sp = make_split(count, per_chunk, P.ntiles, true);
     Pipe pipe;
-    pipe_init<CULL>(pipe, sm, P.rec, sp, csm.list());
+    pipe_init<CULL>(pipe, sm, PENCIL ? P.prec : P.rec, sp, csm.list());
     uint32_t n_exact = 0;
     const float eps_r2 = 2.0f * P.eps_r;
 
     for (uint32_t item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
         const uint32_t chunk = item / sp.parts, part = item - chunk * sp.parts;
-        FastRays<RP> fr;
+        typename SelectT<PENCIL, PencilRays<RP>, FastRays<RP>>::type fr;
+        if constexpr (PENCIL) { fr.ex = P.pE[0]; fr.ey = P.pE[1]; fr.ez = P.pE[2]; fr.slack = P.p_lam_slack; }
         ColdState<R, !CULL> st(cold.get());
         auto& dist = st.dist; auto& best = st.best; auto& sid = st.sid;
         uint32_t live = 0;
@@ -802,14 +969,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
             sid[k] = s;
             dist[k] = FLT_MAX;
             best[k] = -1;
-            fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
+            if constexpr (PENCIL) pencil_set_slot<RP>(fr, k, O, D, false, FLT_MAX, ok);
+            else fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
         }
         // fetch() re-reads a ray for the exact path: primary rays of other parts may not be published yet
         auto fetch = [&](int k, v3& O, v3& D) {
             if (PRIMARY && !P.trace_api) { primary_ray(P, sid[k], O, D); }
             else { const float4 o = P.ray_o[sid[k]], d = P.ray_d[sid[k]]; O = mk3(o); D = mk3(d); }
         };
-        if (CULL)
+        if constexpr (PENCIL)
+            scan_pass_pencil<RP, J, true>(pipe, fr, dist, best, live, P.triv, fetch, n_exact, (int)(part * sp.len));
+        else if constexpr (CULL)
             scan_item_culled<RP, J, true, GRAZ>(pipe, csm.get(), fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len),
                                                 min((int)((part + 1) * sp.len), P.ntiles), P.tile_box, P.super_box, P.cls1, P.cls2);
         else
@@ -887,52 +1057,69 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FramePar
 //   NEAREST : the nearest occluder's material decides (transparent -> lit); never split.
 // lit[] arrives with every light's bit set (k_finish); occluded lights are cleared here.
 // ------------------------------------------------------------------------------------------------
-template <int RP, int J, int MINB, bool NEAREST, bool GRAZ, bool CULL>
+// P.light_sel >= 0: the launch serves that light only (one launch per light: pencil launches, and the generic launches of
+// the lights that do not qualify in a frame that uses the pencil filter).
+// PENCIL (any-hit, brute force): the pencil filter around the light.  w points from the light to the hit point, occluders
+// between the two have 0 < lambda <= lambda_O; occluders BEYOND the light (the reference's shadow rays are unbounded)
+// cannot exist for a "safe" ray (FrameParams::p_axis); an unsafe ray skips the scan and is tested exactly against every
+// triangle in the epilogue (rare by construction: pencil_light_setup only accepts lights outside the scene box).
+template <int RP, int J, int MINB, bool NEAREST, bool GRAZ, bool CULL, bool PENCIL = false>
 __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant__ FrameParams P, int level) {
+    static_assert(!PENCIL || (!NEAREST && !CULL), "the pencil filter serves any-hit shadow rays in the brute-force scan");
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
     __shared__ CullStorage<CULL> csm;
     __shared__ ColdStorage<R, !CULL> cold;
-    const uint32_t nl = (uint32_t)P.nlights;
+    const int lsel = P.light_sel;
+    const uint32_t nl = lsel >= 0 ? 1u : (uint32_t)P.nlights;
     const uint32_t count = P.counters[kCntHit + level] * nl;
     const uint32_t per_chunk = kThreads * R;
     const Split sp = make_split(count, per_chunk, P.ntiles, !NEAREST);
     Pipe pipe;
-    pipe_init<CULL>(pipe, sm, P.rec, sp, csm.list());
+    pipe_init<CULL>(pipe, sm, PENCIL ? P.prec : P.rec, sp, csm.list());
     uint32_t n_exact = 0;
     const float eps_r2 = 2.0f * P.eps_r;
 
     for (uint32_t item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
         const uint32_t chunk = item / sp.parts, part = item - chunk * sp.parts;
-        FastRays<RP> fr;
+        typename SelectT<PENCIL, PencilRays<RP>, FastRays<RP>>::type fr;
+        if constexpr (PENCIL) { fr.ex = P.pE[0]; fr.ey = P.pE[1]; fr.ez = P.pE[2]; fr.slack = P.p_lam_slack; }
         ColdState<R, !CULL> st(cold.get());
         auto& dist = st.dist; auto& best = st.best; auto& sid = st.sid;
-        uint32_t live = 0;
+        uint32_t live = 0, valid = 0, unsafe = 0;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const uint32_t ray = chunk * per_chunk + threadIdx.x * R + k;
             const bool ok = ray < count;
+            bool scan = ok;
             v3 O = mk3(0, 0, 0), D = mk3(0, 0, 1);
             sid[k] = 0;
             if (ok) {
-                const uint32_t h = ray / nl, l = ray - h * nl;
+                const uint32_t h = ray / nl, l = lsel >= 0 ? (uint32_t)lsel : ray - h * nl;
                 sid[k] = P.q_hit[h];
                 O = e_add(mk3(P.hit[sid[k]]), mk3(0.1f, 0.1f, 0.1f));
                 D = mk3(P.lights[l][0], P.lights[l][1], P.lights[l][2]);
-                live |= 1u << k;
+                valid |= 1u << k;
+                if constexpr (PENCIL) {
+                    const float go = P.p_axis == 0 ? D.x - O.x : (P.p_axis == 1 ? D.y - O.y : D.z - O.z);   // the sign of a float difference is exact
+                    if (!(P.p_sign * go >= 0.0f)) { unsafe |= 1u << k; scan = false; }
+                }
+                if (scan) live |= 1u << k;
             }
             dist[k] = FLT_MAX;
             best[k] = -1;
-            fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
+            if constexpr (PENCIL) pencil_set_slot<RP>(fr, k, O, D, true, 0.0f, scan);
+            else fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
         }
-        const uint32_t valid = live;
         const uint32_t ray0 = chunk * per_chunk + threadIdx.x * R;   // slot k of this thread is work item ray0 + k
         auto fetch = [&](int k, v3& O, v3& D) {   // the exact shadow ray of slot k: hit + (0.1, 0.1, 0.1) -> light (raytracing.cpp:246-248)
-            const uint32_t l = (ray0 + k) % nl;
+            const uint32_t l = lsel >= 0 ? (uint32_t)lsel : (ray0 + k) % nl;
             O = e_add(mk3(P.hit[sid[k]]), mk3(0.1f, 0.1f, 0.1f));
             D = mk3(P.lights[l][0], P.lights[l][1], P.lights[l][2]);
         };
-        if (CULL)
+        if constexpr (PENCIL)
+            scan_pass_pencil<RP, J, false>(pipe, fr, dist, best, live, P.triv, fetch, n_exact, (int)(part * sp.len));
+        else if constexpr (CULL)
             scan_item_culled<RP, J, NEAREST, GRAZ>(pipe, csm.get(), fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len),
                                                    min((int)((part + 1) * sp.len), P.ntiles), P.tile_box, P.super_box, P.cls1, P.cls2);
         else
@@ -970,6 +1157,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
                 }
             } else {
                 lit = (live >> k) & 1u;  // still alive after every triangle of this part: no occluder found here
+                if (PENCIL && ((unsafe >> k) & 1u)) {   // not scanned: every triangle exactly, once (part 0)
+                    lit = true;
+                    if (part == 0)
+                        for (int tri = 0; lit && tri < P.ntri; ++tri) {
+                            const float4 e = exact_eval_tri(P.triv, tri, O.x, O.y, O.z, D.x, D.y, D.z);
+                            if (e.w >= 0.0f && e.w < FLT_MAX) lit = false;
+                        }
+                    if (part == 0) n_exact += (uint32_t)P.ntri;
+                }
                 if (part == 0) {
                     for (int a = 0; lit && a < P.n_always; ++a) {
                         const float4 e = exact_eval_tri(P.triv, (int)P.always_list[a], O.x, O.y, O.z, D.x, D.y, D.z);
@@ -982,7 +1178,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
                     }
                 }
             }
-            if (!lit) atomicAnd(&P.lit[sid[k]], ~(1u << ((ray0 + k) % nl)));
+            if (!lit) atomicAnd(&P.lit[sid[k]], ~(1u << (lsel >= 0 ? (uint32_t)lsel : (ray0 + k) % nl)));
         }
     }
     if (n_exact) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)n_exact);

@@ -1,0 +1,300 @@
+// rt_pencil.h -- the "pencil" filter: rays whose lines all pass through one common point E.
+//
+// Primary rays all come from the eye (main.cpp:300-320 unprojects the same pixel on the near and the far plane, so the
+// line origin -> dest passes through the eye up to rounding) and every shadow ray of a light ends AT the light
+// (raytracing.cpp:246-248: dest = MyLightPositions[i], exactly).  For such a pencil of lines the ray-triangle test
+// needs no ray origin at all.  With p_i = v_i - E and a ray direction w (pointing away from E):
+//     a = w.(p1 x p2)   b = w.(p2 x p0)   c = w.(p0 x p1)        sigma = a + b + c = w.n,   n = (v1-v0) x (v2-v0)
+// are the (unnormalised) barycentric weights of v0, v1, v2 at the point where the line meets the triangle's plane,
+//     lambda = det / sigma,   det = p0.(p1 x p2)
+// is that point's distance from E along w, and the line pierces the triangle iff a, b, c have the sign of sigma.
+// Hits the reference can accept lie at lambda > 0 (in front of the eye / on the hit point's side of the light, see the
+// launch conditions below), i.e. sign(sigma) = sign(det): the three vectors are pre-multiplied by sign(det), and the
+// candidate test becomes "a', b', c' >= 0 and lambda < lambda_hi" -- three 3-term dot products, two adds and one FMA
+// per (ray, triangle): 12 packed FP32 instructions per ray pair instead of 16, no reciprocal, and the compare logic
+// shrinks to the OR of four sign bits.
+//
+// This header is shared by the CUDA library (record construction in k_build_pencil, launch set-up in rt_b200.cu)
+// and by the CPU soundness test (tests/pencil_check.cpp), which replays the filter with fmaf() -- the filter uses
+// only IEEE FMAs and adds, so the CPU replay is the same arithmetic as the FFMA2/FADD2 instructions.
+//
+// Soundness ("pencil filter"): the tolerances E0, E1 bound the reference's own rounding relative to
+// the true line through its float origin and dest (same constants as the generic filter record).  On top of that
+//   * the true line misses E by at most `delta` and w is within 8u of its direction: the plane point moves by at most
+//     (2.2/|cos|)(delta + 8u*lam_max), a barycentric by gmax times that -> E1p = E1 + 2.5*gmax*(delta + 8u*lam_max);
+//   * a >= -(E0 + E1p/|cos|)*sigma  <=>  w.(A + E0*n) + E1p*|n| >= 0 : E0 is folded into the vector, E1p*|n| into the
+//     constant term of the FMA chain together with the chain's own rounding (<= 4.1u|A'|);
+//   * distance: lambda < lam_O + best + s_lam + K_r/|cos|  <=>  |det| - K_r*|n| < (lam_O + best + s_lam) * sigma, so the
+//     1/|cos| part of the guard band is folded into the per-triangle constant det_lo.
+// Pairs with |cos| < cos_g need no answer: the pencil kernels are only used when the scene-level proof of
+// rt_b200.cu:build_records says the reference rejects every such pair itself (no_grazing; cos_g = 1.05e-5 for a light,
+// max(1.05e-5, 2.5*delta/lambda_min) for the camera: E and the true line must be on the same side of the plane).
+// Exactness of the bound (no first-order argument): with H = signed distance of E to the plane, C = n.w, and H', C'
+// the same for the true line, |H - H'| <= delta <= 0.4|H'| and |C - C'| <= 8u <= 0.05|C'|, so lambda' = H/C has the
+// sign of lambda* = H'/C', |lambda' - lambda*| <= (delta + lambda* 8u)/(0.95|C'|), |X' - X*| <= 2.06(delta + lambda* 8u)/|C'|.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define RT_HD __host__ __device__ __forceinline__
+#else
+#define RT_HD inline
+#endif
+
+namespace rt {
+
+constexpr double kPencilU = 5.9604644775390625e-8;   // 2^-24
+
+// ------------------------------------------------------------------------------------------------
+// Tolerances of one triangle (shared by the generic filter record and the pencil record).
+// W = dominant axis class of the record position (the generic filter's 2-D projection).
+// ------------------------------------------------------------------------------------------------
+struct FilterTol {
+    bool always;            // the filter cannot bound this triangle ("always exact")
+    double n3[3], nn;       // u x v and its length
+    double su, sv, tu, tv;  // projected barycentric functionals (generic record)
+    double E0, E1;
+    int U, V;
+};
+
+RT_HD FilterTol filter_tolerances(const float A[3], const float B[3], const float C[3], int W, double M) {
+    FilterTol t;
+    t.always = false;
+    const double u3[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]};
+    const double v3d[3] = {(double)C[0] - A[0], (double)C[1] - A[1], (double)C[2] - A[2]};
+    t.n3[0] = u3[1] * v3d[2] - u3[2] * v3d[1];
+    t.n3[1] = u3[2] * v3d[0] - u3[0] * v3d[2];
+    t.n3[2] = u3[0] * v3d[1] - u3[1] * v3d[0];
+    t.nn = sqrt(t.n3[0] * t.n3[0] + t.n3[1] * t.n3[1] + t.n3[2] * t.n3[2]);
+    const double uu = u3[0] * u3[0] + u3[1] * u3[1] + u3[2] * u3[2], vv = v3d[0] * v3d[0] + v3d[1] * v3d[1] + v3d[2] * v3d[2];
+    t.U = (W + 1) % 3; t.V = (W + 2) % 3;
+    const double det = u3[t.U] * v3d[t.V] - u3[t.V] * v3d[t.U];   // == n3[W]
+    t.su = t.sv = t.tu = t.tv = 0.0; t.E0 = t.E1 = 0.0;
+    if (!(t.nn > 0.0) || !isfinite(t.nn) || !(uu > 0.0) || !(vv > 0.0) || !(fabs(det) > 0.0) || !isfinite(det)) { t.always = true; return t; }
+    // s = 1 at B, t = 1 at C, both 0 at A, as functions of the (U, V) coordinates
+    t.su = v3d[t.V] / det; t.sv = -v3d[t.U] / det; t.tu = -u3[t.V] / det; t.tv = u3[t.U] / det;
+    const double gs = sqrt(t.su * t.su + t.sv * t.sv), gt = sqrt(t.tu * t.tu + t.tv * t.tv);
+    const double gq = sqrt((t.su + t.tu) * (t.su + t.tu) + (t.sv + t.tv) * (t.sv + t.tv));
+    const double gmax = fmax(gs, fmax(gt, gq));   // >= the in-plane gradients (the projection only stretches them)
+    const double sinphi = t.nn / sqrt(uu * vv);
+    const double kappa = fmax(1.0, 0.25 / sinphi);
+    // DESIGN.md "filter soundness": E0 covers the rounding of the reference's own dot-product barycentrics
+    // (<= 28uM*gmax/sin(phi) + 8u/sin^2(phi)) plus the generic filter's arithmetic (<= 16uM*gmax),
+    // E1*|1/cos| the shift of the plane point caused by the two sides' error along the ray (<= 34uM/|cos|)
+    t.E0 = 256.0 * kPencilU * M * gmax * kappa + 1e-6;
+    t.E1 = 64.0 * kPencilU * M * gmax * kappa;
+    if (!(t.E0 < 64.0) || !isfinite(t.E0)) t.always = true;   // beyond this the dilated triangle is so large that "always exact" is cheaper
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pencil launch set-up (one per common point: the camera, or one light)
+// ------------------------------------------------------------------------------------------------
+struct PencilSetup {
+    double E[3];      // the common point
+    double M;         // power-of-two bound on |coordinate| of the scene, the ray origins and E
+    double delta;     // every ray's true line (through its float origin and dest) passes within delta of E
+    double lam_max;   // >= |X - E| for every scene point X
+    double cos_g;     // the filter answers for pairs with |cos(true line, plane)| >= cos_g; below that the launch must
+                      // be covered by the scene-level proof that the reference rejects the pair itself
+    float lam_slack;  // s_lam: ray-side guard band of the distance test
+    float Ef[3];      // E rounded to float (what the kernels subtract)
+};
+constexpr double kPencilCosMin = 1.05e-5;   // the generic filter's grazing threshold (cos_min = 1e-5) + its 8u evaluation error
+
+// M_scene: bound on |coordinate| of the scene and the ray origins.  Sets M (also covers E), lam_max and s_lam.
+RT_HD void pencil_finish_setup(PencilSetup& S, double M_scene) {
+    double Me = M_scene, e2 = 0.0;
+    for (int k = 0; k < 3; ++k) { Me = fmax(Me, fabs(S.E[k])); e2 += S.E[k] * S.E[k]; S.Ef[k] = (float)S.E[k]; }
+    S.M = Me;
+    S.lam_max = 1.7320508 * M_scene + sqrt(e2) + 1e-3 * Me;   // |X - E| <= |X| + |E|
+    // s_lam = 128uM (reference side + lam_O evaluation) + 3*delta, rounded up
+    S.lam_slack = (float)((128.0 * kPencilU * S.M + 3.0 * S.delta) * 1.0001);
+}
+
+// Pencil record (4 float4 = 64 B, same position / tile layout as the generic record):
+//   q0 = ( A'x, A'y, A'z, sA )   a'' = fma(A'x, wx, fma(A'y, wy, fma(A'z, wz, sA)))      weight of v0 (1 - s - t)
+//   q1 = ( B'x, B'y, B'z, sB )                                                            weight of v1 (s)
+//   q2 = ( C'x, C'y, C'z, sC )                                                            weight of v2 (t)
+//   q3 = ( -det_lo, id, nv, 0 )  e = fma(a''+b''+c'', lambda_hi, -det_lo);  id / nv copied from the generic record
+// candidate  <=>  sign bits of a'', b'', c'', e all clear.   "never" record: A' = B' = C' = 0, slacks = -1.
+RT_HD void pencil_never(float q[16]) {
+    for (int i = 0; i < 12; ++i) q[i] = 0.0f;
+    q[3] = q[7] = q[11] = -1.0f;
+    q[12] = 0.0f; q[15] = 0.0f;   // q[13] (id), q[14] (nv) are the caller's
+}
+
+RT_HD float pencil_round_up(double v) {   // smallest-ish float >= v (v >= 0)
+    float f = (float)v;
+    if ((double)f < v) f = f * 1.0000002f + 1e-37f;
+    return f;
+}
+
+// Returns false (and writes a "never" record) when no ray of the pencil can validly hit the triangle.
+RT_HD bool pencil_record(const float A[3], const float B[3], const float C[3], double E0, double E1, const PencilSetup& S, float q[16]) {
+    double p0[3], p1[3], p2[3], u[3], v[3], e12[3];
+    for (int k = 0; k < 3; ++k) {
+        p0[k] = (double)A[k] - S.E[k]; p1[k] = (double)B[k] - S.E[k]; p2[k] = (double)C[k] - S.E[k];
+        u[k] = (double)B[k] - A[k]; v[k] = (double)C[k] - A[k]; e12[k] = (double)C[k] - B[k];
+    }
+    const double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+    const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    const double det = p0[0] * n[0] + p0[1] * n[1] + p0[2] * n[2];
+    const double lp0 = sqrt(p0[0] * p0[0] + p0[1] * p0[1] + p0[2] * p0[2]);
+    // E (numerically) in the triangle's plane: a valid non-grazing hit would need lambda*|cos| = |det|/|n| <= 1e-9|p0|,
+    // i.e. lambda <= 1e-4*|p0| -- nearer to E than any hit the launch conditions allow (lambda_min >= 1e-3*M).
+    // Also the sign of det (computed to ~1e-15 relative to |p0||n|) is reliable beyond this threshold.
+    if (!(nn > 0.0) || !isfinite(nn) || !isfinite(det) || !(fabs(det) > 1e-9 * lp0 * nn)) { pencil_never(q); return false; }
+    const double sg = det > 0.0 ? 1.0 : -1.0;
+    double Av[3] = {p1[1] * p2[2] - p1[2] * p2[1], p1[2] * p2[0] - p1[0] * p2[2], p1[0] * p2[1] - p1[1] * p2[0]};
+    double Bv[3] = {p2[1] * p0[2] - p2[2] * p0[1], p2[2] * p0[0] - p2[0] * p0[2], p2[0] * p0[1] - p2[1] * p0[0]};
+    double Cv[3] = {p0[1] * p1[2] - p0[2] * p1[1], p0[2] * p1[0] - p0[0] * p1[2], p0[0] * p1[1] - p0[1] * p1[0]};
+    // in-plane gradients of the three weights: |opposite edge| / |n|
+    const double l12 = sqrt(e12[0] * e12[0] + e12[1] * e12[1] + e12[2] * e12[2]);
+    const double lu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), lv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double gmax = fmax(l12, fmax(lu, lv)) / nn;
+    const double shift = S.delta + 8.0 * kPencilU * S.lam_max;          // how far the pencil line can be from the true line near the scene
+    const double E1p = E1 + 2.5 * gmax * shift;
+    const double Kr = 48.0 * kPencilU * S.M + 2.5 * shift;              // 1/|cos| part of the distance guard band
+    double* vec[3] = {Av, Bv, Cv};
+    for (int r = 0; r < 3; ++r) {
+        double len2 = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            const double x = sg * (vec[r][k] + E0 * n[k]);
+            q[4 * r + k] = (float)x;
+            len2 += x * x;
+        }
+        // constant term: E1p*|n| (x1.5) + rounding of the 3-FMA chain and of the stored vector (<= 4.1u|A'|, x2)
+        q[4 * r + 3] = pencil_round_up(1.5 * E1p * nn + 8.0 * kPencilU * sqrt(len2) + 1e-30);
+        if (!isfinite(q[4 * r]) || !isfinite(q[4 * r + 1]) || !isfinite(q[4 * r + 2]) || !isfinite(q[4 * r + 3])) { pencil_never(q); return false; }
+    }
+    // det_lo <= (|det| - Kr*|n|) * (1 - 8u), rounded down; negative is fine (the distance clause then always passes)
+    const double dl = fabs(det) - Kr * nn;
+    double dlo = dl > 0.0 ? dl * (1.0 - 16.0 * kPencilU) : dl * (1.0 + 16.0 * kPencilU);
+    float f = (float)dlo;
+    if ((double)f > dlo) f = f > 0.0f ? f * 0.9999998f : f * 1.0000002f - 1e-37f;
+    q[12] = -f;
+    q[15] = 0.0f;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: can the primary rays of a frame be treated as a pencil, and around which point?
+// corners: the 24 floats of rt_params (4 x (origin, dest): c00, c01, c10, c11 -- main.cpp:355-358).
+// Every primary ray is the bilinear blend (weights w_i >= 0, sum 1) of the four corner rays, origin and dest with the
+// SAME weights (main.cpp:380-386).  With o_i = O_i - E, d_i = D_i - E:
+//     (O - E) x (D - E) = sum_i w_i^2 (o_i x d_i) + sum_{i<j} w_i w_j (o_i x d_j + o_j x d_i)
+// is bounded by max(|o_i x d_i|, |o_i x d_j + o_j x d_i| / 2) because sum_i w_i^2 + 2 sum_{i<j} w_i w_j = 1, and
+// |D - O| >= min_i (d_i - o_i).g for the unit mean direction g.  Their ratio bounds the distance from E to the exact
+// blended line; the float evaluation of the blend moves origin and dest by <= eps_o each.
+// Returns false when the frame is not a (forward) pencil: parallel rays, eye behind the near plane, ...
+// ------------------------------------------------------------------------------------------------
+inline bool pencil_camera_setup(const float corners[24], double M_scene, PencilSetup& S) {
+    double O[4][3], D[4][3], g[4][3];
+    double Mc = 0.0;
+    for (int c = 0; c < 4; ++c)
+        for (int k = 0; k < 3; ++k) {
+            O[c][k] = corners[6 * c + k]; D[c][k] = corners[6 * c + 3 + k]; g[c][k] = D[c][k] - O[c][k];
+            if (!isfinite(O[c][k]) || !isfinite(D[c][k])) return false;
+            Mc = fmax(Mc, fmax(fabs(O[c][k]), fabs(D[c][k])));
+        }
+    // least-squares point closest to the four corner lines: sum_i (I - g_i g_i^T) E = sum_i (I - g_i g_i^T) O_i
+    double Am[3][3] = {{0}}, bv[3] = {0, 0, 0};
+    for (int c = 0; c < 4; ++c) {
+        const double l2 = g[c][0] * g[c][0] + g[c][1] * g[c][1] + g[c][2] * g[c][2];
+        if (!(l2 > 0.0)) return false;
+        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < 3; ++k) {
+                const double m = (r == k ? 1.0 : 0.0) - g[c][r] * g[c][k] / l2;
+                Am[r][k] += m; bv[r] += m * O[c][k];
+            }
+    }
+    const double det = Am[0][0] * (Am[1][1] * Am[2][2] - Am[1][2] * Am[2][1]) - Am[0][1] * (Am[1][0] * Am[2][2] - Am[1][2] * Am[2][0]) +
+                       Am[0][2] * (Am[1][0] * Am[2][1] - Am[1][1] * Am[2][0]);
+    if (!(fabs(det) > 1e-9)) return false;   // (near-)parallel rays: no common point
+    double E[3];
+    for (int k = 0; k < 3; ++k) {
+        double Mk[3][3];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Mk[r][c] = (c == k) ? bv[r] : Am[r][c];
+        E[k] = (Mk[0][0] * (Mk[1][1] * Mk[2][2] - Mk[1][2] * Mk[2][1]) - Mk[0][1] * (Mk[1][0] * Mk[2][2] - Mk[1][2] * Mk[2][0]) +
+                Mk[0][2] * (Mk[1][0] * Mk[2][1] - Mk[1][1] * Mk[2][0])) / det;
+        if (!isfinite(E[k])) return false;
+    }
+    double o[4][3], d[4][3];
+    for (int c = 0; c < 4; ++c) for (int k = 0; k < 3; ++k) { o[c][k] = O[c][k] - E[k]; d[c][k] = D[c][k] - E[k]; }
+    auto cross = [](const double* a, const double* b, double* r) { r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0]; };
+    auto norm = [](const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+    double crossmax = 0.0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = i; j < 4; ++j) {
+            double x[3], y[3];
+            cross(o[i], d[j], x);
+            if (i == j) { crossmax = fmax(crossmax, norm(x)); continue; }
+            cross(o[j], d[i], y);
+            const double s[3] = {x[0] + y[0], x[1] + y[1], x[2] + y[2]};
+            crossmax = fmax(crossmax, 0.5 * norm(s));
+        }
+    double gm[3] = {0, 0, 0};
+    for (int c = 0; c < 4; ++c) for (int k = 0; k < 3; ++k) gm[k] += g[c][k];
+    const double gl = norm(gm);
+    if (!(gl > 0.0)) return false;
+    for (int k = 0; k < 3; ++k) gm[k] /= gl;
+    double lenmin = INFINITY, lam_o_min = INFINITY, lenmax = 0.0;
+    for (int c = 0; c < 4; ++c) {
+        lenmin = fmin(lenmin, g[c][0] * gm[0] + g[c][1] * gm[1] + g[c][2] * gm[2]);
+        lenmax = fmax(lenmax, norm(g[c]));
+    }
+    if (!(lenmin > 0.0)) return false;
+    // forward pencil: (O - E).(D - O) > 0 for every blend  <=  o_i.g_j > 0 for all i, j; the smallest o_i.g_j / max|g|
+    // is a lower bound of lambda_O (distance from E to the ray origin along the ray)
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) lam_o_min = fmin(lam_o_min, (o[i][0] * g[j][0] + o[i][1] * g[j][1] + o[i][2] * g[j][2]) / lenmax);
+    if (!(M_scene < 1e18)) return false;
+    double Me = M_scene, omax = 0.0;
+    for (int k = 0; k < 3; ++k) { Me = fmax(Me, fabs(E[k])); S.E[k] = E[k]; }
+    for (int c = 0; c < 4; ++c) omax = fmax(omax, norm(o[c]));
+    // float evaluation of the blend: <= 4u*Mc per component on origin and dest, plus the common scaling (1 + eta),
+    // |eta| <= 2u, of both about the world origin (the float weights do not sum to exactly 1).  Moving origin and dest
+    // by eps moves the line's point at parameter tau (0 at the origin, 1 at dest) by <= (|1 - tau| + |tau|)*eps; E sits
+    // at tau = -lambda_O / |D - O|, |tau| <= omax / lenmin.
+    const double eps_o = 4.0 * kPencilU * 1.7320508 * Mc + 2.0 * kPencilU * 1.7320508 * fmax(Mc, Me);
+    S.delta = crossmax / lenmin + (1.0 + 2.0 * omax / lenmin) * eps_o;
+    pencil_finish_setup(S, M_scene);
+    // launch conditions: E well in front of every ray origin (lambda_min >= 2e-3*M, see pencil_record) and a usable delta
+    const double lam_min = lam_o_min - 4.0 * S.delta - 64.0 * kPencilU * S.M;
+    if (!(lam_min >= 2e-3 * S.M)) return false;
+    if (!(S.delta <= 1e-3 * S.M)) return false;
+    // E and the true line's closest point E' must lie on the same side of every plane a valid pair can hit:
+    // |dist(E', plane)| = lambda*|cos| >= lam_min*cos_g must exceed delta with room to spare (factor 2.5)
+    S.cos_g = fmax(kPencilCosMin, 2.5 * S.delta / lam_min);
+    return true;
+}
+
+// Shadow rays of one light: dest = the light exactly, so delta = 0.  box_lo / box_hi: the bounding box of everything a
+// filter record can make a hit of (union of the tile boxes).  The pencil handles occluders on the hit point's side of
+// the light; a ray whose continuation BEYOND the light could re-enter the box is handled exactly by the kernel
+// (k_shadow, "unsafe" rays).  The launch is worthwhile only if the light is outside the box along some axis by a gap
+// >= 2e-3*M (then lambda >= gap for every record hit, and rays from inside the box are all safe).
+// axis / sign: ray with origin O is safe iff sign * (L[axis] - O[axis]) >= 0.
+inline bool pencil_light_setup(const float L[3], const float box_lo[3], const float box_hi[3], double M_scene, PencilSetup& S, int& axis, float& sign) {
+    double Me = M_scene;
+    for (int k = 0; k < 3; ++k) { if (!isfinite(L[k])) return false; Me = fmax(Me, fabs((double)L[k])); }
+    if (!(Me < 1e18)) return false;
+    double best_gap = 0.0;
+    axis = -1; sign = 0.f;
+    for (int k = 0; k < 3; ++k) {
+        if (!(box_lo[k] <= box_hi[k])) continue;   // empty / NaN box
+        const double up = (double)L[k] - box_hi[k], dn = (double)box_lo[k] - L[k];
+        if (up > best_gap) { best_gap = up; axis = k; sign = 1.f; }
+        if (dn > best_gap) { best_gap = dn; axis = k; sign = -1.f; }
+    }
+    if (axis < 0 || !(best_gap >= 2e-3 * Me)) return false;
+    for (int k = 0; k < 3; ++k) S.E[k] = L[k];
+    S.delta = 0.0;
+    S.cos_g = kPencilCosMin;
+    pencil_finish_setup(S, M_scene);
+    return true;
+}
+}  // namespace rt

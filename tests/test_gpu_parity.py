@@ -435,6 +435,47 @@ def test_fine_mesh_uses_the_clause_free_kernels(gpu, port):
     assert not (gpu.stats()["variant"] & 1)
 
 
+def test_pencil_filter_is_invisible(gpu, port):
+    """RT_OPT_PENCIL (default on): primary rays are filtered around the eye and each light's shadow rays around the
+    light whenever the frame qualifies.  Ids, float RGB bits and ray counts must equal the generic filter's, and the
+    oracle's on a lattice -- on the headline scene (default and low camera), with a light inside the scene box (its
+    shadow rays keep the generic filter), several lights, and a camera inside the mesh."""
+    from raytracert_b200 import binding, host, scenes
+    big = scenes.balls_standin()
+    sph = scenes.tessellated_sphere(slices=200, stacks=101)
+    cases = [
+        (big, host.Camera(200, 160, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0)), 2, 3, [(2.5, 4.0, 3.0)], 6),
+        (big, host.Camera(160, 120), 2, 3, [(0.0, 0.0, 4.0)], 6),                                    # the bench camera: eye in the water plane
+        (big, host.Camera(160, 120, (0.2, 0.75, 4.6), (0.0, 0.62, 0.0)), 2, 2, [(2.5, 4.0, 3.0), (0.1, 0.6, 0.2), (-3.0, 2.0, 0.5)], 6),
+        (sph, host.Camera(120, 120, (1.2, 0.9, 2.6), (0.0, 0.0, 0.0)), 2, 2, [(1.2, 0.9, 2.6), (0.0, 3.0, 0.0)], 6),
+        (sph, host.Camera(96, 96, (0.2, 0.1, 0.3), (0.0, 0.0, -1.0)), 1, 2, [(0.2, 0.1, 0.3), (0.0, 0.0, 3.0)], 6),   # eye and one light inside the sphere
+    ]
+    try:
+        for i, (s, cam, pf, lvl, lights, expect) in enumerate(cases):
+            lights = np.asarray(lights, np.float32)
+            c = dict(corners=cam.corners, W=cam.W, H=cam.H, pfx=pf, pfy=pf, max_lvl=lvl, features=63, eye=cam.eye, lights=lights)
+            gpu.set_option(binding.RT_OPT_PENCIL, 0)
+            rgb0, prim0 = gpu_render(gpu, s, c)
+            st0 = gpu.stats()
+            assert not (st0["variant"] & 6)
+            gpu.set_option(binding.RT_OPT_PENCIL, 1)
+            rgb1, prim1 = gpu_render(gpu, s, c)
+            st1 = gpu.stats()
+            assert (st1["variant"] & 6) == expect, f"case {i}: variant {st1['variant']}"
+            assert np.array_equal(prim0, prim1), f"case {i}: {np.count_nonzero(prim0 != prim1)} ids differ"
+            assert np.array_equal(bits(rgb0), bits(rgb1)), f"case {i}: framebuffers differ"
+            for k in ("primary_rays", "shadow_rays", "bounce_rays"):
+                assert st0[k] == st1[k], (i, k)
+            port.set_scene(s); port.configure(cam.eye, lights, 63, lvl)
+            prim1 = prim1.reshape(cam.H, -1)
+            for y in range(3, cam.H, 17):
+                rgb_o, _, prim_o = port.render(cam.corners, cam.W, cam.H, pf, pf, y0=y, ystep=cam.H, want_samples=True)
+                assert np.array_equal(prim1[y], prim_o.reshape(cam.H, -1)[y]), f"case {i} row {y}"
+                assert np.abs(rgb1[y] - rgb_o[y]).max() <= RGB_TOL, f"case {i} row {y}"
+    finally:
+        gpu.set_option(binding.RT_OPT_PENCIL, 1)
+
+
 @pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("RT_FUZZ_SEEDS", "24"))))
 def test_fuzz_random_scenes(gpu, port, seed):
     """Seeded random scenes / cameras / lights / feature masks / materials (incl. transparent ones and analytic

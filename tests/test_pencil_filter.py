@@ -1,0 +1,240 @@
+"""Soundness of the pencil filter (raytracert_b200/csrc/rt_pencil.h) on the CPU.
+
+The pencil filter of k_trace / k_shadow uses only IEEE FMAs and adds, so tests/pencil_check.cpp replays it with fmaf()
+-- the same record construction code the CUDA library compiles, the same operation order -- for EVERY (ray, triangle)
+pair of a scene and compares with the oracle's decision for that pair (oracle/rt_oracle.c:orc_ray_triangle): whatever
+the reference accepts must be a candidate.  Rays: the frame's primary rays (oracle arithmetic), shadow rays from the
+oracle's hit points, and shadow rays from random points on the surfaces.  Runs without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+SO = os.path.join(ROOT, "raytracert_b200", "_build", "pencil_check.so")
+SRC = os.path.join(ROOT, "tests", "pencil_check.cpp")
+HDR = os.path.join(ROOT, "raytracert_b200", "csrc", "rt_pencil.h")
+
+
+class Result(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("pairs", "ref_hits", "candidates", "violations", "grazing_skipped", "unsafe_rays", "always_tris", "never_recs")] + \
+               [(n, C.c_int32) for n in ("setup_ok", "first_bad_ray", "first_bad_tri", "pad")] + [("delta", C.c_double), ("M", C.c_double), ("cos_g", C.c_double)]
+
+
+@pytest.fixture(scope="session")
+def checker(port):
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", SO, SRC], check=True)
+    L = C.CDLL(SO)
+    L.pencil_check.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(Result)]
+    pair_fn = C.cast(port.L.orc_ray_triangle, C.c_void_p)
+
+    def run(mode, setup, M, tris, rays, inv_scale=1.0):
+        setup = np.ascontiguousarray(setup, np.float32)
+        tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        r = Result()
+        L.pencil_check(mode, setup.ctypes.data, float(M), len(tris), tris.ctypes.data, len(rays), rays.ctypes.data, inv_scale, pair_fn, C.byref(r))
+        return r
+    return run
+
+
+def pow2_ceil(v):
+    m = 1.0 / 1024.0
+    while m < v:
+        m *= 2.0
+    return m
+
+
+def magnitude_bound(scene, corners):
+    """rt_b200.cu:magnitude_bound."""
+    ext = float(np.abs(scene.vertices[np.isfinite(scene.vertices)]).max()) if scene.vertices.size else 0.0
+    c = np.asarray(corners, np.float32).reshape(4, 6)
+    return pow2_ceil(max(ext + 0.5, float(np.abs(c[:, :3]).max())))
+
+
+def primary_rays(corners, W, H, pf, step):
+    """main.cpp:380-386 in float32, every step-th pixel of every step-th row, all sub-samples."""
+    c = np.asarray(corners, np.float32).reshape(4, 2, 3)   # c00, c01, c10, c11 x (origin, dest)
+    f = np.float32
+    divX, divY = f(W * pf - 1), f(H * pf - 1)
+    out = []
+    for y in range(0, H, step):
+        for x in range(0, W, step):
+            for sx in range(pf):
+                for sy in range(pf):
+                    xs = f(1) - (f(x) * f(pf) + f(sx)) / divX
+                    ys = f(1) - (f(y) * f(pf) + f(sy)) / divY
+                    omx, omy = f(1) - xs, f(1) - ys
+                    ray = []
+                    for k in range(2):
+                        top = (c[0, k] * xs + c[2, k] * omx) * ys
+                        bot = (c[1, k] * xs + c[3, k] * omx) * omy
+                        ray.append((top + bot).astype(np.float32))
+                    out.append(np.concatenate(ray))
+    return np.array(out, np.float32)
+
+
+def tri_array(scene):
+    return scene.vertices[scene.indices].reshape(-1, 9)
+
+
+def scene_box(tris, M):
+    """A box at least as large as the union of the tile boxes (k_build_tile_boxes): the triangles + a margin."""
+    t = tris.reshape(-1, 3)
+    t = t[np.isfinite(t).all(axis=1)]
+    m = 0.05 + M * 2.0 ** -14
+    return t.min(axis=0) - m, t.max(axis=0) + m
+
+
+def edge_points(tris, rng, n):
+    """Points ON the edges and AT the vertices of random triangles (float32): rays aimed at them make the reference's
+    own inside/outside decision a coin flip, which is where a filter tolerance that is too tight would show."""
+    t = tris.reshape(-1, 3, 3)
+    pick = rng.integers(0, len(t), n)
+    e = rng.integers(0, 3, n)
+    u = rng.uniform(0, 1, n).astype(np.float32)
+    u[: n // 4] = 0.0                                   # vertices
+    a, b = t[pick, e], t[pick, (e + 1) % 3]
+    return (a + (b - a) * u[:, None]).astype(np.float32)
+
+
+def grazing_product(tris, rays):
+    """max |u||v| over the triangles x max |dest - origin| over the rays (rt_b200.cu:build_records)."""
+    t = tris.reshape(-1, 3, 3).astype(np.float64)
+    uv = np.linalg.norm(t[:, 1] - t[:, 0], axis=1) * np.linalg.norm(t[:, 2] - t[:, 0], axis=1)
+    r = rays.astype(np.float64)
+    return float(uv.max() * np.linalg.norm(r[:, 3:] - r[:, :3], axis=1).max())
+
+
+def check_frame(checker, port, scene, cam, W, H, pf, lights, step, expect_cam=True):
+    tris = tri_array(scene)
+    M = magnitude_bound(scene, cam.corners)
+    rays = primary_rays(cam.corners, W, H, pf, step)
+    if expect_cam:
+        # adversarial primary rays: from the eye through edge / vertex points, origin one unit from the eye like a
+        # near-plane origin (their lines pass within rounding of the eye, far inside the set-up's delta)
+        rng = np.random.default_rng(11)
+        P = edge_points(tris, rng, 1500)
+        eye = np.asarray(cam.eye, np.float32)
+        d = P - eye
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        fwd = np.asarray(cam.corners, np.float32).reshape(4, 2, 3)
+        fwd = (fwd[:, 1] - fwd[:, 0]).mean(axis=0)
+        keep = d @ fwd > 0                              # in front of the camera
+        adv = np.concatenate([eye + d[keep], eye + np.float32(9.0) * d[keep]], axis=1).astype(np.float32)
+    else:
+        adv = rays[:0]
+    total = dict(pairs=0, ref_hits=0, candidates=0)
+    n_lattice = len(rays)
+    for scale in (1.0, 1.0 + 3 * 2.0 ** -24, 1.0 - 3 * 2.0 ** -24):     # rsqrtf is accurate to ~2 ulp
+        for batch in (rays, adv):
+            if not len(batch):
+                continue
+            r = checker(0, cam.corners, M, tris, batch, scale)
+            assert bool(r.setup_ok) == expect_cam, "camera pencil set-up"
+            if not r.setup_ok:
+                break
+            assert r.violations == 0, f"primary: {r.violations} accepted pairs were filtered out (first: ray {r.first_bad_ray}, triangle {r.first_bad_tri})"
+            if r.cos_g * grazing_product(tris, batch) <= 0.9e-5:    # the clause-free premise holds for this batch
+                assert r.grazing_skipped == 0
+            if batch is rays:     # selectivity is judged on the frame's own rays
+                for k in total:
+                    total[k] += getattr(r, k)
+    rays = np.concatenate([rays, adv])
+    # shadow rays: from the oracle's hit points of these primary rays, and from random surface points
+    port.set_scene(scene)
+    port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
+    _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+    origins = [hit[prim >= 0]]
+    rng = np.random.default_rng(5)
+    pick = rng.integers(0, len(tris), 400)
+    bary = rng.dirichlet((1, 1, 1), 400).astype(np.float32)
+    origins.append((tris[pick].reshape(-1, 3, 3) * bary[:, :, None]).sum(axis=1).astype(np.float32))
+    origins = (np.concatenate(origins).astype(np.float32) + np.float32(0.1)).astype(np.float32)   # raytracing.cpp:246
+    lo, hi = scene_box(tris, M)
+    n_light_ok = 0
+    for Lp in lights:
+        Lp = np.asarray(Lp, np.float32)
+        # adversarial shadow rays: origins placed so that the ray to the light passes through an edge / vertex point
+        P = edge_points(tris, rng, 1200)
+        back = P + (P - Lp) * rng.uniform(0.05, 1.5, (len(P), 1)).astype(np.float32)
+        all_o = np.concatenate([origins, back.astype(np.float32)])
+        srays = np.concatenate([all_o, np.broadcast_to(Lp, all_o.shape)], axis=1)
+        setup = np.concatenate([Lp, lo, hi]).astype(np.float32)
+        for scale in (1.0, 1.0 + 3 * 2.0 ** -24):
+            r = checker(1, setup, M, tris, srays, scale)
+            if not r.setup_ok:
+                break
+            assert r.violations == 0, f"shadow {Lp}: {r.violations} accepted pairs were filtered out (first: ray {r.first_bad_ray}, triangle {r.first_bad_tri})"
+            if r.cos_g * grazing_product(tris, srays) <= 0.9e-5:
+                assert r.grazing_skipped == 0
+        n_light_ok += int(r.setup_ok)
+    return total, n_light_ok
+
+
+def test_pencil_sound_on_the_balls_standin(checker, port):
+    """Reduced Balls stand-in (same generator as the headline scene), default and low grazing camera, near lights."""
+    from raytracert_b200 import host, scenes
+    s = scenes.balls_standin(grid=40, slices=24, stacks=12)
+    cam = host.Camera(64, 48)
+    total, nl = check_frame(checker, port, s, cam, 64, 48, 2, [tuple(cam.eye), (2.5, 4.0, 3.0)], step=3)
+    assert total["ref_hits"] > 500 and nl == 2
+    # selectivity: the filter must stay a filter (a few candidates per accepted pair, not "everything")
+    assert total["candidates"] < 20 * total["ref_hits"]
+    cam2 = host.Camera(64, 48, (0.2, 0.75, 4.6), (0.0, 0.62, 0.0))     # near-tangent rays over the terrain
+    total2, _ = check_frame(checker, port, s, cam2, 64, 48, 2, [(2.5, 4.0, 3.0), (-3.0, 2.0, 0.5)], step=3)
+    assert total2["ref_hits"] > 500
+
+
+def test_pencil_sound_on_a_tessellated_sphere(checker, port):
+    from raytracert_b200 import host, scenes
+    s = scenes.tessellated_sphere(slices=96, stacks=49)
+    cam = host.Camera(48, 48, (1.2, 0.9, 2.6), (0.0, 0.0, 0.0))
+    total, nl = check_frame(checker, port, s, cam, 48, 48, 2, [tuple(cam.eye), (0.0, 3.0, 0.0)], step=2)
+    assert total["ref_hits"] > 1000 and nl == 2
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_pencil_sound_on_random_fine_soups(checker, port, seed):
+    """The fuzz test's 'fine mesh' kind: random small triangles, random cameras (sometimes inside the soup) and lights."""
+    from raytracert_b200 import host
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.integers(50, 400))
+    ctr = rng.uniform(-1.5, 1.5, (n, 1, 3))
+    tri = ctr + 0.08 * rng.normal(size=(n, 3, 3))
+    if seed == 3:
+        tri += np.array([40.0, -25.0, 10.0])     # far from the world origin: larger magnitude bound
+    v = tri.reshape(-1, 3).astype(np.float32)
+    idx = np.arange(len(v), dtype=np.uint32).reshape(-1, 3)
+    mats = np.zeros((1, 16), np.float32)
+    s = host.Scene(v, idx, np.zeros(n, np.uint32), host.face_normals(v, idx), mats)
+    centre = v.mean(axis=0)
+    eye = centre + (rng.uniform(-1, 1, 3) + np.array([0, 0, 5.0]) if seed % 3 else rng.uniform(-0.5, 0.5, 3))
+    cam = host.Camera(40, 32, tuple(eye), tuple(centre + rng.uniform(-0.5, 0.5, 3)))
+    lights = centre + rng.uniform(-6, 6, (3, 3))
+    total, _ = check_frame(checker, port, s, cam, 40, 32, 2, [tuple(l) for l in lights], step=1)
+    assert total["pairs"] > 0
+
+
+def test_camera_setup_rejects_what_is_not_a_pencil(checker):
+    """Parallel (orthographic) corner rays, or an eye between the ray origins and the scene, must not use the pencil."""
+    from raytracert_b200 import host
+    tris = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    rays = np.array([[0, 0, 4, 0, 0, -6]], np.float32)
+    ortho = np.array([[-1, 1, 4, -1, 1, -6], [-1, -1, 4, -1, -1, -6], [1, 1, 4, 1, 1, -6], [1, -1, 4, 1, -1, -6]], np.float32)
+    assert not checker(0, ortho.reshape(-1), 8.0, tris, rays).setup_ok
+    cam = host.Camera(32, 32)
+    c = cam.corners.reshape(4, 2, 3).copy()
+    c = c[:, ::-1, :]                                   # origin and dest swapped: rays run TOWARDS the common point
+    assert not checker(0, np.ascontiguousarray(c).reshape(-1), 8.0, tris, rays).setup_ok
+    assert checker(0, cam.corners, 8.0, tris, rays).setup_ok
+    # light inside the scene box: no pencil for its shadow rays
+    setup = np.array([0.2, 0.2, 0.0, -1, -1, -1, 1, 1, 1], np.float32)
+    assert not checker(1, setup, 8.0, tris, rays).setup_ok
+    setup[:3] = (0.2, 0.2, 3.0)
+    assert checker(1, setup, 8.0, tris, rays).setup_ok
