@@ -399,8 +399,6 @@ struct PencilPlan {
     bool cam = false, any_light = false;
     bool light[RT_MAX_LIGHTS] = {};
     PencilSetup cam_setup, light_setup[RT_MAX_LIGHTS];
-    int axis[RT_MAX_LIGHTS] = {};
-    float sign[RT_MAX_LIGHTS] = {};
     size_t slot_vec = 0;   // float4 per record slot
 };
 
@@ -408,6 +406,8 @@ void apply_pencil(FrameParams& P, const RtDevice& d, const PencilPlan& plan, int
     P.prec = d.prec + (size_t)slot * plan.slot_vec;
     P.pE[0] = S.Ef[0]; P.pE[1] = S.Ef[1]; P.pE[2] = S.Ef[2];
     P.p_lam_slack = S.lam_slack;
+    memcpy(P.pF, S.F, sizeof(P.pF));
+    P.p_wmax2 = S.w_max2;
 }
 
 // Decide which launches of this frame can use the pencil filter and build their records.  Conditions: brute force
@@ -419,21 +419,26 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
     const int npad = (d.ntiles + kPadTiles) * kTile;
     plan.slot_vec = (size_t)npad * kRecVec;
     const bool shadows = (rp.features & RT_SHADOWS) && rp.n_lights > 0 && !g.any_transparent;
-    plan.cam = pencil_camera_setup(rp.corners, (double)d.M_built, plan.cam_setup);
-    if (plan.cam && plan.cam_setup.cos_g > kPencilCosMin) {
-        // the camera pencil answers only for |cos| >= cos_g (> the generic 1.05e-5): the clause-free proof of build_records
-        // must hold at that threshold for the primary rays, |b_ref| < |dir||u||v| (cos_g + 10u) < 1e-5
+    // A pencil answers only for pairs with |cos| >= cos_g (>= the generic 1.05e-5): the clause-free proof of
+    // build_records must hold at that threshold for the launch's rays, |b_ref| < |dir||u||v| (cos_g + 10u) < 1e-5.
+    auto proof_holds = [&](const PencilSetup& S, double dir_max) { return (S.cos_g + 6e-7) * (double)g.max_uv * dir_max * 1.01 <= 0.95e-5; };
+    plan.cam = pencil_camera_setup(rp.corners, (double)d.M_built, d.box_lo, d.box_hi, plan.cam_setup);
+    if (plan.cam) {
         double dir_cam = 0.0;
         for (int c = 0; c < 4; ++c) {
             double l2 = 0.0;
             for (int k = 0; k < 3; ++k) { const double t = (double)rp.corners[c * 6 + 3 + k] - rp.corners[c * 6 + k]; l2 += t * t; }
             dir_cam = std::max(dir_cam, std::sqrt(l2));
         }
-        if (!((plan.cam_setup.cos_g + 6e-7) * (double)g.max_uv * dir_cam * 1.01 <= 0.95e-5)) plan.cam = false;
+        plan.cam = proof_holds(plan.cam_setup, dir_cam);
     }
     if (shadows)
         for (uint32_t l = 0; l < rp.n_lights; ++l) {
-            plan.light[l] = pencil_light_setup(rp.lights[l], d.box_lo, d.box_hi, (double)d.M_built, plan.light_setup[l], plan.axis[l], plan.sign[l]);
+            // shadow-ray length: |hit + 0.1 - light| for a hit inside the scene bound (as in direction_bound)
+            double l2 = 0.0;
+            for (int k = 0; k < 3; ++k) l2 += (double)rp.lights[l][k] * rp.lights[l][k];
+            const double dir_l = std::sqrt(l2) + 1.7320508 * ((double)g.scene_extent + 0.1);
+            plan.light[l] = pencil_light_setup(rp.lights[l], d.box_lo, d.box_hi, (double)d.M_built, plan.light_setup[l]) && proof_holds(plan.light_setup[l], dir_l);
             plan.any_light = plan.any_light || plan.light[l];
         }
     if (!plan.cam && !plan.any_light) return RT_OK;
@@ -479,7 +484,6 @@ int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullp
                 Pl.light_sel = l;
                 if (plan->light[l]) {
                     apply_pencil(Pl, d, *plan, 1 + l, plan->light_setup[l]);
-                    Pl.p_axis = plan->axis[l]; Pl.p_sign = plan->sign[l];
                     dispatch_scan(g.scan, kScanShadowPencil, d.num_sms, d.stream, Pl, level, false);
                 } else {
                     dispatch_scan(g.scan, kScanShadowAny, d.num_sms, d.stream, Pl, level, !d.no_grazing);

@@ -103,8 +103,8 @@ struct FrameParams {
     float pE[3];                // the common point, float
     float p_lam_slack;          // s_lam: ray-side guard band of the distance clause
     int light_sel;              // k_shadow: >= 0 -> this launch handles only that light; -1 -> all lights (ray = hit * nlights + light)
-    int p_axis;                 // shadow pencil: a ray with origin O is "safe" (no occluder beyond the light can exist)
-    float p_sign;               //                iff p_sign * (L[p_axis] - O[p_axis]) >= 0
+    float pF[9];                // chart frame u, v, f: a ray is (x, y, 1) = dir / (dir.f) in it
+    float p_wmax2;              // chart bound: 1 + x^2 + y^2 <= p_wmax2, else the ray is not filtered (exact path for everything)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -537,72 +537,82 @@ __device__ __forceinline__ void kill_slot(FastRays<RP>& f, int k) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pencil filter (rt_pencil.h): rays through a common point.  8 registers per ray pair, 12 packed FP32 instructions
-// and 4 LOP3 per (ray pair, triangle); the hot loop ANDs the sign words, "any candidate" = sign bit of the AND clear.
+// Pencil filter (rt_pencil.h): rays through a common point, in the launch's projective chart.  6 registers per ray
+// pair, 9 packed FP32 instructions and 4 LOP3 per (ray pair, triangle); the hot loop ANDs the sign words per ray,
+// "any candidate in the block" = some live ray's AND has its sign bit clear.
 // ------------------------------------------------------------------------------------------------
 template <int RP>
 struct PencilRays {
-    float2 wx[RP], wy[RP], wz[RP];  // direction away from the common point (+-unit ray direction); 0 = finished / unused / degenerate
-    float2 lhi[RP];                 // lambda_hi = lambda_O + nearest distance so far + s_lam; -inf = finished / unused; +inf = degenerate ray (always exact)
-    float ex, ey, ez, slack;        // common point, s_lam (uniform)
+    float2 x[RP], y[RP];    // chart coordinates of the direction away from the common point: dir / (dir.f) = (x, y, 1); NaN = not representable (every triangle exact)
+    float2 zhi[RP];         // depth bound of the distance clause: depth of the origin + (nearest distance so far + s_lam) / |(x, y, 1)|
+    uint32_t dead[2 * RP];  // 0x80000000: finished / unused slot (its sign words are ignored)
 };
 __device__ __forceinline__ float& pair_elem(float2& v, int odd) { return odd ? v.y : v.x; }
 
-// flip: w = -(dest - origin)/|..| (shadow rays: the pencil's centre is the ray's DEST).  nearest0: initial nearest distance
-// (FLT_MAX for a nearest-hit ray that has found nothing yet, 0 for an any-hit shadow ray: r >= 0 <=> lambda <= lambda_O).
+__device__ __forceinline__ float pencil_depth(const FrameParams& P, v3 O) {   // (O - E).f
+    return fmaf(O.x - P.pE[0], P.pF[6], fmaf(O.y - P.pE[1], P.pF[7], (O.z - P.pE[2]) * P.pF[8]));
+}
+// depth bound for a ray whose nearest accepted distance so far is `nearest` (0 for an any-hit shadow ray: r >= 0)
+__device__ __forceinline__ float pencil_zhi(const FrameParams& P, v3 O, float x, float y, float nearest) {
+    const float c = __fmul_ru(rsqrtf(fmaf(x, x, fmaf(y, y, 1.0f))), 1.000002f);   // >= 1/|(x, y, 1)|: depth gained per unit of distance
+    float z = __fadd_ru(pencil_depth(P, O), __fmul_ru(__fadd_ru(nearest, P.p_lam_slack), c));
+    if (!(z < FLT_MAX)) z = FLT_MAX;   // "nothing yet" (nearest = FLT_MAX) and NaN (ray outside the chart): no bound
+    return z;
+}
+
+// flip: the pencil's centre is the ray's DEST (shadow rays), the direction away from it is origin - dest.
+// Returns false when the ray cannot be represented in the chart (does not point into the chart's half space, too far
+// off axis, not finite); the slot then holds NaN coordinates = candidate for every triangle.
 template <int RP>
-__device__ __forceinline__ void pencil_set_slot(PencilRays<RP>& f, int k, v3 O, v3 D, bool flip, float nearest0, bool live) {
-    float dx = D.x - O.x, dy = D.y - O.y, dz = D.z - O.z;
-    const float len2 = dx * dx + dy * dy + dz * dz;
-    float inv = rsqrtf(len2);
-    const bool degenerate = !(len2 > 1e-30f) || !(len2 < 1e30f);   // cannot be normalised: every triangle goes to the exact path
-    if (flip) inv = -inv;
-    dx *= inv; dy *= inv; dz *= inv;
-    float lam = fmaf(dx, O.x - f.ex, fmaf(dy, O.y - f.ey, (dz * (O.z - f.ez))));
-    lam = __fadd_ru(__fadd_ru(lam, nearest0), f.slack);
-    if (!(lam < FLT_MAX)) lam = FLT_MAX;                            // also a NaN (non-finite ray): candidates everywhere, the exact path decides
-    if (degenerate) { dx = dy = dz = 0.0f; lam = __int_as_float(0x7f800000); }
-    if (!live) { dx = dy = dz = 0.0f; lam = __int_as_float(0xff800000); }
+__device__ __forceinline__ bool pencil_set_slot(PencilRays<RP>& f, int k, const FrameParams& P, v3 O, v3 D, bool flip, float nearest0, bool live) {
+    const float s = flip ? -1.0f : 1.0f;
+    const float dx = s * (D.x - O.x), dy = s * (D.y - O.y), dz = s * (D.z - O.z);   // the sign of a float difference is exact
+    const float den = fmaf(dx, P.pF[6], fmaf(dy, P.pF[7], dz * P.pF[8]));
+    const float inv = __fdiv_rn(1.0f, den);
+    float x = fmaf(dx, P.pF[0], fmaf(dy, P.pF[1], dz * P.pF[2])) * inv;
+    float y = fmaf(dx, P.pF[3], fmaf(dy, P.pF[4], dz * P.pF[5])) * inv;
+    const bool ok = (den > 0.0f) && (fmaf(x, x, fmaf(y, y, 1.0f)) <= P.p_wmax2);     // NaN / inf fail both
+    if (!ok) x = y = __int_as_float(0x7fc00000);
+    float z = pencil_zhi(P, O, x, y, nearest0);
+    if (!live) { x = y = 0.0f; z = 0.0f; }
 #pragma unroll
     for (int kk = 0; kk < 2 * RP; ++kk)
         if (kk == k) {
-            pair_elem(f.wx[kk / 2], kk & 1) = dx; pair_elem(f.wy[kk / 2], kk & 1) = dy; pair_elem(f.wz[kk / 2], kk & 1) = dz;
-            pair_elem(f.lhi[kk / 2], kk & 1) = lam;
+            pair_elem(f.x[kk / 2], kk & 1) = x; pair_elem(f.y[kk / 2], kk & 1) = y; pair_elem(f.zhi[kk / 2], kk & 1) = z;
+            f.dead[kk] = live ? 0u : 0x80000000u;
         }
+    return ok;
 }
 
 // sign words of one ray pair against one pencil record: bit 31 of s0 / s1 set <=> certainly not a candidate
 template <int RP>
 __device__ __forceinline__ void pencil_pair(const PencilRays<RP>& f, int p, const float4& q0, const float4& q1, const float4& q2, const float4& q3,
                                             uint32_t& s0, uint32_t& s1) {
-    float2 a = __ffma2_rn(splat2(q0.z), f.wz[p], splat2(q0.w));
-    float2 b = __ffma2_rn(splat2(q1.z), f.wz[p], splat2(q1.w));
-    float2 c = __ffma2_rn(splat2(q2.z), f.wz[p], splat2(q2.w));
-    a = __ffma2_rn(splat2(q0.y), f.wy[p], a);
-    b = __ffma2_rn(splat2(q1.y), f.wy[p], b);
-    c = __ffma2_rn(splat2(q2.y), f.wy[p], c);
-    a = __ffma2_rn(splat2(q0.x), f.wx[p], a);
-    b = __ffma2_rn(splat2(q1.x), f.wx[p], b);
-    c = __ffma2_rn(splat2(q2.x), f.wx[p], c);
-    float2 sg = __fadd2_rn(a, b);
-    sg = __fadd2_rn(sg, c);
-    const float2 e = __ffma2_rn(sg, f.lhi[p], splat2(q3.x));
+    float2 a = __ffma2_rn(splat2(q0.y), f.y[p], splat2(q0.z));
+    float2 b = __ffma2_rn(splat2(q1.y), f.y[p], splat2(q1.z));
+    float2 c = __ffma2_rn(splat2(q2.y), f.y[p], splat2(q2.z));
+    a = __ffma2_rn(splat2(q0.x), f.x[p], a);
+    b = __ffma2_rn(splat2(q1.x), f.x[p], b);
+    c = __ffma2_rn(splat2(q2.x), f.x[p], c);
+    float2 sg = __ffma2_rn(splat2(q1.w), f.y[p], splat2(q2.w));
+    sg = __ffma2_rn(splat2(q0.w), f.x[p], sg);
+    const float2 e = __ffma2_rn(sg, f.zhi[p], splat2(q3.x));
     s0 = __float_as_uint(a.x) | __float_as_uint(b.x) | __float_as_uint(c.x) | __float_as_uint(e.x);
     s1 = __float_as_uint(a.y) | __float_as_uint(b.y) | __float_as_uint(c.y) | __float_as_uint(e.y);
 }
 
 // Ray-side hooks of the cold path, one overload per filter.
+struct GenericBand { float eps_r2; };   // what the ray-side hook of the generic filter needs
 template <int RP>
-__device__ __forceinline__ void ray_nearer(FastRays<RP>& f, int k, float dist, float band, v3) { f.rhi[k] = __float_as_uint(__fadd_ru(dist, band)); }
+__device__ __forceinline__ void ray_nearer(FastRays<RP>& f, int k, float dist, const GenericBand& band, v3) { f.rhi[k] = __float_as_uint(__fadd_ru(dist, band.eps_r2)); }
 template <int RP>
-__device__ __forceinline__ void ray_nearer(PencilRays<RP>& f, int k, float dist, float, v3 O) {
+__device__ __forceinline__ void ray_nearer(PencilRays<RP>& f, int k, float dist, const FrameParams& P, v3 O) {
 #pragma unroll
     for (int kk = 0; kk < 2 * RP; ++kk)
         if (kk == k) {
-            float& lhi = pair_elem(f.lhi[kk / 2], kk & 1);
-            const float lam = fmaf(pair_elem(f.wx[kk / 2], kk & 1), O.x - f.ex, fmaf(pair_elem(f.wy[kk / 2], kk & 1), O.y - f.ey, pair_elem(f.wz[kk / 2], kk & 1) * (O.z - f.ez)));
-            const float v = __fadd_ru(__fadd_ru(lam, dist), f.slack);
-            if (lhi < __int_as_float(0x7f800000) && v < lhi) lhi = v;   // a degenerate ray (+inf) stays "always exact"; NaN keeps the old bound
+            float& zhi = pair_elem(f.zhi[kk / 2], kk & 1);
+            const float v = pencil_zhi(P, O, pair_elem(f.x[kk / 2], kk & 1), pair_elem(f.y[kk / 2], kk & 1), dist);
+            if (v < zhi) zhi = v;   // a ray outside the chart (NaN) keeps "no bound"
         }
 }
 template <int RP>
@@ -611,10 +621,7 @@ template <int RP>
 __device__ __forceinline__ void ray_kill(PencilRays<RP>& f, int k) {
 #pragma unroll
     for (int kk = 0; kk < 2 * RP; ++kk)
-        if (kk == k) {
-            pair_elem(f.wx[kk / 2], kk & 1) = 0.0f; pair_elem(f.wy[kk / 2], kk & 1) = 0.0f; pair_elem(f.wz[kk / 2], kk & 1) = 0.0f;
-            pair_elem(f.lhi[kk / 2], kk & 1) = __int_as_float(0xff800000);
-        }
+        if (kk == k) f.dead[kk] = 0x80000000u;
 }
 
 template <int RP, int J>
@@ -628,9 +635,9 @@ struct BitLayout {
 // Cold path of one filter block: exact re-evaluation of every (ray, triangle) pair in `mask` (bit j*R + k).
 // NEAREST: keeps (dist, best) exactly like intersectMesh; !NEAREST: any-hit, clears the ray's live bit on the first
 // exact hit.  fetch(k, O, D) returns the exact ray of slot k.
-template <int RP, int J, bool NEAREST, class Rays, class DistT, class BestT, class Fetch>
+template <int RP, int J, bool NEAREST, class Rays, class Band, class DistT, class BestT, class Fetch>
 __device__ __forceinline__ void exact_block(uint32_t mask, const float4* rec, int jb, Rays& fr, DistT& dist, BestT& best, uint32_t& live,
-                                            const float4* __restrict__ triv, float band, const Fetch& fetch, uint32_t& n_exact) {
+                                            const float4* __restrict__ triv, const Band& band, const Fetch& fetch, uint32_t& n_exact) {
     constexpr int R = 2 * RP;
     constexpr uint32_t REP = BitLayout<RP, J>::kRep;
     mask &= live * REP;
@@ -703,7 +710,7 @@ __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, D
                     mask |= ((c0 ? 1u : 0u) << (2 * p) | (c1 ? 1u : 0u) << (2 * p + 1)) << (j * R);
                 }
             }
-            exact_block<RP, J, NEAREST>(mask, rec, jb, fr, dist, best, live, triv, eps_r2, fetch, n_exact);
+            exact_block<RP, J, NEAREST>(mask, rec, jb, fr, dist, best, live, triv, GenericBand{eps_r2}, fetch, n_exact);
         }
     }
 }
@@ -711,12 +718,14 @@ __device__ __forceinline__ void scan_tile(const float4* rec, FastRays<RP>& fr, D
 // The same against a tile of PENCIL records (no axis classes).
 template <int RP, int J, bool NEAREST, class DistT, class BestT, class Fetch>
 __device__ __forceinline__ void scan_tile_pencil(const float4* rec, PencilRays<RP>& fr, DistT& dist, BestT& best, uint32_t& live,
-                                                 const float4* __restrict__ triv, const Fetch& fetch, uint32_t& n_exact) {
+                                                 const float4* __restrict__ triv, const FrameParams& P, const Fetch& fetch, uint32_t& n_exact) {
     constexpr int R = 2 * RP;
     const int nvalid = __float_as_int(rec[3].z);
 #pragma unroll 1
     for (int jb = 0; jb < nvalid; jb += J) {
-        uint32_t acc = 0xffffffffu;   // AND of the sign words: bit 31 survives iff every pair of the block is rejected
+        uint32_t acc[R];   // per ray: AND of the sign words; bit 31 survives iff every triangle of the block is rejected
+#pragma unroll
+        for (int k = 0; k < R; ++k) acc[k] = 0xffffffffu;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
@@ -725,10 +734,14 @@ __device__ __forceinline__ void scan_tile_pencil(const float4* rec, PencilRays<R
             for (int p = 0; p < RP; ++p) {
                 uint32_t s0, s1;
                 pencil_pair<RP>(fr, p, q0, q1, q2, q3, s0, s1);
-                acc &= s0 & s1;
+                acc[2 * p] &= s0;
+                acc[2 * p + 1] &= s1;
             }
         }
-        if ((int)acc >= 0) {
+        uint32_t all = 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < R; ++k) all &= acc[k] | fr.dead[k];
+        if ((int)all >= 0) {
             uint32_t mask = 0;
 #pragma unroll 1
             for (int j = 0; j < J; ++j) {
@@ -741,7 +754,7 @@ __device__ __forceinline__ void scan_tile_pencil(const float4* rec, PencilRays<R
                     mask |= ((~s0 >> 31) << (2 * p) | (~s1 >> 31) << (2 * p + 1)) << (j * R);
                 }
             }
-            exact_block<RP, J, NEAREST>(mask, rec, jb, fr, dist, best, live, triv, 0.0f, fetch, n_exact);
+            exact_block<RP, J, NEAREST>(mask, rec, jb, fr, dist, best, live, triv, P, fetch, n_exact);
         }
     }
 }
@@ -847,10 +860,10 @@ __device__ __forceinline__ void scan_pass(Pipe& pipe, FastRays<RP>& fr, DistT& d
 
 template <int RP, int J, bool NEAREST, class DistT, class BestT, class Fetch>
 __device__ __forceinline__ void scan_pass_pencil(Pipe& pipe, PencilRays<RP>& fr, DistT& dist, BestT& best, uint32_t& live,
-                                                 const float4* __restrict__ triv, const Fetch& fetch, uint32_t& n_exact, int tile_begin) {
+                                                 const float4* __restrict__ triv, const FrameParams& P, const Fetch& fetch, uint32_t& n_exact, int tile_begin) {
     for (int tile = tile_begin; tile < tile_begin + (int)pipe.len; ++tile) {
         const float4* rec = pipe_acquire(pipe);
-        if (__any_sync(0xffffffffu, live != 0u)) scan_tile_pencil<RP, J, NEAREST>(rec, fr, dist, best, live, triv, fetch, n_exact);
+        if (__any_sync(0xffffffffu, live != 0u)) scan_tile_pencil<RP, J, NEAREST>(rec, fr, dist, best, live, triv, P, fetch, n_exact);
         pipe_release<false>(pipe);
     }
 }
@@ -938,7 +951,6 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
     for (uint32_t item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
         const uint32_t chunk = item / sp.parts, part = item - chunk * sp.parts;
         typename SelectT<PENCIL, PencilRays<RP>, FastRays<RP>>::type fr;
-        if constexpr (PENCIL) { fr.ex = P.pE[0]; fr.ey = P.pE[1]; fr.ez = P.pE[2]; fr.slack = P.p_lam_slack; }
         ColdState<R, !CULL> st(cold.get());
         auto& dist = st.dist; auto& best = st.best; auto& sid = st.sid;
         uint32_t live = 0;
@@ -969,7 +981,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
             sid[k] = s;
             dist[k] = FLT_MAX;
             best[k] = -1;
-            if constexpr (PENCIL) pencil_set_slot<RP>(fr, k, O, D, false, FLT_MAX, ok);
+            if constexpr (PENCIL) pencil_set_slot<RP>(fr, k, P, O, D, false, FLT_MAX, ok);   // outside the chart: every triangle exact
             else fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
         }
         // fetch() re-reads a ray for the exact path: primary rays of other parts may not be published yet
@@ -978,7 +990,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
             else { const float4 o = P.ray_o[sid[k]], d = P.ray_d[sid[k]]; O = mk3(o); D = mk3(d); }
         };
         if constexpr (PENCIL)
-            scan_pass_pencil<RP, J, true>(pipe, fr, dist, best, live, P.triv, fetch, n_exact, (int)(part * sp.len));
+            scan_pass_pencil<RP, J, true>(pipe, fr, dist, best, live, P.triv, P, fetch, n_exact, (int)(part * sp.len));
         else if constexpr (CULL)
             scan_item_culled<RP, J, true, GRAZ>(pipe, csm.get(), fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len),
                                                 min((int)((part + 1) * sp.len), P.ntiles), P.tile_box, P.super_box, P.cls1, P.cls2);
@@ -1059,10 +1071,11 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FramePar
 // ------------------------------------------------------------------------------------------------
 // P.light_sel >= 0: the launch serves that light only (one launch per light: pencil launches, and the generic launches of
 // the lights that do not qualify in a frame that uses the pencil filter).
-// PENCIL (any-hit, brute force): the pencil filter around the light.  w points from the light to the hit point, occluders
-// between the two have 0 < lambda <= lambda_O; occluders BEYOND the light (the reference's shadow rays are unbounded)
-// cannot exist for a "safe" ray (FrameParams::p_axis); an unsafe ray skips the scan and is tested exactly against every
-// triangle in the epilogue (rare by construction: pencil_light_setup only accepts lights outside the scene box).
+// PENCIL (any-hit, brute force): the pencil filter around the light.  Directions run from the light to the hit point,
+// occluders between the two have 0 < depth <= depth of the origin; occluders BEYOND the light (the reference's shadow
+// rays are unbounded) cannot exist for a ray inside the chart's half space; a ray outside the chart skips the scan and is
+// tested exactly against every triangle in the epilogue (rare by construction: pencil_light_setup only accepts lights
+// outside the scene box, and origins inside the box + bias are always inside the chart).
 template <int RP, int J, int MINB, bool NEAREST, bool GRAZ, bool CULL, bool PENCIL = false>
 __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant__ FrameParams P, int level) {
     static_assert(!PENCIL || (!NEAREST && !CULL), "the pencil filter serves any-hit shadow rays in the brute-force scan");
@@ -1083,7 +1096,6 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
     for (uint32_t item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
         const uint32_t chunk = item / sp.parts, part = item - chunk * sp.parts;
         typename SelectT<PENCIL, PencilRays<RP>, FastRays<RP>>::type fr;
-        if constexpr (PENCIL) { fr.ex = P.pE[0]; fr.ey = P.pE[1]; fr.ez = P.pE[2]; fr.slack = P.p_lam_slack; }
         ColdState<R, !CULL> st(cold.get());
         auto& dist = st.dist; auto& best = st.best; auto& sid = st.sid;
         uint32_t live = 0, valid = 0, unsafe = 0;
@@ -1100,16 +1112,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
                 O = e_add(mk3(P.hit[sid[k]]), mk3(0.1f, 0.1f, 0.1f));
                 D = mk3(P.lights[l][0], P.lights[l][1], P.lights[l][2]);
                 valid |= 1u << k;
-                if constexpr (PENCIL) {
-                    const float go = P.p_axis == 0 ? D.x - O.x : (P.p_axis == 1 ? D.y - O.y : D.z - O.z);   // the sign of a float difference is exact
-                    if (!(P.p_sign * go >= 0.0f)) { unsafe |= 1u << k; scan = false; }
-                }
-                if (scan) live |= 1u << k;
             }
             dist[k] = FLT_MAX;
             best[k] = -1;
-            if constexpr (PENCIL) pencil_set_slot<RP>(fr, k, O, D, true, 0.0f, scan);
-            else fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
+            if constexpr (PENCIL) {
+                // a ray outside the chart (it leaves the light's half space, so an occluder BEYOND the light is possible, or
+                // it is too far off axis) is not scanned: the epilogue tests it exactly against every triangle
+                if (!pencil_set_slot<RP>(fr, k, P, O, D, true, 0.0f, ok) && ok) { unsafe |= 1u << k; scan = false; fr.dead[k] = 0x80000000u; }
+            } else {
+                fast_set_slot<RP>(fr, k, O, D, P.eps_r, ok);
+            }
+            if (scan) live |= 1u << k;
         }
         const uint32_t ray0 = chunk * per_chunk + threadIdx.x * R;   // slot k of this thread is work item ray0 + k
         auto fetch = [&](int k, v3& O, v3& D) {   // the exact shadow ray of slot k: hit + (0.1, 0.1, 0.1) -> light (raytracing.cpp:246-248)
@@ -1118,7 +1131,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant
             D = mk3(P.lights[l][0], P.lights[l][1], P.lights[l][2]);
         };
         if constexpr (PENCIL)
-            scan_pass_pencil<RP, J, false>(pipe, fr, dist, best, live, P.triv, fetch, n_exact, (int)(part * sp.len));
+            scan_pass_pencil<RP, J, false>(pipe, fr, dist, best, live, P.triv, P, fetch, n_exact, (int)(part * sp.len));
         else if constexpr (CULL)
             scan_item_culled<RP, J, NEAREST, GRAZ>(pipe, csm.get(), fr, dist, best, live, P.triv, eps_r2, fetch, n_exact, (int)(part * sp.len),
                                                    min((int)((part + 1) * sp.len), P.ntiles), P.tile_box, P.super_box, P.cls1, P.cls2);

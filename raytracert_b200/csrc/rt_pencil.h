@@ -10,9 +10,14 @@
 // is that point's distance from E along w, and the line pierces the triangle iff a, b, c have the sign of sigma.
 // Hits the reference can accept lie at lambda > 0 (in front of the eye / on the hit point's side of the light, see the
 // launch conditions below), i.e. sign(sigma) = sign(det): the three vectors are pre-multiplied by sign(det), and the
-// candidate test becomes "a', b', c' >= 0 and lambda < lambda_hi" -- three 3-term dot products, two adds and one FMA
-// per (ray, triangle): 12 packed FP32 instructions per ray pair instead of 16, no reciprocal, and the compare logic
-// shrinks to the OR of four sign bits.
+// candidate test becomes "a', b', c' >= 0 and lambda < lambda_hi".
+// Projective chart: all rays of a launch point into one half space (w.f >= 1/W_max for the launch's axis f: the view
+// direction / the axis that separates the light from the scene box), the tests are homogeneous in w, so every ray is
+// represented by w' = w / (w.f) = (x, y, 1) in an orthonormal frame (u, v, f) and the records are stored in that frame:
+//     a = A'x*x + A'y*y + A'z        two FMAs per weight, the constant A'z + slack sits in the record
+//     e = (a + b + c) * zeta_hi - det_lo,   zeta = depth along f of the plane point (= lambda / |w'|)
+// -- 9 packed FP32 instructions per (ray pair, triangle) instead of 16, no reciprocal, and the compare logic is the OR
+// of four sign bits (2 LOP3 per ray).
 //
 // This header is shared by the CUDA library (record construction in k_build_pencil, launch set-up in rt_b200.cu)
 // and by the CPU soundness test (tests/pencil_check.cpp), which replays the filter with fmaf() -- the filter uses
@@ -20,18 +25,20 @@
 //
 // Soundness ("pencil filter"): the tolerances E0, E1 bound the reference's own rounding relative to
 // the true line through its float origin and dest (same constants as the generic filter record).  On top of that
-//   * the true line misses E by at most `delta` and w is within 8u of its direction: the plane point moves by at most
-//     (2.2/|cos|)(delta + 8u*lam_max), a barycentric by gmax times that -> E1p = E1 + 2.5*gmax*(delta + 8u*lam_max);
+//   * the true line misses E by at most `delta` and (x, y, 1) is within theta = 16u*w_max of its direction: the plane point moves by at most
+//     (2.7/|cos|)(delta + theta*lam_max), a barycentric by gmax times that -> E1p = E1 + 3*gmax*(delta + theta*lam_max);
 //   * a >= -(E0 + E1p/|cos|)*sigma  <=>  w.(A + E0*n) + E1p*|n| >= 0 : E0 is folded into the vector, E1p*|n| into the
 //     constant term of the FMA chain together with the chain's own rounding (<= 4.1u|A'|);
 //   * distance: lambda < lam_O + best + s_lam + K_r/|cos|  <=>  |det| - K_r*|n| < (lam_O + best + s_lam) * sigma, so the
 //     1/|cos| part of the guard band is folded into the per-triangle constant det_lo.
 // Pairs with |cos| < cos_g need no answer: the pencil kernels are only used when the scene-level proof of
-// rt_b200.cu:build_records says the reference rejects every such pair itself (no_grazing; cos_g = 1.05e-5 for a light,
-// max(1.05e-5, 2.5*delta/lambda_min) for the camera: E and the true line must be on the same side of the plane).
+// rt_b200.cu:build_records says the reference rejects every such pair itself (no_grazing;
+// cos_g = max(1.05e-5, 2.5*delta/lambda_min, 5*theta): E and the true line must be on the same side of the plane, and
+// the chart direction must not change the cosine by more than a fifth).
 // Exactness of the bound (no first-order argument): with H = signed distance of E to the plane, C = n.w, and H', C'
-// the same for the true line, |H - H'| <= delta <= 0.4|H'| and |C - C'| <= 8u <= 0.05|C'|, so lambda' = H/C has the
-// sign of lambda* = H'/C', |lambda' - lambda*| <= (delta + lambda* 8u)/(0.95|C'|), |X' - X*| <= 2.06(delta + lambda* 8u)/|C'|.
+// the same for the true line, |H - H'| <= delta <= 0.4|H'| and |C - C'| <= theta <= 0.2|C'|, so lambda' = H/C has the
+// sign of lambda* = H'/C', |lambda' - lambda*| <= (delta + lambda* theta)/(0.8|C'|), |X' - X*| <= 2.25(delta + lambda* theta)/|C'|,
+// and 1/|C'| <= 1.2/|C| turns that into 2.7/|C| (the records use 3).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -99,8 +106,13 @@ struct PencilSetup {
     double lam_max;   // >= |X - E| for every scene point X
     double cos_g;     // the filter answers for pairs with |cos(true line, plane)| >= cos_g; below that the launch must
                       // be covered by the scene-level proof that the reference rejects the pair itself
+    double fu[3], fv[3], ff[3];   // orthonormal chart frame; every ray of the launch has w.ff >= 1/w_max
+    double w_max;     // >= |w'| = 1/(w.ff) over the launch's rays (rays beyond it are handled exactly by the kernel)
+    double theta;     // angular error of the float chart coordinates (x, y, 1) against the true direction
     float lam_slack;  // s_lam: ray-side guard band of the distance test
     float Ef[3];      // E rounded to float (what the kernels subtract)
+    float F[9];       // frame rounded to float: u, v, f
+    float w_max2;     // w_max^2 (1 + x^2 + y^2 must not exceed it)
 };
 constexpr double kPencilCosMin = 1.05e-5;   // the generic filter's grazing threshold (cos_min = 1e-5) + its 8u evaluation error
 
@@ -109,26 +121,57 @@ RT_HD void pencil_finish_setup(PencilSetup& S, double M_scene) {
     double Me = M_scene, e2 = 0.0;
     for (int k = 0; k < 3; ++k) { Me = fmax(Me, fabs(S.E[k])); e2 += S.E[k] * S.E[k]; S.Ef[k] = (float)S.E[k]; }
     S.M = Me;
-    S.lam_max = 1.7320508 * M_scene + sqrt(e2) + 1e-3 * Me;   // |X - E| <= |X| + |E|
-    // s_lam = 128uM (reference side + lam_O evaluation) + 3*delta, rounded up
+    if (!(S.lam_max > 0.0)) S.lam_max = 1.7320508 * M_scene + sqrt(e2) + 1e-3 * Me;   // |X - E| <= |X| + |E| (the callers may know better)
+    // s_lam = 128uM (reference side + evaluation of the origin's depth) + 3*delta, rounded up
     S.lam_slack = (float)((128.0 * kPencilU * S.M + 3.0 * S.delta) * 1.0001);
+    for (int k = 0; k < 3; ++k) { S.F[k] = (float)S.fu[k]; S.F[3 + k] = (float)S.fv[k]; S.F[6 + k] = (float)S.ff[k]; }
+    // x = (dir.u)/(dir.f) in float: |dx| <= 4u(1 + |x|)|w'| + u|x| (3-term dots of a rounded difference with a rounded
+    // frame vector, one division), so the direction (x, y, 1) is within 16u*w_max of the true one
+    S.theta = 16.0 * kPencilU * S.w_max;
+    S.w_max2 = (float)(S.w_max * S.w_max * 1.00001);
 }
 
-// Pencil record (4 float4 = 64 B, same position / tile layout as the generic record):
-//   q0 = ( A'x, A'y, A'z, sA )   a'' = fma(A'x, wx, fma(A'y, wy, fma(A'z, wz, sA)))      weight of v0 (1 - s - t)
-//   q1 = ( B'x, B'y, B'z, sB )                                                            weight of v1 (s)
-//   q2 = ( C'x, C'y, C'z, sC )                                                            weight of v2 (t)
-//   q3 = ( -det_lo, id, nv, 0 )  e = fma(a''+b''+c'', lambda_hi, -det_lo);  id / nv copied from the generic record
-// candidate  <=>  sign bits of a'', b'', c'', e all clear.   "never" record: A' = B' = C' = 0, slacks = -1.
+// Completes an orthonormal frame around the unit axis f.
+RT_HD void pencil_frame(PencilSetup& S, const double f[3]) {
+    int k0 = 0;
+    if (fabs(f[1]) < fabs(f[k0])) k0 = 1;
+    if (fabs(f[2]) < fabs(f[k0])) k0 = 2;
+    double t[3] = {0.0, 0.0, 0.0};
+    t[k0] = 1.0;
+    double u[3] = {f[1] * t[2] - f[2] * t[1], f[2] * t[0] - f[0] * t[2], f[0] * t[1] - f[1] * t[0]};
+    const double ul = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    for (int k = 0; k < 3; ++k) { u[k] /= ul; S.ff[k] = f[k]; S.fu[k] = u[k]; }
+    S.fv[0] = f[1] * u[2] - f[2] * u[1]; S.fv[1] = f[2] * u[0] - f[0] * u[2]; S.fv[2] = f[0] * u[1] - f[1] * u[0];
+}
+
+// lam_max from the box of everything a record can make a hit of (+ the 0.1 shadow bias and slack): farthest corner from E.
+RT_HD double pencil_farthest_corner(const double E[3], const float lo[3], const float hi[3]) {
+    double m2 = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        const double a = fabs((double)lo[k] - 0.2 - E[k]), b = fabs((double)hi[k] + 0.2 - E[k]);
+        const double m = fmax(a, b);
+        m2 += m * m;
+    }
+    return sqrt(m2);
+}
+
+// Pencil record (4 float4 = 64 B, same position / tile layout as the generic record), vectors in the chart frame:
+//   q0 = ( A'u, A'v, A'f + sA, Nu )        a'' = fma(A'u, x, fma(A'v, y, A'f + sA))      weight of v0 (1 - s - t)
+//   q1 = ( B'u, B'v, B'f + sB, Nv )                                                        weight of v1 (s)
+//   q2 = ( C'u, C'v, C'f + sC, Nf + sN )   sigma = fma(Nu, x, fma(Nv, y, Nf + sN))        N = sign(det) * n in the chart frame
+//   q3 = ( -det_lo, id, nv, 0 )            e = fma(sigma, zeta_hi, -det_lo);  id / nv copied from the generic record
+// candidate  <=>  sign bits of a'', b'', c'', e all clear.   "never" record: vectors 0, constants -1.
+// (sigma gets its own two FMAs instead of a'' + b'' + c'': the weights carry the whole tolerance in their constants,
+// and that sum would loosen the distance clause by the same relative amount.)
 RT_HD void pencil_never(float q[16]) {
     for (int i = 0; i < 12; ++i) q[i] = 0.0f;
-    q[3] = q[7] = q[11] = -1.0f;
+    q[2] = q[6] = q[10] = q[11] = -1.0f;
     q[12] = 0.0f; q[15] = 0.0f;   // q[13] (id), q[14] (nv) are the caller's
 }
 
-RT_HD float pencil_round_up(double v) {   // smallest-ish float >= v (v >= 0)
+RT_HD float pencil_round_up(double v) {   // a float >= v
     float f = (float)v;
-    if ((double)f < v) f = f * 1.0000002f + 1e-37f;
+    if ((double)f < v) f = (f > 0.0f) ? f * 1.0000002f + 1e-37f : f * 0.9999998f + 1e-37f;
     return f;
 }
 
@@ -155,20 +198,30 @@ RT_HD bool pencil_record(const float A[3], const float B[3], const float C[3], d
     const double l12 = sqrt(e12[0] * e12[0] + e12[1] * e12[1] + e12[2] * e12[2]);
     const double lu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), lv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     const double gmax = fmax(l12, fmax(lu, lv)) / nn;
-    const double shift = S.delta + 8.0 * kPencilU * S.lam_max;          // how far the pencil line can be from the true line near the scene
-    const double E1p = E1 + 2.5 * gmax * shift;
-    const double Kr = 48.0 * kPencilU * S.M + 2.5 * shift;              // 1/|cos| part of the distance guard band
+    const double shift = S.delta + S.theta * S.lam_max;                 // how far the pencil line can be from the true line near the scene
+    const double E1p = E1 + 3.0 * gmax * shift;
+    const double Kr = 48.0 * kPencilU * S.M + 3.0 * shift;              // 1/|cos| part of the distance guard band
     double* vec[3] = {Av, Bv, Cv};
     for (int r = 0; r < 3; ++r) {
-        double len2 = 0.0;
-        for (int k = 0; k < 3; ++k) {
-            const double x = sg * (vec[r][k] + E0 * n[k]);
-            q[4 * r + k] = (float)x;
-            len2 += x * x;
-        }
-        // constant term: E1p*|n| (x1.5) + rounding of the 3-FMA chain and of the stored vector (<= 4.1u|A'|, x2)
-        q[4 * r + 3] = pencil_round_up(1.5 * E1p * nn + 8.0 * kPencilU * sqrt(len2) + 1e-30);
-        if (!isfinite(q[4 * r]) || !isfinite(q[4 * r + 1]) || !isfinite(q[4 * r + 2]) || !isfinite(q[4 * r + 3])) { pencil_never(q); return false; }
+        double x[3], len2 = 0.0;
+        for (int k = 0; k < 3; ++k) { x[k] = sg * (vec[r][k] + E0 * n[k]); len2 += x[k] * x[k]; }
+        const double cu = x[0] * S.fu[0] + x[1] * S.fu[1] + x[2] * S.fu[2];
+        const double cv = x[0] * S.fv[0] + x[1] * S.fv[1] + x[2] * S.fv[2];
+        const double cf = x[0] * S.ff[0] + x[1] * S.ff[1] + x[2] * S.ff[2];
+        // constant term: E1p*|n|*|w'| (x1.5) + rounding of the two FMAs, of the stored coefficients and of the constant
+        // itself (<= 4u(|A'||w'| + sA), x2), |w'| <= w_max
+        const double sA = (1.5 * E1p * nn + 8.0 * kPencilU * sqrt(len2)) * S.w_max * 1.0001 + 1e-30;
+        q[4 * r] = (float)cu; q[4 * r + 1] = (float)cv;
+        q[4 * r + 2] = pencil_round_up(cf + sA);
+        if (!isfinite(q[4 * r]) || !isfinite(q[4 * r + 1]) || !isfinite(q[4 * r + 2])) { pencil_never(q); return false; }
+    }
+    {   // sigma = w'.N must not come out below the true value: constant + 4u|n||w'| (two FMAs, stored coefficients, the constant)
+        const double nu = sg * (n[0] * S.fu[0] + n[1] * S.fu[1] + n[2] * S.fu[2]);
+        const double nv = sg * (n[0] * S.fv[0] + n[1] * S.fv[1] + n[2] * S.fv[2]);
+        const double nf = sg * (n[0] * S.ff[0] + n[1] * S.ff[1] + n[2] * S.ff[2]);
+        q[3] = (float)nu; q[7] = (float)nv;
+        q[11] = pencil_round_up(nf + 8.0 * kPencilU * nn * S.w_max + 1e-30);
+        if (!isfinite(q[3]) || !isfinite(q[7]) || !isfinite(q[11])) { pencil_never(q); return false; }
     }
     // det_lo <= (|det| - Kr*|n|) * (1 - 8u), rounded down; negative is fine (the distance clause then always passes)
     const double dl = fabs(det) - Kr * nn;
@@ -191,7 +244,7 @@ RT_HD bool pencil_record(const float A[3], const float B[3], const float C[3], d
 // blended line; the float evaluation of the blend moves origin and dest by <= eps_o each.
 // Returns false when the frame is not a (forward) pencil: parallel rays, eye behind the near plane, ...
 // ------------------------------------------------------------------------------------------------
-inline bool pencil_camera_setup(const float corners[24], double M_scene, PencilSetup& S) {
+inline bool pencil_camera_setup(const float corners[24], double M_scene, const float* box_lo, const float* box_hi, PencilSetup& S) {
     double O[4][3], D[4][3], g[4][3];
     double Mc = 0.0;
     for (int c = 0; c < 4; ++c)
@@ -261,6 +314,18 @@ inline bool pencil_camera_setup(const float corners[24], double M_scene, PencilS
     // at tau = -lambda_O / |D - O|, |tau| <= omax / lenmin.
     const double eps_o = 4.0 * kPencilU * 1.7320508 * Mc + 2.0 * kPencilU * 1.7320508 * fmax(Mc, Me);
     S.delta = crossmax / lenmin + (1.0 + 2.0 * omax / lenmin) * eps_o;
+    // chart: f = mean view direction.  (x, y) of a blended ray is a convex combination of the corner rays' (x_i, y_i)
+    // (weights w_i g_i.f > 0), so |w'| <= max over the corners
+    pencil_frame(S, gm);
+    S.w_max = 0.0;
+    for (int c = 0; c < 4; ++c) {
+        const double gf = g[c][0] * gm[0] + g[c][1] * gm[1] + g[c][2] * gm[2];
+        if (!(gf > 0.0)) return false;
+        S.w_max = fmax(S.w_max, norm(g[c]) / gf);
+    }
+    S.w_max *= 1.0 + 1e-5;
+    if (!(S.w_max < 8.0)) return false;      // wider than ~83 degrees off axis: not worth it
+    S.lam_max = (box_lo && box_hi && box_lo[0] <= box_hi[0] && box_lo[1] <= box_hi[1] && box_lo[2] <= box_hi[2]) ? pencil_farthest_corner(E, box_lo, box_hi) : 0.0;
     pencil_finish_setup(S, M_scene);
     // launch conditions: E well in front of every ray origin (lambda_min >= 2e-3*M, see pencil_record) and a usable delta
     const double lam_min = lam_o_min - 4.0 * S.delta - 64.0 * kPencilU * S.M;
@@ -268,33 +333,49 @@ inline bool pencil_camera_setup(const float corners[24], double M_scene, PencilS
     if (!(S.delta <= 1e-3 * S.M)) return false;
     // E and the true line's closest point E' must lie on the same side of every plane a valid pair can hit:
     // |dist(E', plane)| = lambda*|cos| >= lam_min*cos_g must exceed delta with room to spare (factor 2.5)
-    S.cos_g = fmax(kPencilCosMin, 2.5 * S.delta / lam_min);
+    // and the chart direction must keep the cosine's sign and size: theta <= 0.2*cos_g
+    S.cos_g = fmax(kPencilCosMin, fmax(2.5 * S.delta / lam_min, 5.0 * S.theta));
     return true;
 }
 
 // Shadow rays of one light: dest = the light exactly, so delta = 0.  box_lo / box_hi: the bounding box of everything a
-// filter record can make a hit of (union of the tile boxes).  The pencil handles occluders on the hit point's side of
-// the light; a ray whose continuation BEYOND the light could re-enter the box is handled exactly by the kernel
-// (k_shadow, "unsafe" rays).  The launch is worthwhile only if the light is outside the box along some axis by a gap
-// >= 2e-3*M (then lambda >= gap for every record hit, and rays from inside the box are all safe).
-// axis / sign: ray with origin O is safe iff sign * (L[axis] - O[axis]) >= 0.
-inline bool pencil_light_setup(const float L[3], const float box_lo[3], const float box_hi[3], double M_scene, PencilSetup& S, int& axis, float& sign) {
+// filter record can make a hit of (union of the tile boxes); box' = box + 0.2 also holds the ray origins (hit + 0.1
+// bias) of every hit inside the box.  Chart axis f = direction from the light to the centre of the box; the launch
+// needs the whole box' strictly inside the half space (X - L).f > 0.  Directions run from the light to the ray origin.
+// The pencil handles occluders on the origin's side of the light (0 < depth <= depth of the origin).  A ray whose
+// origin is not in the half space (its continuation BEYOND the light could re-enter the box: the reference's shadow
+// rays are unbounded) or lies outside the chart (|w'| > w_max) is handled exactly by the kernel (k_shadow, "unsafe"
+// rays); origins inside box' never are: X -> (X - L)/((X - L).f) maps box' to a convex polygon of the chart plane, so
+// |w'| is largest at a corner.
+inline bool pencil_light_setup(const float L[3], const float box_lo[3], const float box_hi[3], double M_scene, PencilSetup& S) {
     double Me = M_scene;
-    for (int k = 0; k < 3; ++k) { if (!isfinite(L[k])) return false; Me = fmax(Me, fabs((double)L[k])); }
-    if (!(Me < 1e18)) return false;
-    double best_gap = 0.0;
-    axis = -1; sign = 0.f;
     for (int k = 0; k < 3; ++k) {
-        if (!(box_lo[k] <= box_hi[k])) continue;   // empty / NaN box
-        const double up = (double)L[k] - box_hi[k], dn = (double)box_lo[k] - L[k];
-        if (up > best_gap) { best_gap = up; axis = k; sign = 1.f; }
-        if (dn > best_gap) { best_gap = dn; axis = k; sign = -1.f; }
+        if (!isfinite(L[k]) || !(box_lo[k] <= box_hi[k])) return false;   // empty / NaN box
+        Me = fmax(Me, fabs((double)L[k]));
     }
-    if (axis < 0 || !(best_gap >= 2e-3 * Me)) return false;
+    if (!(Me < 1e18)) return false;
+    double f[3], fl = 0.0;
+    for (int k = 0; k < 3; ++k) { f[k] = 0.5 * ((double)box_lo[k] + box_hi[k]) - L[k]; fl += f[k] * f[k]; }
+    fl = sqrt(fl);
+    if (!(fl > 0.0) || !isfinite(fl)) return false;
+    for (int k = 0; k < 3; ++k) f[k] /= fl;
+    double gap = INFINITY, wmax = 0.0;
+    for (int c = 0; c < 8; ++c) {
+        double X[3], l2 = 0.0, dp = 0.0;
+        for (int k = 0; k < 3; ++k) { X[k] = (((c >> k) & 1) ? (double)box_hi[k] + 0.2 : (double)box_lo[k] - 0.2) - L[k]; l2 += X[k] * X[k]; dp += X[k] * f[k]; }
+        gap = fmin(gap, dp);
+        if (dp > 0.0) wmax = fmax(wmax, sqrt(l2) / dp);
+    }
+    if (!(gap >= 2e-3 * Me)) return false;            // the light is inside (or too close to) the box: no pencil
     for (int k = 0; k < 3; ++k) S.E[k] = L[k];
     S.delta = 0.0;
-    S.cos_g = kPencilCosMin;
+    S.lam_max = pencil_farthest_corner(S.E, box_lo, box_hi);
+    S.w_max = wmax * (1.0 + 1e-5);
+    if (!(S.w_max < 8.0)) return false;               // too wide a cone for a useful chart
+    pencil_frame(S, f);
     pencil_finish_setup(S, M_scene);
+    S.cos_g = fmax(kPencilCosMin, 5.0 * S.theta);
     return true;
 }
+
 }  // namespace rt

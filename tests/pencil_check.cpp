@@ -47,18 +47,17 @@ extern "C" {
 
 // mode 0: primary rays of the camera `setup24` (24 corner floats); mode 1: shadow rays ending at the light `setup24[0..2]`,
 // box = setup24[3..5] (lo) / [6..8] (hi).  tri: ntri x 9 floats.  rays: n x 6 floats (origin, dest).
-// inv_scale perturbs the normalisation factor (emulates the 2-ulp error of rsqrtf): w = dir * (1/sqrt(len2)) * inv_scale.
+// inv_scale perturbs the chart division (x, y scaled by it: a few ulp of extra direction error).
 int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const float* tri, int nrays, const float* rays, float inv_scale,
                  pair_fn_t pair_fn, PencilCheckResult* out) {
     PencilCheckResult R;
     memset(&R, 0, sizeof(R));
     R.first_bad_ray = R.first_bad_tri = -1;
     PencilSetup S;
-    int axis = 0;
-    float sign = 0.f;
+    memset(&S, 0, sizeof(S));
     bool ok;
-    if (mode == 0) ok = pencil_camera_setup(setup24, M_scene, S);
-    else ok = pencil_light_setup(setup24, setup24 + 3, setup24 + 6, M_scene, S, axis, sign);
+    if (mode == 0) ok = pencil_camera_setup(setup24, M_scene, nullptr, nullptr, S);
+    else ok = pencil_light_setup(setup24, setup24 + 3, setup24 + 6, M_scene, S);
     R.setup_ok = ok ? 1 : 0;
     if (!ok) { *out = R; return 0; }
     R.delta = S.delta; R.M = S.M; R.cos_g = S.cos_g;
@@ -84,16 +83,18 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
 #pragma omp parallel for schedule(dynamic, 16) reduction(+ : pairs, ref_hits, cands, viol, graz, unsafe)
     for (int r = 0; r < nrays; ++r) {
         const float *O = rays + 6 * r, *D = O + 3;
-        if (mode == 1 && !(sign * (D[axis] - O[axis]) >= 0.0f)) { ++unsafe; continue; }   // the kernel tests these exactly
-        // pencil_set_slot
-        float dx = D[0] - O[0], dy = D[1] - O[1], dz = D[2] - O[2];
-        const float len2 = dx * dx + dy * dy + dz * dz;
-        float inv = (1.0f / sqrtf(len2)) * inv_scale;
-        const bool degenerate = !(len2 > 1e-30f) || !(len2 < 1e30f);
-        if (mode == 1) inv = -inv;
-        dx *= inv; dy *= inv; dz *= inv;
-        float lam = fmaf(dx, O[0] - S.Ef[0], fmaf(dy, O[1] - S.Ef[1], dz * (O[2] - S.Ef[2])));
-        if (degenerate) { dx = dy = dz = 0.f; }
+        // pencil_set_slot (rt_kernels.cuh)
+        const float sgn = mode == 1 ? -1.0f : 1.0f;
+        const float dx = sgn * (D[0] - O[0]), dy = sgn * (D[1] - O[1]), dz = sgn * (D[2] - O[2]);
+        const float den = fmaf(dx, S.F[6], fmaf(dy, S.F[7], dz * S.F[8]));
+        const float inv = (1.0f / den) * inv_scale;
+        float x = fmaf(dx, S.F[0], fmaf(dy, S.F[1], dz * S.F[2])) * inv;
+        float y = fmaf(dx, S.F[3], fmaf(dy, S.F[4], dz * S.F[5])) * inv;
+        const bool in_chart = (den > 0.0f) && (fmaf(x, x, fmaf(y, y, 1.0f)) <= S.w_max2);
+        if (!in_chart) { ++unsafe; continue; }   // the kernels test these rays exactly against every triangle
+        // pencil_zhi: depth of the origin + (nearest + s_lam) / |(x, y, 1)|, rounded up
+        const float c = (1.0f / sqrtf(fmaf(x, x, fmaf(y, y, 1.0f)))) * 1.000002f * 1.0000005f;
+        const float zO = fmaf(O[0] - S.Ef[0], S.F[6], fmaf(O[1] - S.Ef[1], S.F[7], (O[2] - S.Ef[2]) * S.F[8]));
         // true direction (double) for the grazing premise
         const double ddx = (double)D[0] - O[0], ddy = (double)D[1] - O[1], ddz = (double)D[2] - O[2];
         const double dl = std::sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
@@ -103,23 +104,19 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
             float dist = 0.f;
             const int hit = pair_fn(O, D, T, T + 3, T + 6, &dist);
             const float* q = &rec[(size_t)16 * i];
-            float lhi;
-            if (degenerate) lhi = INFINITY;
-            else if (mode == 0) {
-                const float best = hit ? nextafterf(dist, INFINITY) : FLT_MAX;
-                lhi = round_up_sum(round_up_sum(lam, best), S.lam_slack);
-                if (!(lhi < FLT_MAX)) lhi = FLT_MAX;
-            } else {
-                lhi = round_up_sum(round_up_sum(lam, 0.0f), S.lam_slack);
-                if (!(lhi < FLT_MAX)) lhi = FLT_MAX;
-            }
-            const float a = fmaf(q[0], dx, fmaf(q[1], dy, fmaf(q[2], dz, q[3])));
-            const float b = fmaf(q[4], dx, fmaf(q[5], dy, fmaf(q[6], dz, q[7])));
-            const float c = fmaf(q[8], dx, fmaf(q[9], dy, fmaf(q[10], dz, q[11])));
-            const float sg = (a + b) + c;
-            const float e = fmaf(sg, lhi, q[12]);
+            const float nearest = (mode == 0) ? (hit ? nextafterf(dist, INFINITY) : FLT_MAX) : 0.0f;
+            const double zd = (double)zO + (double)round_up_sum(nearest, S.lam_slack) * (double)c;
+            float zhi = (float)zd;
+            if ((double)zhi < zd) zhi = nextafterf(zhi, INFINITY);
+            if (!(zhi < FLT_MAX)) zhi = FLT_MAX;
+            const float a = fmaf(q[0], x, fmaf(q[1], y, q[2]));
+            const float b = fmaf(q[4], x, fmaf(q[5], y, q[6]));
+            const float c2 = fmaf(q[8], x, fmaf(q[9], y, q[10]));
+            const float sg = fmaf(q[3], x, fmaf(q[7], y, q[11]));
+            const float e = fmaf(sg, zhi, q[12]);
+            const float cc = c2;
             uint32_t ua, ub, uc, ue;
-            memcpy(&ua, &a, 4); memcpy(&ub, &b, 4); memcpy(&uc, &c, 4); memcpy(&ue, &e, 4);
+            memcpy(&ua, &a, 4); memcpy(&ub, &b, 4); memcpy(&uc, &cc, 4); memcpy(&ue, &e, 4);
             const bool cand = !((ua | ub | uc | ue) >> 31);
             if (cand) ++cands;
             if (hit && dist < FLT_MAX) {
