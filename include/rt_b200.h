@@ -109,6 +109,8 @@ typedef struct rt_stats {
     uint32_t n_launches;                              /* kernels launched for the frame (per GPU)      */
     uint32_t variant;                                 /* bit 0: scan kernels without the grazing clause (fine mesh);
                                                        * bit 1: pencil filter on the primary rays; bit 2: on shadow rays */
+    float ms_trace_primary;                           /* the level-0 (primary ray) part of ms_trace */
+    uint32_t reserved;
 } rt_stats;
 
 /* Single-process mode: use devices 0..n_gpus-1 of this box (n_gpus >= 1); rows are interleaved over

@@ -45,7 +45,8 @@ class RtStats(C.Structure):
                 ("tri_tests", C.c_uint64), ("exact_evals", C.c_uint64), ("ms_total", C.c_float),
                 ("ms_trace", C.c_float), ("ms_shadow", C.c_float), ("ms_shade", C.c_float), ("ms_resolve", C.c_float),
                 ("ms_gather", C.c_float), ("n_gpus", C.c_uint32), ("rank", C.c_uint32),
-                ("n_triangles", C.c_uint32), ("n_levels", C.c_uint32), ("n_launches", C.c_uint32), ("variant", C.c_uint32)]
+                ("n_triangles", C.c_uint32), ("n_levels", C.c_uint32), ("n_launches", C.c_uint32), ("variant", C.c_uint32),
+                ("ms_trace_primary", C.c_float), ("reserved", C.c_uint32)]
 
 
 EXPORTS = ["rt_init", "rt_init_rank", "rt_nccl_unique_id", "rt_upload_scene", "rt_render", "rt_render_async",

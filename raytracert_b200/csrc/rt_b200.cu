@@ -23,6 +23,8 @@ using namespace rt;
 // resident CTAs per SM).  The first entry is the default; RT_B200_TUNE="rp,j,minb" selects another
 // (tools/tune.py sweeps them on the GPU).
 #define RT_SCAN_CONFIGS(X) X(2, 8, 2) X(1, 16, 4)
+// The pencil kernels keep 6 registers per ray pair instead of 14, so they have their own shapes (RT_B200_PTUNE="rp,j,minb").
+#define RT_PENCIL_CONFIGS(X) X(2, 8, 2) X(1, 16, 4)   // more rays per thread would need > 48 KB of (static) shared memory for the cold state
 struct ScanConfig { int rp, j, minb; };
 constexpr uint32_t kMaxChunkSamples = 1u << 23;  // 8 Mi samples per wavefront chunk (84 B of state each)
 
@@ -106,7 +108,7 @@ struct RtDevice {
     int num_sms = 148;
 };
 
-enum KernelKind { kKindTrace = 0, kKindShadow, kKindShade, kKindResolve, kKindGather, kNumKinds };
+enum KernelKind { kKindTrace = 0, kKindShadow, kKindShade, kKindResolve, kKindGather, kKindTracePrimary, kNumKinds };
 constexpr size_t kMaxTimedLaunches = 4096;  // beyond this a frame's launches are still counted, not timed
 
 struct Global {
@@ -116,6 +118,7 @@ struct Global {
     bool scene_ready = false, frame_ready = false;
     NcclApi nccl;
     ScanConfig scan = {2, 8, 2};
+    ScanConfig pscan = {2, 8, 2};    // shape of the pencil kernels
     bool tile_culling = false;       // RT_OPT_TILE_CULLING
     bool pencil = true;              // RT_OPT_PENCIL: common-point filter for primary / shadow rays where it applies
     bool allow_no_grazing = true;    // RT_B200_GRAZING=1 forces the grazing clause on (experiments)
@@ -245,8 +248,6 @@ void launch_scan_gc(int which, int grid, cudaStream_t st, const FrameParams& P, 
 }
 template <int RP, int J, int MINB>
 void launch_scan(int which, int grid, cudaStream_t st, const FrameParams& P, int level, bool grazing_clause) {
-    if (which == kScanPrimaryPencil) { k_trace<RP, J, MINB, true, false, false, true><<<grid, kThreads, 0, st>>>(P, level); return; }
-    if (which == kScanShadowPencil) { k_shadow<RP, J, MINB, false, false, false, true><<<grid, kThreads, 0, st>>>(P, level); return; }
     if (P.cull) {
         if (grazing_clause) launch_scan_gc<RP, J, MINB, true, true>(which, grid, st, P, level);
         else launch_scan_gc<RP, J, MINB, false, true>(which, grid, st, P, level);
@@ -261,6 +262,23 @@ void dispatch_scan(const ScanConfig& c, int which, int num_sms, cudaStream_t st,
 #define RT_X(RP, J, MINB) if (c.rp == RP && c.j == J && c.minb == MINB) return launch_scan<RP, J, MINB>(which, num_sms * MINB, st, P, level, grazing_clause);
     RT_SCAN_CONFIGS(RT_X)
 #undef RT_X
+}
+
+template <int RP, int J, int MINB>
+void launch_pencil(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
+    if (which == kScanPrimaryPencil) k_trace<RP, J, MINB, true, false, false, true><<<grid, kThreads, 0, st>>>(P, level);
+    else k_shadow<RP, J, MINB, false, false, false, true><<<grid, kThreads, 0, st>>>(P, level);
+}
+void dispatch_pencil(const ScanConfig& c, int which, int num_sms, cudaStream_t st, const FrameParams& P, int level) {
+#define RT_X(RP, J, MINB) if (c.rp == RP && c.j == J && c.minb == MINB) return launch_pencil<RP, J, MINB>(which, num_sms * MINB, st, P, level);
+    RT_PENCIL_CONFIGS(RT_X)
+#undef RT_X
+}
+bool pencil_config_exists(const ScanConfig& c) {
+#define RT_X(RP, J, MINB) if (c.rp == RP && c.j == J && c.minb == MINB) return true;
+    RT_PENCIL_CONFIGS(RT_X)
+#undef RT_X
+    return false;
 }
 
 bool scan_config_exists(const ScanConfig& c) {
@@ -278,6 +296,11 @@ void read_tuning_env() {
     if (const char* c = getenv("RT_B200_GRAZING")) g.allow_no_grazing = atoi(c) == 0;
     if (const char* c = getenv("RT_B200_CULL")) g.tile_culling = atoi(c) != 0;   // same as rt_set_option(RT_OPT_TILE_CULLING, ..)
     if (const char* c = getenv("RT_B200_PENCIL")) g.pencil = atoi(c) != 0;       // same as rt_set_option(RT_OPT_PENCIL, ..)
+    if (const char* pe = getenv("RT_B200_PTUNE")) {
+        ScanConfig c = g.pscan;
+        if (sscanf(pe, "%d,%d,%d", &c.rp, &c.j, &c.minb) == 3 && pencil_config_exists(c)) g.pscan = c;
+        else fprintf(stderr, "librt_b200: RT_B200_PTUNE=%s is not a compiled pencil configuration; keeping %d,%d,%d\n", pe, g.pscan.rp, g.pscan.j, g.pscan.minb);
+    }
     const char* e = getenv("RT_B200_TUNE");
     if (!e) return;
     ScanConfig c = g.scan;
@@ -461,11 +484,11 @@ int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullp
     const int grid_small = d.num_sms * 4;
     for (int level = 0; level < levels; ++level) {
         {
-            LaunchTimer t(d, kKindTrace);
+            LaunchTimer t(d, level == 0 ? kKindTracePrimary : kKindTrace);
             if (level == 0 && plan && plan->cam && !P.trace_api) {
                 FrameParams Pp = P;
                 apply_pencil(Pp, d, *plan, 0, plan->cam_setup);
-                dispatch_scan(g.scan, kScanPrimaryPencil, d.num_sms, d.stream, Pp, level, false);
+                dispatch_pencil(g.pscan, kScanPrimaryPencil, d.num_sms, d.stream, Pp, level);
             } else {
                 dispatch_scan(g.scan, level == 0 ? kScanPrimary : kScanBounce, d.num_sms, d.stream, P, level, !d.no_grazing);
             }
@@ -484,7 +507,7 @@ int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullp
                 Pl.light_sel = l;
                 if (plan->light[l]) {
                     apply_pencil(Pl, d, *plan, 1 + l, plan->light_setup[l]);
-                    dispatch_scan(g.scan, kScanShadowPencil, d.num_sms, d.stream, Pl, level, false);
+                    dispatch_pencil(g.pscan, kScanShadowPencil, d.num_sms, d.stream, Pl, level);
                 } else {
                     dispatch_scan(g.scan, kScanShadowAny, d.num_sms, d.stream, Pl, level, !d.no_grazing);
                 }
@@ -694,7 +717,18 @@ int collect_stats() {
         float by_kind[kNumKinds] = {};
         for (size_t i = 0; i < d.kev_kind.size(); ++i)
             if (d.kev_kind[i] >= 0 && cudaEventElapsedTime(&ms, d.kev[2 * i], d.kev[2 * i + 1]) == cudaSuccess) by_kind[d.kev_kind[i]] += ms;
-        st.ms_trace = std::max(st.ms_trace, by_kind[kKindTrace]);
+        if (getenv("RT_B200_LAUNCHLOG")) {   // per-launch device times of the frame, in launch order (diagnostics)
+            static const char* names[kNumKinds] = {"trace", "shadow", "shade/finish", "resolve", "gather", "trace_primary"};
+            for (size_t i = 0; i < d.kev_kind.size(); ++i)
+                if (d.kev_kind[i] >= 0 && cudaEventElapsedTime(&ms, d.kev[2 * i], d.kev[2 * i + 1]) == cudaSuccess && ms > 0.05f)
+                    fprintf(stderr, "librt_b200: launch %3zu %-14s %9.3f ms\n", i, names[d.kev_kind[i]], ms);
+            for (int c = 0; c < d.frame_chunks; ++c) {
+                const uint32_t* cw = &g.host_counters[(size_t)c * kCntWords];
+                for (int l = 0; l < 6; ++l) fprintf(stderr, "librt_b200: chunk %d level %d: %u rays in, %u hits\n", c, l, l == 0 ? 0u : cw[kCntRay + l], cw[kCntHit + l]);
+            }
+        }
+        st.ms_trace = std::max(st.ms_trace, by_kind[kKindTrace] + by_kind[kKindTracePrimary]);
+        st.ms_trace_primary = std::max(st.ms_trace_primary, by_kind[kKindTracePrimary]);
         st.ms_shadow = std::max(st.ms_shadow, by_kind[kKindShadow]);
         st.ms_shade = std::max(st.ms_shade, by_kind[kKindShade]);
         st.ms_resolve = std::max(st.ms_resolve, by_kind[kKindResolve]);

@@ -538,8 +538,9 @@ __device__ __forceinline__ void kill_slot(FastRays<RP>& f, int k) {
 
 // ------------------------------------------------------------------------------------------------
 // Pencil filter (rt_pencil.h): rays through a common point, in the launch's projective chart.  6 registers per ray
-// pair, 9 packed FP32 instructions and 4 LOP3 per (ray pair, triangle); the hot loop ANDs the sign words per ray,
-// "any candidate in the block" = some live ray's AND has its sign bit clear.
+// pair; the hot loop evaluates the three weights only -- 6 packed FP32 instructions and 3 LOP3 per (ray pair,
+// triangle) -- and ANDs the sign words per ray ("any candidate in the block" = some live ray's AND has its sign bit
+// clear); the cold path rebuilds the block's mask with the full test (+ 3 packed instructions for the distance clause).
 // ------------------------------------------------------------------------------------------------
 template <int RP>
 struct PencilRays {
@@ -599,6 +600,21 @@ __device__ __forceinline__ void pencil_pair(const PencilRays<RP>& f, int p, cons
     const float2 e = __ffma2_rn(sg, f.zhi[p], splat2(q3.x));
     s0 = __float_as_uint(a.x) | __float_as_uint(b.x) | __float_as_uint(c.x) | __float_as_uint(e.x);
     s1 = __float_as_uint(a.y) | __float_as_uint(b.y) | __float_as_uint(c.y) | __float_as_uint(e.y);
+}
+
+// Hot-loop form: the three weights only (6 packed FP32 instructions + 1 LOP3 per ray), no distance clause.  The pairs it
+// lets through that the full test would stop (triangles pierced by the ray's line behind the nearest hit / beyond a shadow
+// ray's origin) cost a cold-path entry, not an exact evaluation: the cold path rebuilds its mask with pencil_pair().
+template <int RP>
+__device__ __forceinline__ void pencil_pair_hot(const PencilRays<RP>& f, int p, const float4& q0, const float4& q1, const float4& q2, uint32_t& s0, uint32_t& s1) {
+    float2 a = __ffma2_rn(splat2(q0.y), f.y[p], splat2(q0.z));
+    float2 b = __ffma2_rn(splat2(q1.y), f.y[p], splat2(q1.z));
+    float2 c = __ffma2_rn(splat2(q2.y), f.y[p], splat2(q2.z));
+    a = __ffma2_rn(splat2(q0.x), f.x[p], a);
+    b = __ffma2_rn(splat2(q1.x), f.x[p], b);
+    c = __ffma2_rn(splat2(q2.x), f.x[p], c);
+    s0 = __float_as_uint(a.x) | __float_as_uint(b.x) | __float_as_uint(c.x);
+    s1 = __float_as_uint(a.y) | __float_as_uint(b.y) | __float_as_uint(c.y);
 }
 
 // Ray-side hooks of the cold path, one overload per filter.
@@ -726,16 +742,18 @@ __device__ __forceinline__ void scan_tile_pencil(const float4* rec, PencilRays<R
         uint32_t acc[R];   // per ray: AND of the sign words; bit 31 survives iff every triangle of the block is rejected
 #pragma unroll
         for (int k = 0; k < R; ++k) acc[k] = 0xffffffffu;
+        static_assert(J % 2 == 0, "the hot loop folds two triangles per AND");
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1];
-            const float4 q2 = rec[(jb + j) * kRecVec + 2], q3 = rec[(jb + j) * kRecVec + 3];
+        for (int j = 0; j < J; j += 2) {   // two triangles per step: acc & u & u' is one LOP3
+            const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1], q2 = rec[(jb + j) * kRecVec + 2];
+            const float4 r0 = rec[(jb + j + 1) * kRecVec + 0], r1 = rec[(jb + j + 1) * kRecVec + 1], r2 = rec[(jb + j + 1) * kRecVec + 2];
 #pragma unroll
             for (int p = 0; p < RP; ++p) {
-                uint32_t s0, s1;
-                pencil_pair<RP>(fr, p, q0, q1, q2, q3, s0, s1);
-                acc[2 * p] &= s0;
-                acc[2 * p + 1] &= s1;
+                uint32_t s0, s1, u0, u1;
+                pencil_pair_hot<RP>(fr, p, q0, q1, q2, s0, s1);
+                pencil_pair_hot<RP>(fr, p, r0, r1, r2, u0, u1);
+                acc[2 * p] &= s0 & u0;
+                acc[2 * p + 1] &= s1 & u1;
             }
         }
         uint32_t all = 0xffffffffu;
