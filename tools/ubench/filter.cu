@@ -193,6 +193,62 @@ __device__ __forceinline__ bool block_v6(const Rays<RP>& f, const float4* rec) {
     return any;
 }
 
+// V7: V6 with scalar FFMAs (3 register operands each) and without the grazing clause
+// V8: V6 packed, without the grazing clause (the shipped clause-free kernels)
+template <int RP, int J, int V>
+__device__ __forceinline__ bool block_v78(const Rays<RP>& f, const float4* rec) {
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const float4 q0 = rec[j * 4 + 0], q1 = rec[j * 4 + 1], q2 = rec[j * 4 + 2];
+        if (V == 8) {
+#pragma unroll
+            for (int p = 0; p < RP; ++p) {
+                float2 b = __fmul2_rn(splat2(q0.x), f.dx[p]);
+                b = __ffma2_rn(splat2(q0.y), f.dy[p], b);
+                b = __ffma2_rn(splat2(q0.z), f.dz[p], b);
+                float2 a = __ffma2_rn(splat2(q0.x), f.ox[p], splat2(q0.w));
+                a = __ffma2_rn(splat2(q0.y), f.oy[p], a);
+                a = __ffma2_rn(splat2(q0.z), f.oz[p], a);
+                const float2 rc = make_float2(rcp_approx(-b.x), rcp_approx(-b.y));
+                const float2 r = __fmul2_rn(a, rc);
+                const float2 iu = __ffma2_rn(r, f.dx[p], f.ox[p]);
+                const float2 iv = __ffma2_rn(r, f.dy[p], f.oy[p]);
+                float2 s = __ffma2_rn(splat2(q1.x), iu, splat2(q1.z));
+                s = __ffma2_rn(splat2(q1.y), iv, s);
+                float2 t = __ffma2_rn(splat2(q2.x), iu, splat2(q2.z));
+                t = __ffma2_rn(splat2(q2.y), iv, t);
+                float2 q = __fadd2_rn(splat2(q1.w), make_float2(-s.x, -s.y));
+                q = __fadd2_rn(q, make_float2(-t.x, -t.y));
+                const float m0 = fminf(fminf(s.x, t.x), q.x), m1 = fminf(fminf(s.y, t.y), q.y);
+                const float2 e = __fmul2_rn(splat2(q2.w), rc);
+                const bool c0 = (!(m0 < -fabsf(e.x)) && (__float_as_uint(r.x) < f.rhi[2 * p]));
+                const bool c1 = (!(m1 < -fabsf(e.y)) && (__float_as_uint(r.y) < f.rhi[2 * p + 1]));
+                any = any || c0 || c1;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2 * RP; ++k) {
+                const int p = k / 2;
+                const float dx = (k & 1) ? f.dx[p].y : f.dx[p].x, dy = (k & 1) ? f.dy[p].y : f.dy[p].x, dz = (k & 1) ? f.dz[p].y : f.dz[p].x;
+                const float ox = (k & 1) ? f.ox[p].y : f.ox[p].x, oy = (k & 1) ? f.oy[p].y : f.oy[p].x, oz = (k & 1) ? f.oz[p].y : f.oz[p].x;
+                const float b = fmaf(q0.z, dz, fmaf(q0.y, dy, q0.x * dx));
+                const float a = fmaf(q0.z, oz, fmaf(q0.y, oy, fmaf(q0.x, ox, q0.w)));
+                const float rc = rcp_approx(-b);
+                const float r = a * rc;
+                const float iu = fmaf(r, dx, ox), iv = fmaf(r, dy, oy);
+                const float s = fmaf(q1.y, iv, fmaf(q1.x, iu, q1.z));
+                const float t = fmaf(q2.y, iv, fmaf(q2.x, iu, q2.z));
+                const float q = (q1.w - s) - t;
+                const float m = fminf(fminf(s, t), q);
+                const float e = q2.w * rc;
+                any = any || (!(m < -fabsf(e)) && (__float_as_uint(r) < f.rhi[k]));
+            }
+        }
+    }
+    return any;
+}
+
 template <int RP, int J, int V, int MINB>
 __global__ void __launch_bounds__(256, MINB) k(const float4* rec_g, float* out, unsigned long long* cyc, float seed) {
     __shared__ float4 tile[kTile * 4];
@@ -213,7 +269,8 @@ __global__ void __launch_bounds__(256, MINB) k(const float4* rec_g, float* out, 
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll 1
         for (int jb = 0; jb < kTile; jb += J) {
-            const bool any = (V == 0) ? block_v0<RP, J>(f, tile + jb * 4) : (V == 1) ? block_v1<RP, J>(f, tile + jb * 4) : (V == 6) ? block_v6<RP, J>(f, tile + jb * 4) : block_vx<RP, J, V>(f, tile + jb * 4, sink);
+            const bool any = (V == 0) ? block_v0<RP, J>(f, tile + jb * 4) : (V == 1) ? block_v1<RP, J>(f, tile + jb * 4) : (V == 6) ? block_v6<RP, J>(f, tile + jb * 4)
+                           : (V == 7 || V == 8) ? block_v78<RP, J, V>(f, tile + jb * 4) : block_vx<RP, J, V>(f, tile + jb * 4, sink);
             if (any) { ++hits; f.rhi[0] ^= hits; }   // rare side effect so nothing is optimised away
         }
     }
@@ -250,15 +307,13 @@ int main() {
         h[4 * i + 3] = make_float4(1.001f, -1e-6f, 1e-5f, 0.f);
     }
     cudaMemcpy(rec, h, sizeof(h), cudaMemcpyHostToDevice);
-    run<2, 8, 0, 2>("V0 rp2 j8 minb2 (shipped)", rec, out, cyc);
     run<2, 8, 6, 2>("V6 2-D projected (16 packed)", rec, out, cyc);
-    run<1, 16, 6, 4>("V6 rp1 j16 minb4", rec, out, cyc);
-    run<2, 8, 2, 2>("V2 FMA chain + MUFU, no compares", rec, out, cyc);
-    run<2, 8, 3, 2>("V3 FMA chain only", rec, out, cyc);
-    run<2, 8, 4, 2>("V4 V0 without |cos| clause", rec, out, cyc);
-    run<2, 8, 5, 2>("V5 V0 without min3", rec, out, cyc);
-    run<1, 8, 0, 4>("V0 rp1 j8 minb4", rec, out, cyc);
-    run<1, 8, 2, 4>("V2 rp1", rec, out, cyc);
-    run<1, 8, 3, 4>("V3 rp1", rec, out, cyc);
+    run<2, 8, 8, 2>("V8 V6 clause-free packed rp2 j8", rec, out, cyc);
+    run<2, 8, 7, 2>("V7 clause-free scalar rp2 j8", rec, out, cyc);
+    run<1, 16, 7, 2>("V7 clause-free scalar rp1 j16 minb2", rec, out, cyc);
+    run<1, 16, 7, 4>("V7 clause-free scalar rp1 j16 minb4", rec, out, cyc);
+    run<2, 8, 7, 3>("V7 clause-free scalar rp2 j8 minb3", rec, out, cyc);
+    run<3, 4, 7, 2>("V7 clause-free scalar rp3 j4", rec, out, cyc);
+    run<3, 4, 8, 2>("V8 clause-free packed rp3 j4", rec, out, cyc);
     return 0;
 }
