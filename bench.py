@@ -276,7 +276,7 @@ def main():
         # Scan kernels of the last frame.  Algorithmic flops = 42 per (ray, triangle) test (the minimal ray-dependent
         # form of rayIntersectTriangle for a GENERAL ray) x rays x triangles; every kernel performs every test of the reference.
         #   k_trace generic  : bounce levels (and the primary level when the pencil filter does not apply): 27 executed flop / test
-        #   k_trace pencil   : primary rays, common-point filter in a projective chart: 9 FFMA2 per ray pair = 18 executed flop / test
+        #   k_trace pencil   : primary rays, common-point filter in a projective chart: hot loop 6 FFMA2 per ray pair = 12 executed flop / test
         #   k_shadow         : any-hit; the reference's shadow rays are full scans, so its tests count in full although rays exit early
         variant = int(st["variant"])
         pencil_primary, pencil_shadow = bool(variant & 2), bool(variant & 4)
@@ -287,24 +287,26 @@ def main():
             a = FLOPS_PER_TEST * rays_gpu * ntri / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
             return {"kernel": name, "ms": ms, "tests_per_s": rays_gpu * ntri / (ms * 1e-3) if ms > 0 else 0.0, "achieved": a, "frac": a / fp32_peak,
                     "executed_flops_per_test": executed, "executed_frac": a * executed / FLOPS_PER_TEST / fp32_peak}
-        rows = [kernel_row("k_trace primary (%s filter)" % ("pencil" if pencil_primary else "generic"), counts[0] / world, ms_primary, 18 if pencil_primary else 27),
+        rows = [kernel_row("k_trace primary (%s filter)" % ("pencil" if pencil_primary else "generic"), counts[0] / world, ms_primary, 12 if pencil_primary else 27),
                 kernel_row("k_trace bounce levels (generic filter)", counts[2] / world, ms_bounce, 27),
-                kernel_row("k_shadow any-hit (%s filter)" % ("pencil" if pencil_shadow else "generic"), counts[1] / world, float(kinds[1]), 18 if pencil_shadow else 27)]
+                kernel_row("k_shadow any-hit (%s filter)" % ("pencil" if pencil_shadow else "generic"), counts[1] / world, float(kinds[1]), 12 if pencil_shadow else 27)]
         dom = max(rows, key=lambda r: r["ms"])
         ach = dom["achieved"]
         roof = {"bound": "fp32", "kernel": dom["kernel"] + " -- the launch kind with the largest share of the frame", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach / fp32_peak,
                 # rt_probe_fp32_peak(): what a register-resident FFMA/FFMA2 loop sustains on this device right now (TFLOP/s)
                 "peak_fma_loop_measured": fp32_probe, "frac_of_measured_fma_loop": ach / fp32_probe if fp32_probe > 0 else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the frame's largest launch (primary scan, 8.39 M rays), one
-                # `ncu --set full` capture of this command (profiles/); only meaningful for the default workload
-                "traffic": 590.9e6 if args.workload == "balls" and world == 1 else None, "traffic_unit": "B per launch (primary scan, chunk 0)", "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of that kind (level-1 bounce scan of chunk 0,
+                # 4.34 M rays, 134.6 ms), one `ncu --set full` capture of this command (profiles/r1h_k_trace_bounce_full.txt);
+                # only meaningful for the default workload
+                "traffic": 182.7e6 if args.workload == "balls" and world == 1 else None, "traffic_unit": "B per launch (level-1 bounce scan, chunk 0)",
+                "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
                 "frac_at_measured_clock": (ach / (fp32_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])) if clocks.get("sm_mhz") else None,
                 "executed_flops_per_test": dom["executed_flops_per_test"], "executed_frac": dom["executed_frac"],
                 "frame_achieved": FLOPS_PER_TEST * rays * ntri / world / (ms_dev * 1e-3) / 1e12,
                 "by_kernel": rows,
                 "note": "achieved/frac count 42 algorithmic flop per test (general-ray form, SURVEY 8d). The pencil kernels do the same tests "
-                        "with 18 executed flop (rays through a common point need no origin arithmetic), so their algorithmic rate -- and "
+                        "with 12 executed flop in the hot loop (rays through a common point need no origin arithmetic; the distance clause runs in the cold path), so their algorithmic rate -- and "
                         "frame_achieved -- can exceed the FP32 peak; executed_frac is the FMA-pipe-level figure for every row.",
                 "ms_by_kernel": dict(zip(["k_trace", "k_shadow", "k_shade", "k_resolve", "gather", "k_trace_primary"], [float(x) for x in kinds]))}
         line = {"metric": METRIC, "value": rays / ms_dev / 1e3, "unit": "Mrays/s",
