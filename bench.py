@@ -29,6 +29,26 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
     os.environ["NCCL_DEBUG"] = "WARN"
 
+# ... and whatever a native library still prints to file descriptor 1 (NCCL's banner at NCCL_DEBUG=INFO set in a config
+# file, for one) must not reach it either: fd 1 is pointed at stderr for the whole run, the JSON line goes to the saved fd.
+_JSON_FD = None
+
+
+def guard_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    if _JSON_FD is None:
+        print(json.dumps(line), flush=True)
+    else:
+        os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "Mrays/s (Balls stand-in 800x800, 16 spp, shadows + reflection depth 3)"
 FLOPS_PER_TEST = 42  # minimal ray-dependent restatement of raytracing.cpp:111-151, FMA = 2
 
@@ -168,7 +188,7 @@ def run_reference(args, name):
             "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -182,6 +202,7 @@ def main():
     ap.add_argument("--no-accelerated", action="store_true", help="skip the separately reported tile-culling frames (profiling runs)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     args = ap.parse_args()
+    guard_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args, args.workload)
@@ -334,7 +355,7 @@ def main():
                                     "sample": f"every {k}th pixel of every {k}th row of the same frame ({npix} of {W * H} pixels, all {pf * pf} sub-samples "
                                               f"each), {dt:.1f} s; the reference's own raytracing.cpp/mesh.cpp (-O2 -ffp-contract=off), OpenMP over pixels in the harness",
                                     "ms_per_frame_extrapolated": dt * 1e3 * W * H / npix}
-        print(json.dumps(line), flush=True)
+        emit(line)
     R.shutdown()
     if world > 1:
         import torch.distributed as td
