@@ -25,7 +25,7 @@ $(BUILD)/librt_host.so: $(HOSTDIR)/mesh.cpp $(HOSTDIR)/host_capi.cpp $(wildcard 
 	@mkdir -p $(BUILD)
 	$(CXX) $(HOSTFLAGS) -shared -o $@ $(HOSTDIR)/mesh.cpp $(HOSTDIR)/host_capi.cpp
 
-$(BUILD)/librt_b200.so: $(wildcard $(CSRC)/*.cu) $(wildcard $(CSRC)/*.cuh) include/rt_b200.h
+$(BUILD)/librt_b200.so: $(wildcard $(CSRC)/*.cu) $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/rt_b200.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/rt_b200.cu -cudart static -ldl
 

@@ -3,10 +3,12 @@
 // Reference functions replaced (paths under /root/reference/CG_Project):
 //   k_build_records / k_build_tile_boxes -- (new) per-triangle filter records, built from u,v,n,uu,uv,vv,D of
 //                        raytracing.cpp:106-140, and per-tile bounds for the opt-in tile culling
+//   k_build_pencil    -- (new) per-frame records of the common-point ("pencil") filter around the eye / a light (rt_pencil.h)
 //   k_trace           -- main.cpp:377-388 ray generation (PRIMARY) + intersectMesh raytracing.cpp:161-192
+//                        (PENCIL: primary rays through the common-point filter)
 //   k_finish          -- tail of intersectMesh / head of trace (raytracing.cpp:183-191, 387-396): winner's hit point,
 //                        analytic spheres, hit record
-//   k_shadow          -- isShadow raytracing.cpp:241-261
+//   k_shadow          -- isShadow raytracing.cpp:241-261 (PENCIL: any-hit rays of one light through the common-point filter)
 //   k_shade           -- shade/diffuseOnly/blinnPhongSpecularOnly/reflection/refraction/addOffset/trace
 //                        raytracing.cpp:197-232, 266-330, 335-406
 //   k_resolve         -- main.cpp:391-393 + RGBValue clamp main.cpp:24-42

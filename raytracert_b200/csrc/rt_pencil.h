@@ -14,23 +14,25 @@
 // Projective chart: all rays of a launch point into one half space (w.f >= 1/W_max for the launch's axis f: the view
 // direction / the axis that separates the light from the scene box), the tests are homogeneous in w, so every ray is
 // represented by w' = w / (w.f) = (x, y, 1) in an orthonormal frame (u, v, f) and the records are stored in that frame:
-//     a = A'x*x + A'y*y + A'z        two FMAs per weight, the constant A'z + slack sits in the record
-//     e = (a + b + c) * zeta_hi - det_lo,   zeta = depth along f of the plane point (= lambda / |w'|)
+//     a = A'u*x + A'v*y + A'f        two FMAs per weight, the constant A'f + slack sits in the record
+//     e = sigma * zeta_hi - det_lo,  sigma = Nu*x + Nv*y + Nf,  zeta = depth along f of the plane point (= lambda / |w'|)
 // -- 9 packed FP32 instructions per (ray pair, triangle) instead of 16, no reciprocal, and the compare logic is the OR
-// of four sign bits (2 LOP3 per ray).
+// of four sign bits (2 LOP3 per ray).  The kernels' hot loop evaluates the three weights only (6 instructions); the
+// distance clause e runs when the cold path rebuilds a block's candidate mask (rt_kernels.cuh: pencil_pair_hot / pencil_pair).
 //
 // This header is shared by the CUDA library (record construction in k_build_pencil, launch set-up in rt_b200.cu)
 // and by the CPU soundness test (tests/pencil_check.cpp), which replays the filter with fmaf() -- the filter uses
-// only IEEE FMAs and adds, so the CPU replay is the same arithmetic as the FFMA2/FADD2 instructions.
+// only IEEE FMAs, so the CPU replay is the same arithmetic as the FFMA2 instructions.
 //
 // Soundness ("pencil filter"): the tolerances E0, E1 bound the reference's own rounding relative to
 // the true line through its float origin and dest (same constants as the generic filter record).  On top of that
 //   * the true line misses E by at most `delta` and (x, y, 1) is within theta = 16u*w_max of its direction: the plane point moves by at most
 //     (2.7/|cos|)(delta + theta*lam_max), a barycentric by gmax times that -> E1p = E1 + 3*gmax*(delta + theta*lam_max);
-//   * a >= -(E0 + E1p/|cos|)*sigma  <=>  w.(A + E0*n) + E1p*|n| >= 0 : E0 is folded into the vector, E1p*|n| into the
-//     constant term of the FMA chain together with the chain's own rounding (<= 4.1u|A'|);
-//   * distance: lambda < lam_O + best + s_lam + K_r/|cos|  <=>  |det| - K_r*|n| < (lam_O + best + s_lam) * sigma, so the
-//     1/|cos| part of the guard band is folded into the per-triangle constant det_lo.
+//   * a >= -(E0 + E1p/|cos|)*sigma  <=>  w'.(A + E0*n) + E1p*|n|*|w'| >= 0 : E0 is folded into the vector, E1p*|n|*w_max into
+//     the constant term of the FMA chain together with the chain's own rounding (<= 4u(|A'||w'| + constant));
+//   * distance: lambda < lam_O + best + s_lam + K_r/|cos|  <=>  |det| - K_r*|n| < zeta_hi * sigma with
+//     zeta_hi = zeta_O + (best + s_lam)/|w'|, so the 1/|cos| part of the guard band is folded into the per-triangle
+//     constant det_lo (sigma's own constant carries 8u|n|w_max: it is never under-estimated).
 // Pairs with |cos| < cos_g need no answer: the pencil kernels are only used when the scene-level proof of
 // rt_b200.cu:build_records says the reference rejects every such pair itself (no_grazing;
 // cos_g = max(1.05e-5, 2.5*delta/lambda_min, 5*theta): E and the true line must be on the same side of the plane, and
@@ -294,16 +296,13 @@ inline bool pencil_camera_setup(const float corners[24], double M_scene, const f
     const double gl = norm(gm);
     if (!(gl > 0.0)) return false;
     for (int k = 0; k < 3; ++k) gm[k] /= gl;
-    double lenmin = INFINITY, lam_o_min = INFINITY, lenmax = 0.0;
-    for (int c = 0; c < 4; ++c) {
-        lenmin = fmin(lenmin, g[c][0] * gm[0] + g[c][1] * gm[1] + g[c][2] * gm[2]);
-        lenmax = fmax(lenmax, norm(g[c]));
-    }
+    double lenmin = INFINITY, lam_o_min = INFINITY;
+    for (int c = 0; c < 4; ++c) lenmin = fmin(lenmin, g[c][0] * gm[0] + g[c][1] * gm[1] + g[c][2] * gm[2]);
     if (!(lenmin > 0.0)) return false;
-    // forward pencil: (O - E).(D - O) > 0 for every blend  <=  o_i.g_j > 0 for all i, j; the smallest o_i.g_j / max|g|
-    // is a lower bound of lambda_O (distance from E to the ray origin along the ray)
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) lam_o_min = fmin(lam_o_min, (o[i][0] * g[j][0] + o[i][1] * g[j][1] + o[i][2] * g[j][2]) / lenmax);
+    // forward pencil: both O - E = sum w_i o_i and D - O = sum w_i g_i have a positive component along the mean direction
+    // (o_i.gm > 0, g_i.gm > 0 for every corner) and are collinear up to delta, so they point the same way; and
+    // lambda_O = |O - E| >= (O - E).gm >= min_i o_i.gm
+    for (int c = 0; c < 4; ++c) lam_o_min = fmin(lam_o_min, o[c][0] * gm[0] + o[c][1] * gm[1] + o[c][2] * gm[2]);
     if (!(M_scene < 1e18)) return false;
     double Me = M_scene, omax = 0.0;
     for (int k = 0; k < 3; ++k) { Me = fmax(Me, fabs(E[k])); S.E[k] = E[k]; }

@@ -221,6 +221,53 @@ def test_pencil_sound_on_random_fine_soups(checker, port, seed):
     assert total["pairs"] > 0
 
 
+def _grid_patch(n, size, centre, tilt=0.3):
+    """A tilted, slightly bumpy n x n grid patch (2 n^2 triangles) of edge size/n around `centre`."""
+    from raytracert_b200 import host
+    u = np.linspace(-0.5, 0.5, n + 1)
+    X, Z = np.meshgrid(u * size, u * size)
+    Y = tilt * X + 0.05 * size * np.sin(9 * X / size) * np.cos(7 * Z / size)
+    v = (np.stack([X, Y, Z], axis=-1).reshape(-1, 3) + np.asarray(centre)).astype(np.float32)
+    idx = []
+    for i in range(n):
+        for j in range(n):
+            a = i * (n + 1) + j
+            idx += [(a, a + 1, a + n + 1), (a + 1, a + n + 2, a + n + 1)]
+    idx = np.array(idx, np.uint32)
+    return host.Scene(v, idx, np.zeros(len(idx), np.uint32), host.face_normals(v, idx), np.zeros((1, 16), np.float32))
+
+
+@pytest.mark.parametrize("case", ["wide_frame", "light_close_to_the_box", "tiny_triangles", "far_from_the_origin", "camera_far_away"])
+def test_pencil_sound_in_extreme_setups(checker, port, case):
+    """Corners of the launch conditions: a very wide frame (large chart extent), a light just far enough from the scene box
+    (w_max close to its cap), millimetre triangles (large barycentric gradients), a scene at |coordinate| ~ 60 (large
+    magnitude bound), a camera 9 units away (rays near the far plane)."""
+    from raytracert_b200 import host
+    if case == "wide_frame":
+        s = _grid_patch(24, 3.0, (0, 0, 0))
+        cam = host.Camera(160, 36, (0.0, 1.2, 3.0), (0.0, 0.0, 0.0))
+        lights, W, H = [(0.5, 3.0, 1.0)], 160, 36
+    elif case == "light_close_to_the_box":
+        s = _grid_patch(24, 3.0, (0, 0, 0))
+        cam = host.Camera(48, 36, (0.0, 2.2, 3.4), (0.0, 0.0, 0.0))
+        lights, W, H = [(0.3, 1.25, 0.2), (1.9, 1.3, -1.7)], 48, 36      # low over the patch: wide cones
+    elif case == "tiny_triangles":
+        s = _grid_patch(40, 0.08, (0.2, 0.1, -0.3))
+        cam = host.Camera(48, 36, (0.2, 0.6, 0.9), (0.2, 0.1, -0.3))       # the patch covers a few pixels; the edge-aimed rays do the work
+        lights, W, H = [(0.4, 1.5, 0.3)], 48, 36
+    elif case == "far_from_the_origin":
+        s = _grid_patch(24, 3.0, (55.0, -40.0, 20.0))
+        cam = host.Camera(48, 36, (55.0, -38.5, 23.5), (55.0, -40.0, 20.0))
+        lights, W, H = [(56.0, -36.5, 21.0)], 48, 36
+    else:
+        s = _grid_patch(24, 3.0, (0, 0, 0))
+        cam = host.Camera(48, 36, (0.5, 4.0, 8.0), (0.0, 0.0, 0.0))
+        lights, W, H = [(0.0, 6.0, 0.0)], 48, 36
+    total, nl = check_frame(checker, port, s, cam, W, H, 2, lights, step=1 if case == "tiny_triangles" else 2)
+    assert total["ref_hits"] > (10 if case == "tiny_triangles" else 100), case
+    assert nl >= 1, case
+
+
 def test_camera_setup_rejects_what_is_not_a_pencil(checker):
     """Parallel (orthographic) corner rays, or an eye between the ray origins and the scene, must not use the pencil."""
     from raytracert_b200 import host
