@@ -1,4 +1,5 @@
-// pencil_check.cpp -- TEST INFRASTRUCTURE: CPU replay of the pencil filter (raytracert_b200/csrc/rt_pencil.h).
+// pencil_check.cpp -- TEST INFRASTRUCTURE: CPU replay of the pencil filter (raytracert_b200/csrc/rt_pencil.h) and a CPU
+// restatement of the generic filter (generic_check, at the end).
 //
 // The pencil filter uses only IEEE FMAs and adds, so fmaf() here is the arithmetic of the FFMA2 / FADD2 instructions
 // of k_trace / k_shadow.  For a batch of rays and a triangle soup this replays record construction (the same
@@ -138,6 +139,110 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
         }
     }
     R.pairs = pairs; R.ref_hits = ref_hits; R.candidates = cands; R.violations = viol; R.grazing_skipped = graz; R.unsafe_rays = unsafe;
+    R.first_bad_ray = bad_ray; R.first_bad_tri = bad_tri;
+    *out = R;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The GENERIC filter (rt_kernels.cuh: k_build_records / fast_set / filter_pair), restated for the CPU.  Its only
+// non-IEEE operations are MUFU.RCP and rsqrtf; `rc_scale` / `inv_scale` perturb them by a few ulp.  Same question as
+// above: every pair the reference accepts must be a candidate -- with the tightest admissible distance bound in
+// nearest-hit mode (mode 0: rhi from the next float above the pair's own distance), and with no bound (mode 1: any-hit).
+// bmin: the grazing clause's threshold (1e-5), or < 0 for the clause-free records.
+// ------------------------------------------------------------------------------------------------
+int generic_check(int mode, double M, float bmin, int ntri, const float* tri, int nrays, const float* rays, float rc_scale, float inv_scale,
+                  pair_fn_t pair_fn, PencilCheckResult* out) {
+    PencilCheckResult R;
+    memset(&R, 0, sizeof(R));
+    R.first_bad_ray = R.first_bad_tri = -1;
+    R.setup_ok = 1;
+    R.M = M;
+    const float cos_min = 1.0e-5f, u32 = 5.9604645e-8f;
+    const float eps_r = (float)M * (48.0f * u32 / cos_min + 128.0f * u32);   // rt_b200.cu: eps_r_for
+    std::vector<float> rec((size_t)ntri * 16);
+    std::vector<uint8_t> state(ntri), cls(ntri);
+    for (int i = 0; i < ntri; ++i) {
+        const float *A = tri + 9 * i, *B = A + 3, *C = A + 6;
+        float* q = &rec[(size_t)16 * i];
+        for (int k = 0; k < 16; ++k) q[k] = 0.f;
+        q[12] = -1.0f;   // "never"
+        const float u[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, v[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+        const float n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+        const float uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], uv = u[0] * v[0] + u[1] * v[1] + u[2] * v[2], vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+        const float Df = uv * uv - uu * vv;
+        if (n[0] == 0.f && n[1] == 0.f && n[2] == 0.f) { state[i] = 2; ++R.never_recs; continue; }
+        const int W = dominant_axis(A, B, C);
+        cls[i] = (uint8_t)W;
+        const FilterTol t = filter_tolerances(A, B, C, W, M);
+        if (t.always || !(std::fabs(Df) > 0.f) || !std::isfinite(Df)) { state[i] = 1; ++R.always_tris; continue; }
+        const double a3[3] = {A[0], A[1], A[2]};
+        const double inv = 1.0 / t.nn;
+        const double n3[3] = {t.n3[0] * inv, t.n3[1] * inv, t.n3[2] * inv};
+        q[0] = (float)n3[0]; q[1] = (float)n3[1]; q[2] = (float)n3[2]; q[3] = (float)(-(n3[0] * a3[0] + n3[1] * a3[1] + n3[2] * a3[2]));
+        q[4] = (float)t.su; q[5] = (float)t.sv; q[6] = (float)(-(t.su * a3[t.U] + t.sv * a3[t.V]) + t.E0); q[7] = (float)(1.0 + 3.0 * t.E0);
+        q[8] = (float)t.tu; q[9] = (float)t.tv; q[10] = (float)(-(t.tu * a3[t.U] + t.tv * a3[t.V]) + t.E0); q[11] = (float)(-t.E1);
+        q[12] = bmin;
+    }
+    int64_t pairs = 0, ref_hits = 0, cands = 0, viol = 0;
+    int bad_ray = -1, bad_tri = -1;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : pairs, ref_hits, cands, viol)
+    for (int r = 0; r < nrays; ++r) {
+        const float *O = rays + 6 * r, *D = O + 3;
+        // fast_set
+        float d[3] = {D[0] - O[0], D[1] - O[1], D[2] - O[2]};
+        const float len2 = fmaf(d[2], d[2], fmaf(d[1], d[1], d[0] * d[0]));
+        float inv = (1.0f / sqrtf(len2)) * inv_scale;
+        if (!(len2 > 1e-30f) || !(len2 < 1e30f)) inv = 0.0f;
+        for (int k = 0; k < 3; ++k) d[k] *= inv;
+        const float o[3] = {fmaf(-eps_r, d[0], O[0]), fmaf(-eps_r, d[1], O[1]), fmaf(-eps_r, d[2], O[2])};
+        for (int i = 0; i < ntri; ++i) {
+            ++pairs;
+            const float* T = tri + 9 * i;
+            float dist = 0.f;
+            const int hit = pair_fn(O, D, T, T + 3, T + 6, &dist);
+            const float* q = &rec[(size_t)16 * i];
+            const int W = cls[i], U = (W + 1) % 3, V = (W + 2) % 3;
+            // filter_pair
+            float b = q[0] * d[0];
+            b = fmaf(q[1], d[1], b);
+            b = fmaf(q[2], d[2], b);
+            float a = fmaf(q[0], o[0], q[3]);
+            a = fmaf(q[1], o[1], a);
+            a = fmaf(q[2], o[2], a);
+            const float rc = (1.0f / (-b)) * rc_scale;
+            const float rr = a * rc;
+            const float iu = fmaf(rr, d[U], o[U]), iv = fmaf(rr, d[V], o[V]);
+            float s = fmaf(q[4], iu, q[6]);
+            s = fmaf(q[5], iv, s);
+            float t = fmaf(q[8], iu, q[10]);
+            t = fmaf(q[9], iv, t);
+            float qq = q[7] + (-s);
+            qq = qq + (-t);
+            const float m = fminf(fminf(s, t), qq);
+            const float e = q[11] * rc;
+            uint32_t rbits, rhi = 0x7f7fffffu;
+            memcpy(&rbits, &rr, 4);
+            if (mode == 0 && hit) {
+                const float best = nextafterf(dist, INFINITY);
+                const float hi = round_up_sum(best, 2.0f * eps_r);
+                memcpy(&rhi, &hi, 4);
+            }
+            bool cand = !(m < -std::fabs(e)) && (rbits < rhi);
+            if (bmin > 0.0f) cand = cand || (std::fabs(b) < bmin);
+            if (cand) ++cands;
+            if (hit && dist < FLT_MAX) {
+                ++ref_hits;
+                if (state[i] == 1) continue;
+                if (!cand) {
+                    ++viol;
+#pragma omp critical
+                    if (bad_ray < 0) { bad_ray = r; bad_tri = i; }
+                }
+            }
+        }
+    }
+    R.pairs = pairs; R.ref_hits = ref_hits; R.candidates = cands; R.violations = viol;
     R.first_bad_ray = bad_ray; R.first_bad_tri = bad_tri;
     *out = R;
     return 0;

@@ -4,7 +4,11 @@ The pencil filter of k_trace / k_shadow uses only IEEE FMAs and adds, so tests/p
 -- the same record construction code the CUDA library compiles, the same operation order -- for EVERY (ray, triangle)
 pair of a scene and compares with the oracle's decision for that pair (oracle/rt_oracle.c:orc_ray_triangle): whatever
 the reference accepts must be a candidate.  Rays: the frame's primary rays (oracle arithmetic), shadow rays from the
-oracle's hit points, and shadow rays from random points on the surfaces.  Runs without a GPU."""
+oracle's hit points, and shadow rays from random points on the surfaces.  Runs without a GPU.
+
+The second half does the same for the GENERIC filter (every bounce ray, and every ray when the pencil conditions do not
+hold): pencil_check.cpp:generic_check restates k_build_records / fast_set / filter_pair with fmaf(); its two approximate
+operations (MUFU.RCP, rsqrtf) are perturbed by a few ulp in both directions."""
 import ctypes as C
 import os
 import subprocess
@@ -39,6 +43,22 @@ def checker(port):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         r = Result()
         L.pencil_check(mode, setup.ctypes.data, float(M), len(tris), tris.ctypes.data, len(rays), rays.ctypes.data, inv_scale, pair_fn, C.byref(r))
+        return r
+    return run
+
+
+@pytest.fixture(scope="session")
+def generic_checker(checker, port):
+    """CPU restatement of the GENERIC filter (pencil_check.cpp:generic_check), same calling convention."""
+    L = C.CDLL(SO)
+    L.generic_check.argtypes = [C.c_int, C.c_double, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.POINTER(Result)]
+    pair_fn = C.cast(port.L.orc_ray_triangle, C.c_void_p)
+
+    def run(mode, M, bmin, tris, rays, rc_scale=1.0, inv_scale=1.0):
+        tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 9)
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        r = Result()
+        L.generic_check(mode, float(M), bmin, len(tris), tris.ctypes.data, len(rays), rays.ctypes.data, rc_scale, inv_scale, pair_fn, C.byref(r))
         return r
     return run
 
@@ -266,6 +286,89 @@ def test_pencil_sound_in_extreme_setups(checker, port, case):
     total, nl = check_frame(checker, port, s, cam, W, H, 2, lights, step=1 if case == "tiny_triangles" else 2)
     assert total["ref_hits"] > (10 if case == "tiny_triangles" else 100), case
     assert nl >= 1, case
+
+
+def bounce_like_rays(tris, rng, n):
+    """Continuation-ray shaped rays (raytracing.cpp:266-285): origin = P + 0.01 * dir, dest = P + dir, P on a surface; half of
+    them aimed at an edge / vertex point of another triangle."""
+    t = tris.reshape(-1, 3, 3)
+    pick = rng.integers(0, len(t), n)
+    bary = rng.dirichlet((1, 1, 1), n).astype(np.float32)
+    P = (t[pick] * bary[:, :, None]).sum(axis=1).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    target = edge_points(tris, rng, n)
+    d[: n // 2] = (target - P)[: n // 2]
+    d = (d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)).astype(np.float32)
+    return np.concatenate([P + np.float32(0.01) * d, P + d], axis=1).astype(np.float32)
+
+
+def check_generic(generic_checker, port, scene, cam, W, H, pf, lights, step, clause_free):
+    tris = tri_array(scene)
+    M = magnitude_bound(scene, cam.corners)
+    rng = np.random.default_rng(17)
+    rays = primary_rays(cam.corners, W, H, pf, step)
+    port.set_scene(scene)
+    port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
+    _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+    origins = (hit[prim >= 0] + np.float32(0.1)).astype(np.float32)
+    batches = [("primary", rays), ("bounce", bounce_like_rays(tris, rng, 1500))]
+    for Lp in lights:
+        Lp = np.asarray(Lp, np.float32)
+        P = edge_points(tris, rng, 600)
+        back = (P + (P - Lp) * rng.uniform(0.05, 1.5, (len(P), 1)).astype(np.float32)).astype(np.float32)
+        o = np.concatenate([origins, back])
+        batches.append(("shadow", np.concatenate([o, np.broadcast_to(Lp, o.shape)], axis=1)))
+    hits = 0
+    for name, batch in batches:
+        bmin = 1.0e-5
+        if clause_free and grazing_product(tris, batch) * 1.11e-5 < 1e-5:     # rt_b200.cu:build_records
+            bmin = -0.5
+        for mode in (0, 1):
+            for rc_scale, inv_scale in ((1.0, 1.0), (1.0 + 2.0 ** -22, 1.0 - 2.0 ** -22), (1.0 - 2.0 ** -22, 1.0 + 2.0 ** -22)):
+                r = generic_checker(mode, M, bmin, tris, batch, rc_scale, inv_scale)
+                assert r.violations == 0, f"{name} rays, mode {mode}: {r.violations} accepted pairs were filtered out (first: ray {r.first_bad_ray}, triangle {r.first_bad_tri})"
+        hits += r.ref_hits
+    return hits
+
+
+def test_generic_filter_sound_on_the_balls_standin(generic_checker, port):
+    """The same all-pairs check for the generic filter (k_trace / k_shadow without the pencil option; every bounce ray)."""
+    from raytracert_b200 import host, scenes
+    s = scenes.balls_standin(grid=40, slices=24, stacks=12)
+    cam = host.Camera(64, 48, (0.2, 0.75, 4.6), (0.0, 0.62, 0.0))
+    assert check_generic(generic_checker, port, s, cam, 64, 48, 2, [(2.5, 4.0, 3.0)], 3, clause_free=True) > 500
+
+
+@pytest.mark.parametrize("name", ["cube", "shadow_test", "dodge"])
+def test_generic_filter_sound_on_reference_scenes(generic_checker, port, name):
+    """Scenes shipped with the reference (large triangles, slivers: the grazing clause stays)."""
+    from conftest import load_scene
+    from raytracert_b200 import host
+    s = load_scene(name)
+    cam = {"cube": host.Camera(40, 40, (2.6, 2.4, 3.0), (.5, .5, .5)), "shadow_test": host.Camera(40, 30, (1, 5, 7), (1, 1.2, 0.7)),
+           "dodge": host.Camera(48, 27, (.75, .55, 1.1), (.07, 0, .23))}[name]
+    lights = [tuple(cam.eye)]
+    assert check_generic(generic_checker, port, s, cam, cam.W, cam.H, 1, lights, 2 if name == "dodge" else 1, clause_free=False) > 50
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_generic_filter_sound_on_random_soups(generic_checker, port, seed):
+    """Random soups with triangle sizes over two decades, slivers included (the fuzz test's kinds 0 and 3)."""
+    from raytracert_b200 import host
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.integers(50, 300))
+    ctr = rng.uniform(-1.5, 1.5, (n, 1, 3))
+    size = 10 ** rng.uniform(-2.0, 0.2, (n, 1, 1))
+    tri = ctr + size * rng.normal(size=(n, 3, 3))
+    if seed % 2:
+        tri[1, 2] = tri[1, 0] + (tri[1, 1] - tri[1, 0]) * 0.5          # exactly collinear in double, not in float
+        tri[2, 2] = tri[2, 1] + 1e-6 * (tri[2, 0] - tri[2, 1])         # sliver
+    v = tri.reshape(-1, 3).astype(np.float32)
+    idx = np.arange(len(v), dtype=np.uint32).reshape(-1, 3)
+    s = host.Scene(v, idx, np.zeros(n, np.uint32), host.face_normals(v, idx), np.zeros((1, 16), np.float32))
+    cam = host.Camera(40, 32, tuple(rng.uniform(-1, 1, 3) + np.array([0, 0, 5.0])), tuple(rng.uniform(-0.5, 0.5, 3)))
+    lights = rng.uniform(-6, 6, (2, 3))
+    check_generic(generic_checker, port, s, cam, 40, 32, 1, [tuple(l) for l in lights], 1, clause_free=False)
 
 
 def test_camera_setup_rejects_what_is_not_a_pencil(checker):

@@ -83,15 +83,54 @@ def sweep(name, scene, cam, W, H, pf, lights, n_rays):
     return out
 
 
+L.generic_check.argtypes = [C.c_int, C.c_double, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.POINTER(T.Result)]
+
+
+def generic_sweep(name, scene, cam, W, H, pf, lights, n_rays, clause_free):
+    """The generic filter (pencil_check.cpp:generic_check) on frame rays, continuation-ray shaped rays and shadow rays."""
+    t0 = time.time()
+    tris = np.ascontiguousarray(T.tri_array(scene), np.float32)
+    M = T.magnitude_bound(scene, cam.corners)
+    rng = np.random.default_rng(23)
+    step = max(1, int(np.sqrt(W * H * pf * pf / max(n_rays, 1))))
+    rays = T.primary_rays(cam.corners, W, H, pf, step)
+    port.set_scene(scene)
+    port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
+    _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+    origins = (hit[prim >= 0] + np.float32(0.1)).astype(np.float32)
+    batches = [("primary rays of the frame", rays), ("continuation-ray shaped rays, half of them aimed at edges / vertices", T.bounce_like_rays(tris, rng, n_rays))]
+    for Lp in lights:
+        Lp = np.asarray(Lp, np.float32)
+        Pe = T.edge_points(tris, rng, max(200, n_rays // 4))
+        back = (Pe + (Pe - Lp) * rng.uniform(0.05, 1.5, (len(Pe), 1)).astype(np.float32)).astype(np.float32)
+        o = np.concatenate([origins, back])
+        batches.append((f"shadow rays to {tuple(float(x) for x in Lp)}", np.concatenate([o, np.broadcast_to(Lp, o.shape)], axis=1)))
+    out = {"scene": name + " -- GENERIC filter", "triangles": int(len(tris)), "launches": []}
+    for label, batch in batches:
+        batch = np.ascontiguousarray(batch, np.float32)
+        bmin = -0.5 if clause_free and T.grazing_product(tris, batch) * 1.11e-5 < 1e-5 else 1.0e-5
+        for mode in (0, 1):
+            r = T.Result()
+            L.generic_check(mode, float(M), bmin, len(tris), tris.ctypes.data, len(batch), batch.ctypes.data, 1.0 + 2.0 ** -22, 1.0 - 2.0 ** -22, pair_fn, C.byref(r))
+            out["launches"].append({"kind": label, "mode": "nearest-hit (tightest distance bound)" if mode == 0 else "any-hit", "grazing_clause": bmin > 0, "setup_ok": True,
+                                    "rays": int(len(batch)), "pairs": int(r.pairs), "accepted_by_reference": int(r.ref_hits), "candidates": int(r.candidates),
+                                    "violations": int(r.violations), "grazing_skipped": 0})
+    out["seconds"] = time.time() - t0
+    out["pairs_total"] = sum(l["pairs"] for l in out["launches"])
+    out["violations_total"] = sum(l["violations"] for l in out["launches"])
+    return out
+
+
 res = []
 s = scenes.balls_standin()
 cam = host.Camera(800, 800, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0))
 res.append(sweep("Balls stand-in, bench camera", s, cam, 800, 800, 4, [(2.5, 4.0, 3.0), (0.0, 0.0, 4.0), (-6.0, 3.0, 1.0)], args.rays))
+res.append(generic_sweep("Balls stand-in, bench camera", s, cam, 800, 800, 4, [(2.5, 4.0, 3.0)], args.rays // 2, True))
 cam2 = host.Camera(800, 800)
 res.append(sweep("Balls stand-in, default camera (eye in the water plane)", s, cam2, 800, 800, 4, [tuple(cam2.eye)], args.rays // 2))
 if args.sphere_rays > 0:
     s1 = scenes.tessellated_sphere()
     cam3 = host.Camera(3840, 2160, (0.0, 0.6, 3.4), (0, 0, 0))
     res.append(sweep("1 M-triangle sphere (configs[3])", s1, cam3, 3840, 2160, 4, [(2.5, 4.0, 3.0)], args.sphere_rays))
-print(json.dumps({"what": "CPU replay of the pencil filter against the oracle, every (ray, triangle) pair", "sweeps": res,
+print(json.dumps({"what": "CPU replay of the pencil filter (and restatement of the generic filter) against the oracle, every (ray, triangle) pair", "sweeps": res,
                   "pairs_total": sum(r["pairs_total"] for r in res), "violations_total": sum(r["violations_total"] for r in res)}))
