@@ -44,7 +44,17 @@ static int dominant_axis(const float* A, const float* B, const float* C) {   // 
     return w;
 }
 
+// g_premise = 1: the launch relies on the scene-level clause-free proof (pairs with |cos| < cos_g are certain misses in the
+// reference; what rt_b200.cu requires today).  g_premise = 0: no such proof -- instead a triangle whose plane passes within
+// lam_max*cos_g + 2*delta of the common point is left to the exact path for every ray (counted in near_plane), because for
+// every other triangle a pair that can hit inside the scene has |cos| = |H'|/lambda >= cos_g by geometry alone.
+static int g_premise = 1;
+static long long g_near_plane = 0;
+
 extern "C" {
+
+void pencil_check_set_premise(int on) { g_premise = on; }
+long long pencil_check_near_planes(void) { return g_near_plane; }
 
 // mode 0: primary rays of the camera `setup24` (24 corner floats); mode 1: shadow rays ending at the light `setup24[0..2]`,
 // box = setup24[3..5] (lo) / [6..8] (hi).  tri: ntri x 9 floats.  rays: n x 6 floats (origin, dest).
@@ -65,6 +75,7 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
 
     std::vector<float> rec((size_t)ntri * 16);
     std::vector<uint8_t> state(ntri);   // 0 record, 1 always (not in the records), 2 never
+    long long near_plane = 0;
     for (int i = 0; i < ntri; ++i) {
         const float *A = tri + 9 * i, *B = A + 3, *C = A + 6;
         float* q = &rec[(size_t)16 * i];
@@ -76,8 +87,14 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
         if (n[0] == 0.f && n[1] == 0.f && n[2] == 0.f) { state[i] = 2; pencil_never(q); ++R.never_recs; continue; }
         const FilterTol t = filter_tolerances(A, B, C, dominant_axis(A, B, C), M_scene);
         if (t.always || !(std::fabs(Df) > 0.f) || !std::isfinite(Df)) { state[i] = 1; pencil_never(q); ++R.always_tris; continue; }
+        if (!g_premise) {
+            double H = 0.0;
+            for (int k = 0; k < 3; ++k) H += ((double)A[k] - S.E[k]) * t.n3[k];
+            if (!(std::fabs(H) / t.nn >= S.lam_max * S.cos_g + 2.0 * S.delta)) { state[i] = 1; pencil_never(q); ++near_plane; continue; }
+        }
         if (!pencil_record(A, B, C, t.E0, t.E1, S, q)) { state[i] = 2; ++R.never_recs; }
     }
+    g_near_plane = near_plane;
 
     int64_t pairs = 0, ref_hits = 0, cands = 0, viol = 0, graz = 0, unsafe = 0;
     int bad_ray = -1, bad_tri = -1;
@@ -130,7 +147,7 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
                     const double v[3] = {(double)C[0] - A[0], (double)C[1] - A[1], (double)C[2] - A[2]};
                     const double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
                     const double cs = std::fabs(n[0] * ddx + n[1] * ddy + n[2] * ddz) / (std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) * dl);
-                    if (cs < S.cos_g) { ++graz; continue; }
+                    if (g_premise && cs < S.cos_g) { ++graz; continue; }
                     ++viol;
 #pragma omp critical
                     if (bad_ray < 0) { bad_ray = r; bad_tri = i; }
