@@ -108,7 +108,8 @@ typedef struct rt_stats {
     uint32_t n_gpus, rank, n_triangles, n_levels;
     uint32_t n_launches;                              /* kernels launched for the frame (per GPU)      */
     uint32_t variant;                                 /* bit 0: scan kernels without the grazing clause (fine mesh);
-                                                       * bit 1: pencil filter on the primary rays; bit 2: on shadow rays */
+                                                       * bit 1: pencil filter on the primary rays; bit 2: on shadow rays;
+                                                       * bit 3: pencil records built without the clause-free proof */
     float ms_trace_primary;                           /* the level-0 (primary ray) part of ms_trace */
     uint32_t reserved;
 } rt_stats;
@@ -163,6 +164,11 @@ int rt_trace(const rt_params* params, int n, const float* origins, const float* 
  * camera / light outside the scene box; rt_stats.variant says what was used).  Same filter + exact tiers, identical
  * image and ids.  0 = always the generic filter. */
 #define RT_OPT_PENCIL 2
+/* RT_OPT_PENCIL_ANY (default 0, EXPERIMENTAL -- checked on the CPU only, tests/test_pencil_filter.py; not yet run on a GPU):
+ * 1 = the pencil filter is also used for scenes without the clause-free proof (large triangles: cube, dodge).  Triangles
+ * whose plane passes within lam_max*cos_g + 2*delta of the common point get "always candidate" records (at most 16 per
+ * launch, else that launch keeps the generic kernels); rt_stats.variant bit 3 says it was used. */
+#define RT_OPT_PENCIL_ANY 3
 int rt_set_option(int option, int value);
 
 int rt_get_stats(rt_stats* out);

@@ -16,6 +16,7 @@ RT_ALL_FEATURES = 63
 RT_MAX_LIGHTS = 16
 RT_OPT_TILE_CULLING = 1
 RT_OPT_PENCIL = 2
+RT_OPT_PENCIL_ANY = 3
 
 
 class RtMaterial(C.Structure):

@@ -85,6 +85,7 @@ struct RtDevice {
     // pencil filter (rt_pencil.h): slot 0 = records around the eye, slot 1 + l = around light l; rebuilt every frame
     float4* prec = nullptr; size_t cap_prec = 0;
     float4* scene_box = nullptr;            // device: union of the tile boxes (k_scene_box)
+    unsigned int* n_near = nullptr;         // device: "always candidate" records per pencil slot (RT_OPT_PENCIL_ANY)
     float box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0};   // host copy, valid while the generic records are
     // per-chunk state
     size_t cap_samples = 0;
@@ -121,6 +122,7 @@ struct Global {
     ScanConfig pscan = {2, 8, 2};    // shape of the pencil kernels
     bool tile_culling = false;       // RT_OPT_TILE_CULLING
     bool pencil = true;              // RT_OPT_PENCIL: common-point filter for primary / shadow rays where it applies
+    bool pencil_any = false;         // RT_OPT_PENCIL_ANY (experimental): also for scenes without the clause-free proof
     bool allow_no_grazing = true;    // RT_B200_GRAZING=1 forces the grazing clause on (experiments)
     float max_uv = 0.f;              // max over the triangles of |v1-v0| * |v2-v0| (see build_records)
     float max_ni = 1.f;              // max over the materials of max(Ni, 1/Ni): bounds the refracted direction
@@ -210,7 +212,7 @@ int create_device(RtDevice& d, int device, int rank) {
 void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
-    void* ptrs[] = {d.prec, d.scene_box, d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+    void* ptrs[] = {d.n_near, d.prec, d.scene_box, d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
                     d.q_hit, d.key, d.hit0, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -296,6 +298,7 @@ void read_tuning_env() {
     if (const char* c = getenv("RT_B200_GRAZING")) g.allow_no_grazing = atoi(c) == 0;
     if (const char* c = getenv("RT_B200_CULL")) g.tile_culling = atoi(c) != 0;   // same as rt_set_option(RT_OPT_TILE_CULLING, ..)
     if (const char* c = getenv("RT_B200_PENCIL")) g.pencil = atoi(c) != 0;       // same as rt_set_option(RT_OPT_PENCIL, ..)
+    if (const char* c = getenv("RT_B200_PENCIL_ANY")) g.pencil_any = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_ANY, ..)
     if (const char* pe = getenv("RT_B200_PTUNE")) {
         ScanConfig c = g.pscan;
         if (sscanf(pe, "%d,%d,%d", &c.rp, &c.j, &c.minb) == 3 && pencil_config_exists(c)) g.pscan = c;
@@ -421,6 +424,7 @@ void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float e
 struct PencilPlan {
     bool cam = false, any_light = false;
     bool light[RT_MAX_LIGHTS] = {};
+    bool no_premise = false;   // built without the clause-free proof (RT_OPT_PENCIL_ANY)
     PencilSetup cam_setup, light_setup[RT_MAX_LIGHTS];
     size_t slot_vec = 0;   // float4 per record slot
 };
@@ -438,13 +442,16 @@ void apply_pencil(FrameParams& P, const RtDevice& d, const PencilPlan& plan, int
 // the geometric launch conditions of pencil_camera_setup / pencil_light_setup.
 int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
     plan = PencilPlan();
-    if (!g.pencil || cull || !d.no_grazing || d.ntri == 0) return RT_OK;
+    // premise: the scene-level clause-free proof holds (pairs below cos_min are certain misses in the reference).  Without it
+    // the pencil is used only under RT_OPT_PENCIL_ANY (experimental): near-plane triangles become "always candidate" records.
+    const bool premise = d.no_grazing;
+    if (!g.pencil || cull || d.ntri == 0 || (!premise && !g.pencil_any)) return RT_OK;
     const int npad = (d.ntiles + kPadTiles) * kTile;
     plan.slot_vec = (size_t)npad * kRecVec;
     const bool shadows = (rp.features & RT_SHADOWS) && rp.n_lights > 0 && !g.any_transparent;
     // A pencil answers only for pairs with |cos| >= cos_g (>= the generic 1.05e-5): the clause-free proof of
     // build_records must hold at that threshold for the launch's rays, |b_ref| < |dir||u||v| (cos_g + 10u) < 1e-5.
-    auto proof_holds = [&](const PencilSetup& S, double dir_max) { return (S.cos_g + 6e-7) * (double)g.max_uv * dir_max * 1.01 <= 0.95e-5; };
+    auto proof_holds = [&](const PencilSetup& S, double dir_max) { return !premise || (S.cos_g + 6e-7) * (double)g.max_uv * dir_max * 1.01 <= 0.95e-5; };
     plan.cam = pencil_camera_setup(rp.corners, (double)d.M_built, d.box_lo, d.box_hi, plan.cam_setup);
     if (plan.cam) {
         double dir_cam = 0.0;
@@ -467,12 +474,29 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
     if (!plan.cam && !plan.any_light) return RT_OK;
     int rc = ensure(d.prec, d.cap_prec, plan.slot_vec * (1 + (shadows ? rp.n_lights : 0)));
     if (rc) return rc;
+    if (!d.n_near) CU(cudaMalloc(&d.n_near, sizeof(unsigned int) * (1 + RT_MAX_LIGHTS)));
+    if (!premise) CU(cudaMemsetAsync(d.n_near, 0, sizeof(unsigned int) * (1 + RT_MAX_LIGHTS), d.stream));
     const int grid = (npad + 127) / 128;
-    if (plan.cam) k_build_pencil<<<grid, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.cam_setup, d.prec);
+    if (plan.cam)
+        k_build_pencil<<<grid, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.cam_setup, d.prec, premise ? 1 : 0, d.n_near);
     for (uint32_t l = 0; shadows && l < rp.n_lights; ++l)
         if (plan.light[l])
-            k_build_pencil<<<grid, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.light_setup[l], d.prec + (size_t)(1 + l) * plan.slot_vec);
+            k_build_pencil<<<grid, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.light_setup[l],
+                                                       d.prec + (size_t)(1 + l) * plan.slot_vec, premise ? 1 : 0, d.n_near + 1 + l);
     CU(cudaGetLastError());
+    if (!premise) {
+        // too many "always candidate" records would turn the scan into an exact scan: such a launch keeps the generic kernels
+        unsigned int h_near[1 + RT_MAX_LIGHTS];
+        CU(cudaMemcpyAsync(h_near, d.n_near, sizeof(h_near), cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        if (h_near[0] > kPencilMaxNear) plan.cam = false;
+        plan.any_light = false;
+        for (uint32_t l = 0; l < rp.n_lights; ++l) {
+            if (h_near[1 + l] > kPencilMaxNear) plan.light[l] = false;
+            plan.any_light = plan.any_light || plan.light[l];
+        }
+        plan.no_premise = plan.cam || plan.any_light;
+    }
     return RT_OK;
 }
 
@@ -602,7 +626,7 @@ int render_enqueue(const rt_params* rp) {
         rc = build_records(d, M, direction_bound(*rp, true, nullptr, nullptr, 0)); if (rc) return rc;
         PencilPlan plan;
         rc = plan_pencil(d, *rp, g.tile_culling && d.ntiles <= kCullMaxTiles, plan); if (rc) return rc;
-        d.pencil_used = (plan.cam ? 2u : 0u) | (plan.any_light ? 4u : 0u);
+        d.pencil_used = (plan.cam ? 2u : 0u) | (plan.any_light ? 4u : 0u) | (plan.no_premise ? 8u : 0u);
         rc = ensure_chunk_state(d, chunk_cap, rp->want_prim_id != 0, (size_t)rows_per_rank * row_samples); if (rc) return rc;
         rc = ensure_counters(d, std::max(1u, nchunks)); if (rc) return rc;
         size_t need_local = (size_t)rows_per_rank * W * 3;
@@ -753,6 +777,7 @@ void rt_shutdown(void) {
     g.scene_ready = g.frame_ready = false;
     g.tile_culling = false;
     g.pencil = true;
+    g.pencil_any = false;
     g_stage_triv.release(); g_stage_nm.release(); g_stage_sph.release(); g_stage_perm.release(); g_stage_mat.release();
 }
 
@@ -1102,6 +1127,7 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
 int rt_set_option(int option, int value) {
     if (option == RT_OPT_TILE_CULLING) { g.tile_culling = value != 0; return RT_OK; }
     if (option == RT_OPT_PENCIL) { g.pencil = value != 0; return RT_OK; }
+    if (option == RT_OPT_PENCIL_ANY) { g.pencil_any = value != 0; return RT_OK; }
     return fail(RT_ERR_INVALID, "unknown option %d", option);
 }
 

@@ -247,8 +247,10 @@ __global__ void k_scene_box(const float4* __restrict__ super_box, int nsuper, fl
 // Pencil records around the common point S.E (rt_pencil.h), position by position next to the generic records: a
 // position that is "never" there (padding, degenerate, always-exact triangle) is "never" here; id and the tile's
 // record count are copied.  M is the magnitude bound the generic records were built with (same E0 / E1).
+// premise = 0 (RT_OPT_PENCIL_ANY, no clause-free proof): triangles whose plane passes too close to the common point get an
+// "always candidate" record and are counted in *n_near (rt_pencil.h: pencil_plane_near).
 __global__ void k_build_pencil(const float4* __restrict__ triv, const float4* __restrict__ rec, int npos, int c1_end, int c2_end, float M,
-                               const PencilSetup S, float4* __restrict__ prec) {
+                               const PencilSetup S, float4* __restrict__ prec, int premise, unsigned int* __restrict__ n_near) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= npos) return;
     const float4 g3 = rec[4 * pos + 3];
@@ -260,7 +262,10 @@ __global__ void k_build_pencil(const float4* __restrict__ triv, const float4* __
         const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
         const float a3f[3] = {A.x, A.y, A.z}, b3f[3] = {B.x, B.y, B.z}, c3f[3] = {C.x, C.y, C.z};
         const FilterTol t = filter_tolerances(a3f, b3f, c3f, W, (double)M);
-        if (!t.always) pencil_record(a3f, b3f, c3f, t.E0, t.E1, S, q);
+        if (!t.always) {
+            if (!premise && pencil_plane_near(a3f, b3f, c3f, S)) { pencil_always(q); atomicAdd(n_near, 1u); }
+            else pencil_record(a3f, b3f, c3f, t.E0, t.E1, S, q);
+        }
     }
     prec[4 * pos] = make_float4(q[0], q[1], q[2], q[3]);
     prec[4 * pos + 1] = make_float4(q[4], q[5], q[6], q[7]);

@@ -177,6 +177,25 @@ RT_HD float pencil_round_up(double v) {   // a float >= v
     return f;
 }
 
+// Launches WITHOUT the scene-level clause-free proof (RT_OPT_PENCIL_ANY, experimental): a pair that hits inside the scene
+// has |cos| = |H'|/lambda >= |H'|/lam_max (H' = distance of the true line's point nearest E to the plane), so for a
+// triangle whose plane stays lam_max*cos_g + 2*delta away from E no pair below cos_g exists, by geometry alone.  The (few)
+// triangles nearer than that get an "always candidate" record: the exact path decides for every ray.
+RT_HD bool pencil_plane_near(const float A[3], const float B[3], const float C[3], const PencilSetup& S) {
+    const double u[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]};
+    const double v[3] = {(double)C[0] - A[0], (double)C[1] - A[1], (double)C[2] - A[2]};
+    const double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+    const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    const double H = ((double)A[0] - S.E[0]) * n[0] + ((double)A[1] - S.E[1]) * n[1] + ((double)A[2] - S.E[2]) * n[2];
+    return !(fabs(H) >= (S.lam_max * S.cos_g + 2.0 * S.delta) * nn * 1.001);   // NaN: near
+}
+RT_HD void pencil_always(float q[16]) {   // weights = 1, sigma = 1, e = zeta_hi + 1e30 > 0: a candidate for every ray
+    for (int i = 0; i < 12; ++i) q[i] = 0.0f;
+    q[2] = q[6] = q[10] = q[11] = 1.0f;
+    q[12] = 1e30f; q[15] = 0.0f;
+}
+constexpr unsigned int kPencilMaxNear = 16;   // more "always candidate" records than this: the launch keeps the generic kernels
+
 // Returns false (and writes a "never" record) when no ray of the pencil can validly hit the triangle.
 RT_HD bool pencil_record(const float A[3], const float B[3], const float C[3], double E0, double E1, const PencilSetup& S, float q[16]) {
     double p0[3], p1[3], p2[3], u[3], v[3], e12[3];

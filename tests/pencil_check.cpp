@@ -46,7 +46,7 @@ static int dominant_axis(const float* A, const float* B, const float* C) {   // 
 
 // g_premise = 1: the launch relies on the scene-level clause-free proof (pairs with |cos| < cos_g are certain misses in the
 // reference; what rt_b200.cu requires today).  g_premise = 0: no such proof -- instead a triangle whose plane passes within
-// lam_max*cos_g + 2*delta of the common point is left to the exact path for every ray (counted in near_plane), because for
+// lam_max*cos_g + 2*delta of the common point gets an "always candidate" record (counted in near_plane), because for
 // every other triangle a pair that can hit inside the scene has |cos| = |H'|/lambda >= cos_g by geometry alone.
 static int g_premise = 1;
 static long long g_near_plane = 0;
@@ -87,11 +87,7 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
         if (n[0] == 0.f && n[1] == 0.f && n[2] == 0.f) { state[i] = 2; pencil_never(q); ++R.never_recs; continue; }
         const FilterTol t = filter_tolerances(A, B, C, dominant_axis(A, B, C), M_scene);
         if (t.always || !(std::fabs(Df) > 0.f) || !std::isfinite(Df)) { state[i] = 1; pencil_never(q); ++R.always_tris; continue; }
-        if (!g_premise) {
-            double H = 0.0;
-            for (int k = 0; k < 3; ++k) H += ((double)A[k] - S.E[k]) * t.n3[k];
-            if (!(std::fabs(H) / t.nn >= S.lam_max * S.cos_g + 2.0 * S.delta)) { state[i] = 1; pencil_never(q); ++near_plane; continue; }
-        }
+        if (!g_premise && pencil_plane_near(A, B, C, S)) { pencil_always(q); ++near_plane; continue; }   // as k_build_pencil does
         if (!pencil_record(A, B, C, t.E0, t.E1, S, q)) { state[i] = 2; ++R.never_recs; }
     }
     g_near_plane = near_plane;

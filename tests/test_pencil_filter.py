@@ -299,11 +299,11 @@ def test_pencil_sound_in_extreme_setups(checker, port, case):
 
 @pytest.mark.parametrize("name", ["cube", "cube_default_camera", "shadow_test", "dodge", "mirror_room"])
 def test_pencil_sound_without_the_clause_free_premise(checker, port, name):
-    """Groundwork for scenes with large triangles (not used by the library yet): without the scene-level
+    """Groundwork for scenes with large triangles (experimental in the library): without the scene-level
     proof that the reference rejects grazing pairs, the pencil filter is still sound for every triangle whose plane stays
     lam_max*cos_g + 2*delta away from the common point -- a pair that can hit inside the scene then has |cos| >= cos_g by
-    geometry alone.  The few triangles nearer than that would go to the exact path (cube under the default camera: the four
-    triangles of the two faces whose planes contain the eye)."""
+    geometry alone.  The few triangles nearer than that get "always candidate" records (cube under the default camera: the four
+    triangles of the two faces whose planes contain the eye).  RT_OPT_PENCIL_ANY wires this into the library (default off)."""
     from conftest import load_scene
     from raytracert_b200 import host, scenes
     s = scenes.mirror_room(n=12) if name == "mirror_room" else load_scene("cube" if name.startswith("cube") else name)
@@ -325,7 +325,8 @@ def test_pencil_sound_without_the_clause_free_premise(checker, port, name):
     for batch in (rays, adv):
         r = checker(0, cam.corners, M, tris, batch, premise=False)
         assert r.setup_ok and r.violations == 0 and r.grazing_skipped == 0, f"{name}: {r.violations} accepted pairs were filtered out"
-        assert checker.near_planes == (4 if name == "cube_default_camera" else (1 if name == "dodge" else 0))
+        lo_n, hi_n = {"cube_default_camera": (4, 4), "dodge": (1, 4)}.get(name, (0, 0))
+        assert lo_n <= checker.near_planes <= hi_n
         accepted += r.ref_hits
     assert accepted > 1000
     port.set_scene(s)
