@@ -56,6 +56,8 @@ extern "C" {
 void pencil_check_set_premise(int on) { g_premise = on; }
 long long pencil_check_near_planes(void) { return g_near_plane; }
 
+// mode 2 (groundwork for reflection pencils): rays leaving a common point that the caller describes
+// directly -- setup24 = E (3 floats), chart axis f (3, any length), delta, w_max, lam_min; nearest-hit semantics like mode 0.
 // mode 0: primary rays of the camera `setup24` (24 corner floats); mode 1: shadow rays ending at the light `setup24[0..2]`,
 // box = setup24[3..5] (lo) / [6..8] (hi).  tri: ntri x 9 floats.  rays: n x 6 floats (origin, dest).
 // inv_scale perturbs the chart division (x, y scaled by it: a few ulp of extra direction error).
@@ -68,7 +70,20 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
     memset(&S, 0, sizeof(S));
     bool ok;
     if (mode == 0) ok = pencil_camera_setup(setup24, M_scene, nullptr, nullptr, S);
-    else ok = pencil_light_setup(setup24, setup24 + 3, setup24 + 6, M_scene, S);
+    else if (mode == 1) ok = pencil_light_setup(setup24, setup24 + 3, setup24 + 6, M_scene, S);
+    else {
+        double f[3] = {setup24[3], setup24[4], setup24[5]};
+        const double fl = std::sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+        for (int k = 0; k < 3; ++k) { S.E[k] = setup24[k]; f[k] /= fl; }
+        S.delta = setup24[6];
+        S.w_max = setup24[7];
+        const double lam_min = setup24[8];
+        pencil_frame(S, f);
+        pencil_finish_setup(S, M_scene);
+        S.cos_g = std::fmax(kPencilCosMin, std::fmax(2.5 * S.delta / lam_min, 5.0 * S.theta));
+        ok = fl > 0.0 && lam_min >= 2e-3 * S.M && S.w_max < 8.0;
+        mode = 0;   // same ray semantics as primary rays from here on
+    }
     R.setup_ok = ok ? 1 : 0;
     if (!ok) { *out = R; return 0; }
     R.delta = S.delta; R.M = S.M; R.cos_g = S.cos_g;

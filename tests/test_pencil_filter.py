@@ -342,6 +342,51 @@ def test_pencil_sound_without_the_clause_free_premise(checker, port, name):
             assert r.violations == 0 and r.grazing_skipped == 0, f"{name}, light {Lp}: {r.violations} accepted pairs were filtered out"
 
 
+def test_reflection_pencil_around_the_mirrored_eye(checker, port):
+    """Groundwork: the reflections of primary rays off one plane (here the stand-in's water, y = 0) form a
+    pencil through the mirror image of the eye.  Reflected rays computed like reflection() / addOffset()
+    (raytracing.cpp:266-285) in float32; the same records and the same filter, around E*, must keep every accepted pair."""
+    from raytracert_b200 import host, scenes
+    f = np.float32
+    s = scenes.balls_standin(grid=48, slices=24, stacks=12)
+    cam = host.Camera(120, 120, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0))
+    tris = tri_array(s)
+    M = magnitude_bound(s, cam.corners)
+    rays = primary_rays(cam.corners, 120, 120, 2, 1)
+    port.set_scene(s)
+    port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
+    _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+    nrm = s.normals[np.maximum(prim, 0)]
+    flat = np.all(tris.reshape(-1, 3, 3)[:, :, 1] == 0.0, axis=1)          # triangles lying exactly in the plane y = 0
+    sel = np.where((prim >= 0) & flat[np.maximum(prim, 0)])[0]
+    assert len(sel) > 2000
+    P = hit[sel].astype(f)
+    ray = (rays[sel, 3:] - rays[sel, :3]).astype(f)
+    r = (ray * (f(1) / np.sqrt((ray * ray).sum(1, dtype=f)).astype(f))[:, None]).astype(f)
+    nf = nrm[sel].astype(f)
+    R = (r - (f(2) * (nf * r).sum(1, dtype=f))[:, None] * nf).astype(f)
+    dest = (P + R).astype(f)
+    off = (dest - P).astype(f)
+    off = (off * (f(1) / np.sqrt((off * off).sum(1, dtype=f)).astype(f))[:, None]).astype(f)
+    point = (P + off * f(0.01)).astype(f)
+    brays = np.concatenate([point, dest], axis=1).astype(f)
+    estar = np.asarray(cam.eye, np.float64) * np.array([1.0, -1.0, 1.0])
+    dd = (dest - point).astype(np.float64)
+    dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    w = estar - point.astype(np.float64)
+    delta = np.linalg.norm(w - (w * dd).sum(1)[:, None] * dd, axis=1).max()
+    assert delta < 1e-5                                  # the camera pencil's own delta is 5e-6
+    fax = dd.mean(axis=0)
+    fax /= np.linalg.norm(fax)
+    setup = np.zeros(24, np.float32)
+    setup[:3], setup[3:6] = estar, fax
+    setup[6], setup[7], setup[8] = 4 * delta, (1.0 / (dd @ fax)).max() * 1.05, np.linalg.norm(point - estar, axis=1).min() * 0.9
+    for scale in (1.0, 1.0 + 3 * 2.0 ** -24):
+        res = checker(2, setup, M, tris, brays, scale)
+        assert res.setup_ok and res.violations == 0 and res.grazing_skipped == 0 and res.unsafe_rays == 0
+    assert res.candidates < 3 * len(brays)              # about one per ray: the triangle it starts on
+
+
 def bounce_like_rays(tris, rng, n):
     """Continuation-ray shaped rays (raytracing.cpp:266-285): origin = P + 0.01 * dir, dest = P + dir, P on a surface; half of
     them aimed at an edge / vertex point of another triangle."""
