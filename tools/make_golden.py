@@ -7,7 +7,7 @@ oracle/_ref):      make -C oracle ref && python tools/make_golden.py
 What it writes (all small, all regenerated deterministically):
   tests/golden/scenes/<name>.npz    scenes as the reference's own loader produced them (cube, dodge,
                                     shadow_test, quirks) or as raytracert_b200.scenes generated them
-                                    (room, glass, balls_small); UB pins applied (Tr/Ni = 1
+                                    (room, glass, balls_small, balls_fine); UB pins applied (Tr/Ni = 1
                                     where the MTL never sets them)
   tests/golden/loader/<name>.npz    raw reference-loader dumps for the loader parity test
   tests/golden/renders/<case>.npz   reference outputs per render case: clamped float RGB per pixel, u8
@@ -77,7 +77,8 @@ def main():
     sc["room"] = scenes.mirror_room()
     sc["glass"] = glass_room()
     sc["balls_small"] = scenes.balls_standin(grid=24, slices=16, stacks=8)
-    for name in ("room", "glass", "balls_small"):
+    sc["balls_fine"] = scenes.balls_standin(grid=48, slices=24, stacks=12)     # fine enough for the clause-free / pencil kernels
+    for name in ("room", "glass", "balls_small", "balls_fine"):
         sc[name].save(os.path.join(G, "scenes", name + ".npz"))
 
     OBL = ((2.6, 2.4, 3.0), (.5, .5, .5))
@@ -104,6 +105,8 @@ def main():
         ("glass_56_lvl6", "glass", 56, 56, RM, 1, 1, 6, 63, [(1.5, 2.8, 2.5)]),
         ("glass_40_pf2_norefraction", "glass", 40, 40, RM, 2, 2, 4, 63 & ~32, [(1.5, 2.8, 2.5)]),
         ("balls_small_64_pf2_lvl3", "balls_small", 64, 64, BL, 2, 2, 3, 63, [(2.5, 4.0, 3.0)]),
+        ("balls_fine_96x64_pf2_2lights_lvl3", "balls_fine", 96, 64, BL, 2, 2, 3, 63, [(2.5, 4.0, 3.0), (0.0, 2.6, 5.2)]),
+        ("balls_fine_default_camera_72_pf2", "balls_fine", 72, 72, None, 2, 2, 2, 63, None),
     ]
     for name, sname, W, H, look, pfx, pfy, lvl, feats, lights in cases:
         cam = host.Camera(W, H) if look is None else host.Camera(W, H, look[0], look[1])
