@@ -45,7 +45,7 @@ extern "C" {
 #define RT_HAS_NI 16u
 #define RT_HAS_TR 32u
 
-#define RT_MAX_LIGHTS 16
+#define RT_MAX_LIGHTS 16 /* the reference's 'L' key (main.cpp:334-336) has no limit: more lights are an error here (RT_ERR_INVALID), never a truncated frame */
 
 /* One Material (mesh.h:116-122), 64 bytes, laid out as four float4 for the device. */
 typedef struct rt_material {
@@ -96,7 +96,7 @@ typedef struct rt_params {
     uint32_t want_prim_id;                 /* also keep the per-sample primary primitive id      */
 } rt_params;
 
-/* Counters of the last rt_render / rt_trace (this process's share of the frame). */
+/* Counters of the last completed rt_render / rt_trace (this process's share of the frame). */
 typedef struct rt_stats {
     uint64_t primary_rays, shadow_rays, bounce_rays; /* == intersectMesh calls by kind              */
     uint64_t tri_tests;                               /* rays * triangles, the reference's count     */
@@ -109,7 +109,8 @@ typedef struct rt_stats {
     uint32_t n_launches;                              /* kernels launched for the frame (per GPU)      */
     uint32_t variant;                                 /* bit 0: scan kernels without the grazing clause (fine mesh);
                                                        * bit 1: pencil filter on the primary rays; bit 2: on shadow rays;
-                                                       * bit 3: pencil records built without the clause-free proof */
+                                                       * bit 3: pencil records built without the clause-free proof;
+                                                       * bit 4: the frame / batch was a CUDA-graph replay */
     float ms_trace_primary;                           /* the level-0 (primary ray) part of ms_trace */
     uint32_t reserved;
 } rt_stats;
@@ -148,7 +149,7 @@ int rt_download_framebuffer_u8(uint8_t* rgb8);
 int rt_trace(const rt_params* params, int n, const float* origins, const float* dests, float* rgb,
              int32_t* prim_id, float* hit);
 
-/* Options (rt_set_option; they persist until rt_shutdown).
+/* Options (rt_set_option; they persist until rt_shutdown -- across rt_init, so they may be set before it).
  * RT_OPT_TILE_CULLING (default 0): 1 = conservative tile culling.  Triangles are scanned in tiles of 128; with this
  *   option only tiles (found through a two-level hierarchy of bounding boxes) that some ray of a thread block can reach
  *   are streamed, and a warp skips a tile when none of its own rays can reach the box of the tile's (tolerance-dilated)
@@ -164,11 +165,17 @@ int rt_trace(const rt_params* params, int n, const float* origins, const float* 
  * camera / light outside the scene box; rt_stats.variant says what was used).  Same filter + exact tiers, identical
  * image and ids.  0 = always the generic filter. */
 #define RT_OPT_PENCIL 2
-/* RT_OPT_PENCIL_ANY (default 0, EXPERIMENTAL -- checked on the CPU only, tests/test_pencil_filter.py; not yet run on a GPU):
- * 1 = the pencil filter is also used for scenes without the clause-free proof (large triangles: cube, dodge).  Triangles
- * whose plane passes within lam_max*cos_g + 2*delta of the common point get "always candidate" records (at most 16 per
- * launch, else that launch keeps the generic kernels); rt_stats.variant bit 3 says it was used. */
+/* RT_OPT_PENCIL_ANY (default 1): the pencil filter is also used for scenes without the scene-level clause-free proof
+ * (large triangles: cube.obj, dodgeColorTest.obj).  Triangles whose plane passes within lam_max*cos_g + 2*delta of the
+ * common point get "always candidate" records -- the exact path decides for every ray -- (at most 16 per launch, else
+ * that launch keeps the generic kernels); rt_stats.variant bit 3 says it was used.  0 = pencil launches only under the
+ * clause-free proof.  Same filter + exact tiers, identical image and ids (tests/test_gpu_parity.py). */
 #define RT_OPT_PENCIL_ANY 3
+/* RT_OPT_GRAPH (default -1 = auto): small frames and small rt_trace batches (samples x triangles <= 4e9: the launch gaps
+ * would dominate -- cube.obj at 800x800 is 44 launches for 0.6 ms) are replayed from a captured CUDA graph (every scan
+ * launch has a fixed grid: persistent CTAs read their ray counts from device counters); rt_stats.variant bit 4.
+ * 0 = never, 1 = always.  A replayed frame reports no per-kernel times (rt_stats.ms_trace .. ms_resolve are 0). */
+#define RT_OPT_GRAPH 4
 int rt_set_option(int option, int value);
 
 int rt_get_stats(rt_stats* out);

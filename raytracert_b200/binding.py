@@ -17,6 +17,7 @@ RT_MAX_LIGHTS = 16
 RT_OPT_TILE_CULLING = 1
 RT_OPT_PENCIL = 2
 RT_OPT_PENCIL_ANY = 3
+RT_OPT_GRAPH = 4
 
 
 class RtMaterial(C.Structure):

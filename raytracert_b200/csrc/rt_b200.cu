@@ -75,7 +75,18 @@ struct RtDevice {
     int cls1 = 0, cls2 = 0;             // first tile of dominant-axis class 1 / 2
     uint32_t* perm = nullptr;           // record position -> triangle id (kNoTriangle = padding)
     size_t cap_perm = 0;
-    float M_built = 0.f, dir_built = 0.f;   // magnitude bound / longest ray the records were built for
+    float M_built = 0.f, dir_built = 0.f;   // magnitude bound / longest ray the records were built for (0: not built)
+    uint64_t rec_gen = 0;                   // bumped by every (re)build of the records: invalidates cached pencil records / graphs
+    float* h_small = nullptr;               // pinned: n_always + scene box read back by build_records, n_near by plan_pencil
+    cudaEvent_t ev_stage = nullptr;         // recorded after the last H2D copy out of the upload staging buffers
+    std::vector<uint8_t> plan_key;          // what the cached pencil records were built from (plan_pencil)
+    std::vector<uint8_t> plan_blob;         // the cached PencilPlan
+    cudaGraphExec_t frame_graph = nullptr;  // captured wavefront of a small frame (RT_OPT_GRAPH), valid while graph_key matches
+    std::vector<uint8_t> graph_key;
+    bool capturing = false;                 // launches go into a stream capture: no per-launch events
+    uint32_t launches_in_graph = 0;
+    int levels_in_graph = 0;
+    bool used_graph = false;                // the last frame was a graph replay (rt_stats.variant bit 4)
     bool no_grazing = false;                // the records carry no grazing clause (see build_records)
     unsigned int* n_always = nullptr;       // device counter written by k_build_records
     uint32_t* always_list = nullptr;        // triangles outside the filter (see k_build_records)
@@ -92,7 +103,12 @@ struct RtDevice {
     float4 *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *acc = nullptr, *hit = nullptr;
     uint32_t *lit = nullptr, *q_ray = nullptr, *q_hit = nullptr;
     unsigned long long* key = nullptr;  // nearest-hit merge keys, kKeyEmpty between launches
-    float4* hit0 = nullptr;             // rt_trace: copy of the level-0 hit records
+    bool key_dirty = false;             // a call failed between a scan and its k_finish: re-initialise before the next use
+    float4* hit0 = nullptr; size_t cap_hit0 = 0;          // rt_trace: copy of the level-0 hit records (grow-only)
+    float4* trace_in = nullptr; size_t cap_trace_in = 0;  // rt_trace: packed (origin, dest) rays as uploaded
+    cudaGraphExec_t trace_graph = nullptr;                // rt_trace: captured copies + wavefront of a small batch
+    std::vector<uint8_t> trace_key;
+    uint32_t launches_in_trace_graph = 0;
     uint32_t* counters = nullptr;      // kCntWords per chunk slot
     int counters_slots = 0;
     int frame_chunks = 0;              // counter slots the last frame / trace call used
@@ -116,13 +132,15 @@ struct Global {
     std::vector<RtDevice> devs;
     int world = 0;          // total ranks (== devs.size() in single-process mode)
     bool single_process = true;
-    bool scene_ready = false, frame_ready = false;
+    bool scene_ready = false, frame_ready = false;   // frame_ready: a framebuffer can be downloaded
+    bool stats_ready = false;                        // the counters describe a completed rt_render / rt_trace
     NcclApi nccl;
     ScanConfig scan = {2, 8, 2};
     ScanConfig pscan = {2, 8, 2};    // shape of the pencil kernels
     bool tile_culling = false;       // RT_OPT_TILE_CULLING
     bool pencil = true;              // RT_OPT_PENCIL: common-point filter for primary / shadow rays where it applies
-    bool pencil_any = false;         // RT_OPT_PENCIL_ANY (experimental): also for scenes without the clause-free proof
+    bool pencil_any = true;          // RT_OPT_PENCIL_ANY: also for scenes without the clause-free proof (near-plane triangles: always candidates)
+    int graph_mode = -1;             // RT_OPT_GRAPH: -1 auto (small frames replay a captured CUDA graph), 0 never, 1 always
     bool allow_no_grazing = true;    // RT_B200_GRAZING=1 forces the grazing clause on (experiments)
     float max_uv = 0.f;              // max over the triangles of |v1-v0| * |v2-v0| (see build_records)
     float max_ni = 1.f;              // max over the materials of max(Ni, 1/Ni): bounds the refracted direction
@@ -164,6 +182,8 @@ struct PinnedStage {
 PinnedStage<float4> g_stage_triv, g_stage_nm, g_stage_sph;
 PinnedStage<uint32_t> g_stage_perm;
 PinnedStage<rt_material> g_stage_mat;
+PinnedStage<float4> g_stage_rays, g_stage_out;   // rt_trace: rays in (origin, dest), results out (colour, level-0 hit)
+cudaEvent_t g_stage_event = nullptr;             // recorded after the last H2D copy out of the staging buffers
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -202,6 +222,8 @@ int create_device(RtDevice& d, int device, int rank) {
     CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     for (auto& e : d.ev) CU(cudaEventCreate(&e));
     for (auto& e : d.ev_phase) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&d.ev_stage, cudaEventDisableTiming));
+    CU(cudaHostAlloc((void**)&d.h_small, 64 * sizeof(float), cudaHostAllocDefault));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(RT_ERR_NO_DEVICE, "device %d is sm_%d%d; librt_b200 is built for sm_100a only", device, prop.major, prop.minor);
@@ -213,11 +235,15 @@ void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
     void* ptrs[] = {d.n_near, d.prec, d.scene_box, d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
-                    d.q_hit, d.key, d.hit0, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
+                    d.q_hit, d.key, d.hit0, d.trace_in, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     for (auto& e : d.ev_phase) if (e) cudaEventDestroy(e);
     for (auto& e : d.kev) cudaEventDestroy(e);
+    if (d.frame_graph) cudaGraphExecDestroy(d.frame_graph);
+    if (d.trace_graph) cudaGraphExecDestroy(d.trace_graph);
+    if (d.ev_stage) cudaEventDestroy(d.ev_stage);
+    if (d.h_small) cudaFreeHost(d.h_small);
     if (d.stream) cudaStreamDestroy(d.stream);
     d = RtDevice();
 }
@@ -226,7 +252,7 @@ void destroy_device(RtDevice& d) {
 struct LaunchTimer {
     RtDevice& d;
     bool timed;
-    LaunchTimer(RtDevice& dev, int kind) : d(dev), timed(dev.kev_kind.size() < kMaxTimedLaunches) {
+    LaunchTimer(RtDevice& dev, int kind) : d(dev), timed(!dev.capturing && dev.kev_kind.size() < kMaxTimedLaunches) {
         if (timed) {
             const size_t i = d.kev_kind.size();
             while (d.kev.size() < 2 * (i + 1)) { cudaEvent_t e; cudaEventCreate(&e); d.kev.push_back(e); }
@@ -299,6 +325,7 @@ void read_tuning_env() {
     if (const char* c = getenv("RT_B200_CULL")) g.tile_culling = atoi(c) != 0;   // same as rt_set_option(RT_OPT_TILE_CULLING, ..)
     if (const char* c = getenv("RT_B200_PENCIL")) g.pencil = atoi(c) != 0;       // same as rt_set_option(RT_OPT_PENCIL, ..)
     if (const char* c = getenv("RT_B200_PENCIL_ANY")) g.pencil_any = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_ANY, ..)
+    if (const char* c = getenv("RT_B200_GRAPH")) g.graph_mode = atoi(c) < 0 ? -1 : (atoi(c) != 0);   // same as rt_set_option(RT_OPT_GRAPH, ..)
     if (const char* pe = getenv("RT_B200_PTUNE")) {
         ScanConfig c = g.pscan;
         if (sscanf(pe, "%d,%d,%d", &c.rp, &c.j, &c.minb) == 3 && pencil_config_exists(c)) g.pscan = c;
@@ -335,25 +362,29 @@ float pow2_ceil(float v) {
 // than 1 (they bound the reflected / refracted directions in direction_bound()).  ("Always exact" triangles do not go
 // through the filter at all: always_list.)  Fine meshes (the Balls stand-in, the 1 M-triangle sphere)
 // qualify; scenes with large triangles (cube, ground quads) or far lights keep the clause.
+bool clause_free_for(float dir_max) {
+    return g.allow_no_grazing && g.cos_min <= 1.0e-5f && g.unit_normals && (double)g.max_uv * (double)dir_max <= 0.85;
+}
+
+// The records are (re)built for the request at hand, not for the largest one ever seen: one rt_trace call with a long
+// ray or a far origin must not switch the clause-free kernels (and with them the pencil launches' premise) off for every
+// later frame.  They are kept while they cover the request (M within a factor 4, every ray no longer than dir_built) AND
+// decide the grazing clause the way this request would.  One host synchronisation per rebuild (n_always + scene box).
 int build_records(RtDevice& d, float M, float dir_max) {
     dir_max = pow2_ceil(dir_max);   // coarse steps: a moving camera does not rebuild every frame
-    if (d.M_built >= M && d.dir_built >= dir_max && d.rec) return RT_OK;
+    const bool want_clause_free = clause_free_for(dir_max);
+    if (d.rec && d.M_built >= M && d.M_built <= 4.0f * M && d.dir_built >= dir_max && d.no_grazing == want_clause_free) return RT_OK;
     CU(cudaSetDevice(d.device));
-    M = std::max(M, d.M_built);
-    dir_max = std::max(dir_max, d.dir_built);
     const int npad = (d.ntiles + kPadTiles) * kTile;
     if (!d.n_always) CU(cudaMalloc(&d.n_always, sizeof(unsigned int)));
     CU(cudaMemsetAsync(d.n_always, 0, sizeof(unsigned int), d.stream));
     int rc = ensure(d.always_list, d.cap_always, (size_t)std::max(d.ntri, 1));
     if (rc) return rc;
-    d.no_grazing = g.allow_no_grazing && g.cos_min <= 1.0e-5f && g.unit_normals && (double)g.max_uv * (double)dir_max <= 0.85;
+    d.no_grazing = want_clause_free;
+    d.M_built = 0.f;   // not valid until the read-back below has completed
     k_build_records<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.perm, npad, d.cls1 * kTile, d.cls2 * kTile, M,
                                                            d.no_grazing ? kBminNoGrazing : g.cos_min, d.rec, d.n_always, d.always_list);
     CU(cudaGetLastError());
-    unsigned int n_always = 0;
-    CU(cudaMemcpyAsync(&n_always, d.n_always, sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
-    CU(cudaStreamSynchronize(d.stream));
-    d.n_always_host = (int)n_always;
     const int tiles_padded = d.ntiles + kPadTiles;
     k_build_tile_boxes<<<(tiles_padded + 127) / 128, 128, 0, d.stream>>>(d.triv, d.rec, tiles_padded, M, d.tile_box);
     CU(cudaGetLastError());
@@ -365,13 +396,16 @@ int build_records(RtDevice& d, float M, float dir_max) {
     if (!d.scene_box) CU(cudaMalloc(&d.scene_box, 2 * sizeof(float4)));
     k_scene_box<<<1, 32, 0, d.stream>>>(d.super_box, nsuper, d.scene_box);
     CU(cudaGetLastError());
-    float4 hb[2];
-    CU(cudaMemcpyAsync(hb, d.scene_box, sizeof(hb), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaMemcpyAsync(d.h_small, d.scene_box, 2 * sizeof(float4), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaMemcpyAsync(d.h_small + 8, d.n_always, sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
-    d.box_lo[0] = hb[0].x; d.box_lo[1] = hb[0].y; d.box_lo[2] = hb[0].z;
-    d.box_hi[0] = hb[1].x; d.box_hi[1] = hb[1].y; d.box_hi[2] = hb[1].z;
+    unsigned int n_always = 0;
+    memcpy(&n_always, d.h_small + 8, sizeof(n_always));
+    d.n_always_host = (int)n_always;
+    for (int k = 0; k < 3; ++k) { d.box_lo[k] = d.h_small[k]; d.box_hi[k] = d.h_small[4 + k]; }
     d.M_built = M;
     d.dir_built = dir_max;
+    ++d.rec_gen;
     return RT_OK;
 }
 
@@ -388,6 +422,11 @@ int ensure_chunk_state(RtDevice& d, size_t nsamples, bool want_prim, size_t prim
         // keys are kKeyEmpty whenever no scan is in flight: set once here, restored by k_finish after every read
         CU(cudaMemsetAsync(d.key, 0xff, 8 * nsamples, d.stream));
         d.cap_samples = nsamples;
+        d.key_dirty = false;
+    }
+    if (d.key_dirty) {
+        CU(cudaMemsetAsync(d.key, 0xff, 8 * d.cap_samples, d.stream));
+        d.key_dirty = false;
     }
     if (want_prim) { int rc = ensure(d.prim, d.cap_prim, prim_total); if (rc) return rc; }
     return RT_OK;
@@ -446,6 +485,19 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
     // the pencil is used only under RT_OPT_PENCIL_ANY (experimental): near-plane triangles become "always candidate" records.
     const bool premise = d.no_grazing;
     if (!g.pencil || cull || d.ntri == 0 || (!premise && !g.pencil_any)) return RT_OK;
+    // The pencil records depend on the generic records (rec_gen: scene, M, clause), the corner rays and the lights: an
+    // unchanged frame set-up (a bench loop, a still camera) reuses them -- no build launches, no read-back.
+    std::vector<uint8_t> key(sizeof(uint64_t) + sizeof(rp.corners) + sizeof(rp.lights) + 4 * sizeof(uint32_t));
+    {
+        uint8_t* k = key.data();
+        memcpy(k, &d.rec_gen, sizeof(uint64_t)); k += sizeof(uint64_t);
+        memcpy(k, rp.corners, sizeof(rp.corners)); k += sizeof(rp.corners);
+        memcpy(k, rp.lights, sizeof(rp.lights)); k += sizeof(rp.lights);
+        const uint32_t w[4] = {rp.n_lights, rp.features & RT_SHADOWS, (uint32_t)g.pencil_any, (uint32_t)g.any_transparent};
+        memcpy(k, w, sizeof(w));
+    }
+    if (d.prec && key == d.plan_key && d.plan_blob.size() == sizeof(PencilPlan)) { memcpy(&plan, d.plan_blob.data(), sizeof(PencilPlan)); return RT_OK; }
+    d.plan_key.clear();
     const int npad = (d.ntiles + kPadTiles) * kTile;
     plan.slot_vec = (size_t)npad * kRecVec;
     const bool shadows = (rp.features & RT_SHADOWS) && rp.n_lights > 0 && !g.any_transparent;
@@ -487,8 +539,9 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
     if (!premise) {
         // too many "always candidate" records would turn the scan into an exact scan: such a launch keeps the generic kernels
         unsigned int h_near[1 + RT_MAX_LIGHTS];
-        CU(cudaMemcpyAsync(h_near, d.n_near, sizeof(h_near), cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaMemcpyAsync(d.h_small + 16, d.n_near, sizeof(h_near), cudaMemcpyDeviceToHost, d.stream));
         CU(cudaStreamSynchronize(d.stream));
+        memcpy(h_near, d.h_small + 16, sizeof(h_near));
         if (h_near[0] > kPencilMaxNear) plan.cam = false;
         plan.any_light = false;
         for (uint32_t l = 0; l < rp.n_lights; ++l) {
@@ -497,6 +550,9 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
         }
         plan.no_premise = plan.cam || plan.any_light;
     }
+    d.plan_key = key;
+    d.plan_blob.resize(sizeof(PencilPlan));
+    memcpy(d.plan_blob.data(), &plan, sizeof(PencilPlan));
     return RT_OK;
 }
 
@@ -601,7 +657,19 @@ int validate_params(const rt_params* p, bool need_frame) {
     return RT_OK;
 }
 
-int render_enqueue(const rt_params* rp) {
+// Appends raw bytes to a cache key.
+struct KeyWriter {
+    std::vector<uint8_t>& v;
+    template <class T> void put(const T& x) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&x); v.insert(v.end(), p, p + sizeof(T)); }
+    void put_bytes(const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); v.insert(v.end(), b, b + n); }
+};
+
+// Frames whose launches are short enough for the launch gaps to matter (C1: 44 launches for 0.6 ms of frame) are replayed
+// from a captured CUDA graph.  Every scan launch has a fixed grid (persistent CTAs read their ray counts from device
+// counters), so the whole wavefront -- all chunks, all levels, the resolve -- is capturable as it is.
+constexpr double kGraphMaxTests = 4e9;   // samples x triangles below which RT_OPT_GRAPH = auto captures the frame
+
+int render_enqueue_impl(const rt_params* rp) {
     int rc = check_ready();
     if (rc) return rc;
     if (!g.scene_ready) return fail(RT_ERR_STATE, "rt_render before rt_upload_scene");
@@ -635,36 +703,81 @@ int render_enqueue(const rt_params* rp) {
             rc = ensure(d.fb_gather, d.cap_gather, need_local * G); if (rc) return rc;
             rc = ensure(d.fb_final, d.cap_final, (size_t)W * H * 3); if (rc) return rc;
         }
-        CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords * std::max(1u, nchunks), d.stream));
         d.frame_chunks = (int)std::max(1u, nchunks);
-        if (my_rows < rows_per_rank) CU(cudaMemsetAsync(d.fb_local, 0, need_local * sizeof(float), d.stream));
-        if (rp->want_prim_id) CU(cudaMemsetAsync(d.prim, 0xff, sizeof(int32_t) * rows_per_rank * row_samples, d.stream));
-        CU(cudaEventRecord(d.ev_phase[0], d.stream));
-        for (uint32_t c = 0; c < nchunks; ++c) {
-            FrameParams P;
-            fill_common(P, d, *rp, eps_r, d.counters + (size_t)c * kCntWords);
-            memcpy(P.corners, rp->corners, sizeof(P.corners));
-            P.divX = (float)(W * rp->pixelfactor_x - 1);   // main.cpp:360 (unsigned arithmetic, then float)
-            P.divY = (float)(H * rp->pixelfactor_y - 1);   // main.cpp:361
-            P.W = W; P.H = H; P.pfx = rp->pixelfactor_x; P.pfy = rp->pixelfactor_y;
-            P.row0 = c * rows_per_chunk;
-            P.nrows = std::min(rows_per_chunk, my_rows - P.row0);
-            P.G = G; P.rank = (uint32_t)d.rank;
-            P.nsamples = (uint32_t)(P.nrows * row_samples);
-            P.tiles_x = (W + 7) / 8;
-            P.nslots = P.tiles_x * ((P.nrows + 7) / 8) * 64u * spp;
-            P.sample_base = (unsigned long long)P.row0 * row_samples;
-            P.prim_out = rp->want_prim_id ? d.prim : nullptr;
-            int levels = run_wavefront(d, P, nullptr, &plan);
-            if (levels < 0) return levels;
-            g.stats.n_levels = (uint32_t)levels;
-            {
-                LaunchTimer t(d, kKindResolve);
-                k_resolve<<<d.num_sms * 4, 256, 0, d.stream>>>(P, d.fb_local);
+        int levels_done = 0;
+        // everything the device does for this rank's rows, in stream order (also what a graph capture records)
+        auto body = [&]() -> int {
+            CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords * std::max(1u, nchunks), d.stream));
+            if (my_rows < rows_per_rank) CU(cudaMemsetAsync(d.fb_local, 0, need_local * sizeof(float), d.stream));
+            if (rp->want_prim_id) CU(cudaMemsetAsync(d.prim, 0xff, sizeof(int32_t) * rows_per_rank * row_samples, d.stream));
+            for (uint32_t c = 0; c < nchunks; ++c) {
+                FrameParams P;
+                fill_common(P, d, *rp, eps_r, d.counters + (size_t)c * kCntWords);
+                memcpy(P.corners, rp->corners, sizeof(P.corners));
+                P.divX = (float)(W * rp->pixelfactor_x - 1);   // main.cpp:360 (unsigned arithmetic, then float)
+                P.divY = (float)(H * rp->pixelfactor_y - 1);   // main.cpp:361
+                P.W = W; P.H = H; P.pfx = rp->pixelfactor_x; P.pfy = rp->pixelfactor_y;
+                P.row0 = c * rows_per_chunk;
+                P.nrows = std::min(rows_per_chunk, my_rows - P.row0);
+                P.G = G; P.rank = (uint32_t)d.rank;
+                P.nsamples = (uint32_t)(P.nrows * row_samples);
+                P.tiles_x = (W + 7) / 8;
+                P.nslots = P.tiles_x * ((P.nrows + 7) / 8) * 64u * spp;
+                P.sample_base = (unsigned long long)P.row0 * row_samples;
+                P.prim_out = rp->want_prim_id ? d.prim : nullptr;
+                int levels = run_wavefront(d, P, nullptr, &plan);
+                if (levels < 0) return levels;
+                levels_done = levels;
+                {
+                    LaunchTimer t(d, kKindResolve);
+                    k_resolve<<<d.num_sms * 4, 256, 0, d.stream>>>(P, d.fb_local);
+                }
+                CU(cudaGetLastError());
             }
-            CU(cudaGetLastError());
+            return RT_OK;
+        };
+        const double tests = (double)my_rows * (double)row_samples * (double)std::max(d.ntri, 1);
+        const bool use_graph = g.graph_mode > 0 || (g.graph_mode < 0 && tests <= kGraphMaxTests && !getenv("RT_B200_LAUNCHLOG"));
+        if (!use_graph) {
+            CU(cudaEventRecord(d.ev_phase[0], d.stream));
+            rc = body(); if (rc) return rc;
+            CU(cudaEventRecord(d.ev_phase[1], d.stream));
+        } else {
+            // the captured launches take their arguments by value: the key holds everything they are derived from
+            std::vector<uint8_t> key;
+            KeyWriter kw{key};
+            kw.put(*rp); kw.put(d.rec_gen); kw.put_bytes(&plan, sizeof(plan));
+            const void* ptrs[] = {d.rec, d.triv, d.normal_mat, d.materials, d.spheres, d.prec, d.tile_box, d.super_box, d.always_list, d.ray_o, d.ray_d,
+                                  d.thr, d.acc, d.hit, d.lit, d.q_ray, d.q_hit, d.key, d.counters, d.prim, d.fb_local};
+            kw.put(ptrs);
+            const int cfg[] = {g.scan.rp, g.scan.j, g.scan.minb, g.pscan.rp, g.pscan.j, g.pscan.minb, (int)g.tile_culling, (int)G, d.rank, d.num_sms, (int)g.any_transparent};
+            kw.put(cfg);
+            if (!d.frame_graph || key != d.graph_key) {
+                if (d.frame_graph) { cudaGraphExecDestroy(d.frame_graph); d.frame_graph = nullptr; }
+                d.graph_key.clear();
+                CU(cudaStreamBeginCapture(d.stream, cudaStreamCaptureModeThreadLocal));
+                d.capturing = true;
+                rc = body();
+                d.capturing = false;
+                cudaGraph_t graph = nullptr;
+                const cudaError_t e = cudaStreamEndCapture(d.stream, &graph);
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+                const cudaError_t e2 = cudaGraphInstantiate(&d.frame_graph, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e2 != cudaSuccess) { d.frame_graph = nullptr; return fail(RT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e2)); }
+                d.graph_key = key;
+                d.launches_in_graph = (uint32_t)d.kev_kind.size();
+                d.levels_in_graph = levels_done;
+            }
+            d.kev_kind.assign(d.launches_in_graph, -1);   // counted, not timed individually
+            levels_done = d.levels_in_graph;
+            CU(cudaEventRecord(d.ev_phase[0], d.stream));
+            CU(cudaGraphLaunch(d.frame_graph, d.stream));
+            CU(cudaEventRecord(d.ev_phase[1], d.stream));
         }
-        CU(cudaEventRecord(d.ev_phase[1], d.stream));
+        g.stats.n_levels = (uint32_t)levels_done;
+        d.used_graph = use_graph;
     }
     // one all-gather per frame (rank-major slabs), then de-interleave rows
     if (G > 1 && !g.devs[0].comm) {
@@ -699,7 +812,19 @@ int render_enqueue(const rt_params* rp) {
     g.last = *rp;
     g.rows_per_rank = rows_per_rank;
     g.frame_ready = true;
+    g.stats_ready = true;
     return RT_OK;
+}
+
+// The frame state is invalid while a frame is being enqueued; a call that fails half way may leave a scan without its
+// k_finish (the merge keys are only reset there) and buffers reallocated: nothing of the old frame can be downloaded
+// afterwards, and the keys are re-initialised before their next use.
+int render_enqueue(const rt_params* rp) {
+    g.frame_ready = g.stats_ready = false;
+    const int rc = render_enqueue_impl(rp);
+    if (rc != RT_OK)
+        for (RtDevice& d : g.devs) { d.key_dirty = true; d.capturing = false; }
+    return rc;
 }
 
 int sync_all() {
@@ -758,7 +883,7 @@ int collect_stats() {
         st.ms_resolve = std::max(st.ms_resolve, by_kind[kKindResolve]);
         if (cudaEventElapsedTime(&ms, d.ev_phase[1], d.ev_phase[2]) == cudaSuccess) st.ms_gather = std::max(st.ms_gather, ms);
         st.n_launches = std::max(st.n_launches, (uint32_t)d.kev_kind.size());
-        st.variant |= (d.no_grazing ? 1u : 0u) | d.pencil_used;
+        st.variant |= (d.no_grazing ? 1u : 0u) | d.pencil_used | (d.used_graph ? 16u : 0u);
     }
     st.tri_tests = (st.primary_rays + st.shadow_rays + st.bounce_rays) * (uint64_t)st.n_triangles;
     return RT_OK;
@@ -770,19 +895,28 @@ extern "C" {
 
 const char* rt_last_error(void) { return g.error.c_str(); }
 
-void rt_shutdown(void) {
+// Frees every device resource; the options (rt_set_option) survive, so an option set before rt_init -- which starts by
+// releasing whatever an earlier rt_init left -- is not lost.
+static void release_all() {
     for (RtDevice& d : g.devs) destroy_device(d);
     g.devs.clear();
     g.world = 0;
-    g.scene_ready = g.frame_ready = false;
+    g.scene_ready = g.frame_ready = g.stats_ready = false;
+    if (g_stage_event) { cudaEventDestroy(g_stage_event); g_stage_event = nullptr; }
+    g_stage_triv.release(); g_stage_nm.release(); g_stage_sph.release(); g_stage_perm.release(); g_stage_mat.release();
+    g_stage_rays.release(); g_stage_out.release();
+}
+
+void rt_shutdown(void) {
+    release_all();
     g.tile_culling = false;
     g.pencil = true;
-    g.pencil_any = false;
-    g_stage_triv.release(); g_stage_nm.release(); g_stage_sph.release(); g_stage_perm.release(); g_stage_mat.release();
+    g.pencil_any = true;
+    g.graph_mode = -1;
 }
 
 int rt_init(int n_gpus) {
-    rt_shutdown();
+    release_all();
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -794,15 +928,15 @@ int rt_init(int n_gpus) {
     g.single_process = true;
     for (int i = 0; i < n_gpus; ++i) {
         int rc = create_device(g.devs[i], i, i);
-        if (rc) { rt_shutdown(); return rc; }
+        if (rc) { release_all(); return rc; }
     }
     if (n_gpus > 1) {
-        if (!g.nccl.load()) { rt_shutdown(); return fail(RT_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror()); }
+        if (!g.nccl.load()) { release_all(); return fail(RT_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror()); }
         std::vector<ncclComm_t> comms(n_gpus);
         std::vector<int> ids(n_gpus);
         for (int i = 0; i < n_gpus; ++i) ids[i] = i;
         ncclResult_t r = g.nccl.CommInitAll(comms.data(), n_gpus, ids.data());
-        if (r != 0) { rt_shutdown(); return fail(RT_ERR_NCCL, "ncclCommInitAll failed: %s", g.nccl.GetErrorString(r)); }
+        if (r != 0) { release_all(); return fail(RT_ERR_NCCL, "ncclCommInitAll failed: %s", g.nccl.GetErrorString(r)); }
         for (int i = 0; i < n_gpus; ++i) g.devs[i].comm = comms[i];
     }
     return RT_OK;
@@ -819,7 +953,7 @@ int rt_nccl_unique_id(void* out, size_t cap, size_t* bytes) {
 }
 
 int rt_init_rank(int device, int rank, int world, const void* nccl_id, size_t nccl_id_bytes) {
-    rt_shutdown();
+    release_all();
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -830,14 +964,14 @@ int rt_init_rank(int device, int rank, int world, const void* nccl_id, size_t nc
     g.world = world;
     g.single_process = false;
     int rc = create_device(g.devs[0], device, rank);
-    if (rc) { rt_shutdown(); return rc; }
+    if (rc) { release_all(); return rc; }
     if (world > 1 && nccl_id) {
-        if (!g.nccl.load()) { rt_shutdown(); return fail(RT_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror()); }
-        if (nccl_id_bytes < sizeof(ncclUniqueId)) { rt_shutdown(); return fail(RT_ERR_INVALID, "ncclUniqueId needs %zu bytes", sizeof(ncclUniqueId)); }
+        if (!g.nccl.load()) { release_all(); return fail(RT_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror()); }
+        if (nccl_id_bytes < sizeof(ncclUniqueId)) { release_all(); return fail(RT_ERR_INVALID, "ncclUniqueId needs %zu bytes", sizeof(ncclUniqueId)); }
         ncclUniqueId id;
         memcpy(&id, nccl_id, sizeof(id));
         ncclResult_t r = g.nccl.CommInitRank(&g.devs[0].comm, world, id, rank);
-        if (r != 0) { rt_shutdown(); return fail(RT_ERR_NCCL, "ncclCommInitRank failed: %s", g.nccl.GetErrorString(r)); }
+        if (r != 0) { release_all(); return fail(RT_ERR_NCCL, "ncclCommInitRank failed: %s", g.nccl.GetErrorString(r)); }
     }
     return RT_OK;
 }
@@ -849,51 +983,71 @@ int rt_upload_scene(const rt_scene* sc) {
         return fail(RT_ERR_INVALID, "incomplete rt_scene");
     if (sc->n_spheres && !sc->spheres) return fail(RT_ERR_INVALID, "n_spheres > 0 but spheres is NULL");
     const uint32_t n = sc->n_triangles;
-    for (uint32_t i = 0; i < n; ++i)
-        if (sc->tri_material[i] >= sc->n_materials) return fail(RT_ERR_INVALID, "triangle %u uses material %u of %u", i, sc->tri_material[i], sc->n_materials);
     for (uint32_t i = 0; i < sc->n_spheres; ++i)
         if (sc->spheres[i].material >= sc->n_materials) return fail(RT_ERR_INVALID, "sphere %u uses material %u of %u", i, sc->spheres[i].material, sc->n_materials);
+    // the staging buffers are reused: the copies of the previous upload must have left them
+    for (RtDevice& d : g.devs) {
+        CU(cudaSetDevice(d.device));
+        CU(cudaEventSynchronize(d.ev_stage));
+    }
 
-    // host-side packing: exact corners (3 float4 per triangle), normal+material, bounds
+    // ONE pass over the triangles: validation, packing (exact corners: 3 float4 per triangle; normal + material), the
+    // scene extent, the dominant axis of each plane normal (rt_kernels.cuh: 2-D projected filter) and the inputs of the
+    // clause-free proof (build_records): max |u||v| and "no face normal longer than 1".  Float arithmetic is enough for
+    // all of these: the class only has to be SOME axis with a non-zero normal component (checked again, in double, when
+    // the record is built), max_uv carries a 1e-4 margin, and anything non-finite gives up the proof.
     PinnedStage<float4>&triv = g_stage_triv, &nm = g_stage_nm;
     triv.resize((size_t)3 * std::max(n, 1u));
     nm.resize(std::max(n, 1u));
     if (!triv.data() || !nm.data()) return fail(RT_ERR_CUDA, "out of host memory for the scene staging buffers");
+    static std::vector<uint8_t> cls;
+    cls.resize(n);
+    size_t cnt[4] = {0, 0, 0, 0};
     float extent = 0.f;
+    double max_uuvv = 0.0;
+    bool unit_normals = true;
     for (uint32_t i = 0; i < n; ++i) {
-        const float* c[3] = {sc->v0 + 4 * i, sc->v1 + 4 * i, sc->v2 + 4 * i};
-        for (int k = 0; k < 3; ++k) {
-            triv[3 * i + k] = make_float4(c[k][0], c[k][1], c[k][2], 0.f);
-            for (int a = 0; a < 3; ++a) if (std::isfinite(c[k][a])) extent = std::max(extent, std::fabs(c[k][a]));
-        }
-        float4 v = make_float4(sc->normal[4 * i], sc->normal[4 * i + 1], sc->normal[4 * i + 2], 0.f);
-        memcpy(&v.w, &sc->tri_material[i], 4);
+        const uint32_t m = sc->tri_material[i];
+        if (m >= sc->n_materials) return fail(RT_ERR_INVALID, "triangle %u uses material %u of %u", i, m, sc->n_materials);
+        const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i, *N = sc->normal + 4 * i;
+        triv[3 * i] = make_float4(A[0], A[1], A[2], 0.f);
+        triv[3 * i + 1] = make_float4(B[0], B[1], B[2], 0.f);
+        triv[3 * i + 2] = make_float4(C[0], C[1], C[2], 0.f);
+        float4 v = make_float4(N[0], N[1], N[2], 0.f);
+        memcpy(&v.w, &m, 4);
         nm[i] = v;
+        float e = std::fmax(std::fmax(std::fabs(A[0]), std::fabs(A[1])), std::fabs(A[2]));
+        e = std::fmax(e, std::fmax(std::fmax(std::fabs(B[0]), std::fabs(B[1])), std::fabs(B[2])));
+        e = std::fmax(e, std::fmax(std::fmax(std::fabs(C[0]), std::fabs(C[1])), std::fabs(C[2])));   // fmax drops NaN operands
+        if (e <= FLT_MAX) extent = std::max(extent, e);
+        else  // an infinite coordinate: the finite ones still count
+            for (int k = 0; k < 3; ++k) { for (const float* p3 : {A, B, C}) if (std::isfinite(p3[k])) extent = std::max(extent, std::fabs(p3[k])); }
+        const float ux = B[0] - A[0], uy = B[1] - A[1], uz = B[2] - A[2];
+        const float vx = C[0] - A[0], vy = C[1] - A[1], vz = C[2] - A[2];
+        const float nx = std::fabs(uy * vz - uz * vy), ny = std::fabs(uz * vx - ux * vz), nz = std::fabs(ux * vy - uy * vx);
+        int w = 0;
+        if (ny > nx) w = 1;
+        if (nz > (w == 1 ? ny : nx)) w = 2;   // NaN compares false: non-finite triangles land in class 0 (and are "always exact")
+        cls[i] = (uint8_t)w;
+        ++cnt[w];
+        const double p2 = (double)(ux * ux + uy * uy + uz * uz) * (double)(vx * vx + vy * vy + vz * vz);
+        max_uuvv = (p2 == p2) ? std::max(max_uuvv, p2) : INFINITY;   // NaN vertices: never claim the bound
+        const float l2 = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+        if (!(l2 <= 1.00001f)) unit_normals = false;
     }
-    // group the triangles by the dominant axis of their plane normal (rt_kernels.cuh: 2-D projected filter); stable
-    // inside a class, every class padded to whole tiles
+    g.max_uv = (float)std::min(std::sqrt(max_uuvv) * 1.0001, 1e30);
+    g.unit_normals = unit_normals;
+    // group the triangles by class; stable inside a class, every class padded to whole tiles
     PinnedStage<uint32_t>& perm = g_stage_perm;
     int cls_tiles[3] = {0, 0, 0};
     {
-        std::vector<uint8_t> cls(n);
-        size_t cnt[4] = {0, 0, 0, 0};
-        for (uint32_t i = 0; i < n; ++i) {
-            const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i;
-            const double u[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]};
-            const double v[3] = {(double)C[0] - A[0], (double)C[1] - A[1], (double)C[2] - A[2]};
-            const double nx = std::fabs(u[1] * v[2] - u[2] * v[1]), ny = std::fabs(u[2] * v[0] - u[0] * v[2]), nz = std::fabs(u[0] * v[1] - u[1] * v[0]);
-            int w = 0;
-            if (ny > nx) w = 1;
-            if (nz > (w == 1 ? ny : nx)) w = 2;   // NaN compares false: non-finite triangles land in class 0 (and are "always exact")
-            cls[i] = (uint8_t)w;
-            ++cnt[w];
-        }
         size_t start[4], total = 0;
         int tiles4[4];
         for (int c = 0; c < 4; ++c) { start[c] = total; tiles4[c] = (int)((cnt[c] + kTile - 1) / kTile); total += (size_t)tiles4[c] * kTile; }
         cls_tiles[0] = tiles4[0]; cls_tiles[1] = tiles4[1]; cls_tiles[2] = tiles4[2] + tiles4[3];   // class 3 rides on the W = z path
         if (total == 0) { cls_tiles[0] = 1; total = kTile; }   // an empty scene still has one (padding) tile
         perm.assign(total + (size_t)kPadTiles * kTile, kNoTriangle);
+        if (!perm.data()) return fail(RT_ERR_CUDA, "out of host memory for the scene staging buffers");
         size_t fill[4] = {start[0], start[1], start[2], start[3]};
         for (uint32_t i = 0; i < n; ++i) perm[fill[cls[i]]++] = i;
         if (g.tile_culling && n > 0) {
@@ -948,28 +1102,13 @@ int rt_upload_scene(const rt_scene* sc) {
         const float worst = (ni > 0.f && std::isfinite(ni)) ? std::max(ni, 1.0f / ni) : INFINITY;   // Ni = 0 / NaN: unbounded
         if (sc->materials[i].Tr < 1.0f || !(sc->materials[i].Tr == sc->materials[i].Tr)) g.max_ni = std::max(g.max_ni, worst);
     }
-    {
-        double muv = 0.0;
-        for (uint32_t i = 0; i < n; ++i) {
-            const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i;
-            double uu = 0.0, vv = 0.0;
-            for (int k = 0; k < 3; ++k) { const double a = (double)B[k] - A[k], b = (double)C[k] - A[k]; uu += a * a; vv += b * b; }
-            const double p = std::sqrt(uu) * std::sqrt(vv);
-            muv = (p == p) ? std::max(muv, p) : INFINITY;   // NaN vertices: never claim the bound
-        }
-        g.max_uv = (float)std::min(muv * 1.0001, 1e30);
-        g.unit_normals = true;
-        for (uint32_t i = 0; i < n; ++i) {
-            const float* nn = sc->normal + 4 * i;
-            const double l2 = (double)nn[0] * nn[0] + (double)nn[1] * nn[1] + (double)nn[2] * nn[2];
-            if (!(l2 <= 1.00001)) g.unit_normals = false;
-        }
-    }
     g.scene_extent = extent;
 
+    // Stream-ordered from here on: the copies queue behind whatever frame is still in flight, nothing waits on the host
+    // (a reallocation in ensure() synchronises by itself).  The pinned staging buffers stay alive; ev_stage marks the
+    // point where the copies have left them (waited on at the top of the next upload).
     for (RtDevice& d : g.devs) {
         CU(cudaSetDevice(d.device));
-        CU(cudaStreamSynchronize(d.stream));
         d.ntri = (int)n;
         d.ntiles = cls_tiles[0] + cls_tiles[1] + cls_tiles[2];
         d.cls1 = cls_tiles[0];
@@ -990,7 +1129,9 @@ int rt_upload_scene(const rt_scene* sc) {
         CU(cudaMemcpyAsync(d.normal_mat, nm.data(), sizeof(float4) * nm.size(), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.materials, mats.data(), sizeof(rt_material) * sc->n_materials, cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.spheres, sph.data(), sizeof(float4) * sph.size(), cudaMemcpyHostToDevice, d.stream));
-        CU(cudaStreamSynchronize(d.stream));  // host staging vectors die at return
+        CU(cudaEventRecord(d.ev_stage, d.stream));
+        if (!g_stage_triv.pinned || !g_stage_nm.pinned || !g_stage_perm.pinned || !g_stage_mat.pinned || !g_stage_sph.pinned)
+            CU(cudaStreamSynchronize(d.stream));   // pageable fallback: keep the old, synchronous behaviour
     }
     g.scene_ready = true;
     g.frame_ready = false;
@@ -1067,7 +1208,7 @@ int rt_download_framebuffer_u8(uint8_t* rgb8) {
     return RT_OK;
 }
 
-int rt_trace(const rt_params* rp, int n, const float* origins, const float* dests, float* rgb, int32_t* prim_id, float* hit) {
+static int rt_trace_impl(const rt_params* rp, int n, const float* origins, const float* dests, float* rgb, int32_t* prim_id, float* hit) {
     int rc = check_ready();
     if (rc) return rc;
     if (!g.scene_ready) return fail(RT_ERR_STATE, "rt_trace before rt_upload_scene");
@@ -1079,20 +1220,23 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     RtDevice& d = g.devs[0];
     CU(cudaSetDevice(d.device));
     d.kev_kind.clear();
+    d.used_graph = false;
     float M = magnitude_bound(*rp, origins, 3 * n);
     rc = build_records(d, M, direction_bound(*rp, false, origins, dests, n)); if (rc) return rc;
     rc = ensure_chunk_state(d, (size_t)n, false, 0); if (rc) return rc;
     rc = ensure_counters(d, 1); if (rc) return rc;
-    std::vector<float4> ho(n), hd(n), ht(n, make_float4(1.f, 1.f, 1.f, 0.f)), ha(n, make_float4(0.f, 0.f, 0.f, 0.f));
+    // grow-only buffers, pinned staging: a call allocates nothing once the sizes have been seen
+    const bool want_hit = prim_id || hit;
+    rc = ensure(d.trace_in, d.cap_trace_in, (size_t)2 * n); if (rc) return rc;
+    rc = ensure(d.hit0, d.cap_hit0, (size_t)n); if (rc) return rc;
+    g_stage_rays.resize((size_t)2 * n);
+    g_stage_out.resize((size_t)2 * n);
+    if (!g_stage_rays.data() || !g_stage_out.data()) return fail(RT_ERR_CUDA, "out of host memory for the rt_trace staging buffers");
+    float4* in = g_stage_rays.data();
     for (int i = 0; i < n; ++i) {
-        ho[i] = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], 0.f);
-        hd[i] = make_float4(dests[3 * i], dests[3 * i + 1], dests[3 * i + 2], 0.f);  // w = lvl 0
+        in[2 * i] = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], 0.f);
+        in[2 * i + 1] = make_float4(dests[3 * i], dests[3 * i + 1], dests[3 * i + 2], 0.f);
     }
-    CU(cudaMemcpyAsync(d.ray_o, ho.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
-    CU(cudaMemcpyAsync(d.ray_d, hd.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
-    CU(cudaMemcpyAsync(d.thr, ht.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
-    CU(cudaMemcpyAsync(d.acc, ha.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
-    CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords, d.stream));
     d.frame_chunks = 1;
     d.pencil_used = 0;
     FrameParams P;
@@ -1101,33 +1245,81 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     P.nsamples = (uint32_t)n;
     P.nslots = (uint32_t)n;
     P.G = 1;
-    // the level-0 hit records are copied aside on the device before the bounces overwrite them
-    std::vector<float4> hh;
-    if (prim_id || hit) {
-        if (d.hit0) cudaFree(d.hit0);
-        d.hit0 = nullptr;
-        CU(cudaMalloc(&d.hit0, sizeof(float4) * (size_t)n));
+    float4* out = g_stage_out.data();
+    // one H2D copy in, the wavefront (the level-0 hit records are copied aside on the device before the bounces
+    // overwrite them), two D2H copies out -- all in stream order
+    auto body = [&]() -> int {
+        CU(cudaMemcpyAsync(d.trace_in, in, sizeof(float4) * 2 * n, cudaMemcpyHostToDevice, d.stream));
+        CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords, d.stream));
+        k_init_trace<<<(n + 255) / 256, 256, 0, d.stream>>>(d.trace_in, n, d.ray_o, d.ray_d, d.thr, d.acc);
+        CU(cudaGetLastError());
+        const int levels = run_wavefront(d, P, want_hit ? d.hit0 : nullptr);
+        if (levels < 0) return levels;
+        CU(cudaMemcpyAsync(out, d.acc, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+        if (want_hit) CU(cudaMemcpyAsync(out + n, d.hit0, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+        return RT_OK;
+    };
+    // small batches (the drop-in performRayTracing call is n = 1) replay a captured graph: copies and launches in one submission
+    const bool use_graph = g_stage_rays.pinned && g_stage_out.pinned &&
+                           (g.graph_mode > 0 || (g.graph_mode < 0 && (double)n * (double)std::max(d.ntri, 1) <= kGraphMaxTests && !getenv("RT_B200_LAUNCHLOG")));
+    if (!use_graph) {
+        rc = body(); if (rc) return rc;
+    } else {
+        std::vector<uint8_t> key;
+        KeyWriter kw{key};
+        rt_params rk = *rp;
+        memset(rk.corners, 0, sizeof(rk.corners)); rk.width = rk.height = rk.pixelfactor_x = rk.pixelfactor_y = 0; rk.want_prim_id = 0;   // ignored by rt_trace
+        kw.put(rk); kw.put(d.rec_gen); kw.put(n); kw.put(want_hit); kw.put(P.eps_r);
+        const void* ptrs[] = {d.rec, d.triv, d.normal_mat, d.materials, d.spheres, d.tile_box, d.super_box, d.always_list, d.ray_o, d.ray_d, d.thr, d.acc,
+                              d.hit, d.lit, d.q_ray, d.q_hit, d.key, d.counters, d.trace_in, d.hit0, in, out};
+        kw.put(ptrs);
+        const int cfg[] = {g.scan.rp, g.scan.j, g.scan.minb, (int)g.tile_culling, d.num_sms, (int)g.any_transparent};
+        kw.put(cfg);
+        if (!d.trace_graph || key != d.trace_key) {
+            if (d.trace_graph) { cudaGraphExecDestroy(d.trace_graph); d.trace_graph = nullptr; }
+            d.trace_key.clear();
+            CU(cudaStreamBeginCapture(d.stream, cudaStreamCaptureModeThreadLocal));
+            d.capturing = true;
+            rc = body();
+            d.capturing = false;
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(d.stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(RT_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+            const cudaError_t e2 = cudaGraphInstantiate(&d.trace_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e2 != cudaSuccess) { d.trace_graph = nullptr; return fail(RT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e2)); }
+            d.trace_key = key;
+            d.launches_in_trace_graph = (uint32_t)d.kev_kind.size();
+        }
+        d.kev_kind.assign(d.launches_in_trace_graph, -1);
+        CU(cudaGraphLaunch(d.trace_graph, d.stream));
+        d.used_graph = true;
     }
-    int levels = run_wavefront(d, P, (prim_id || hit) ? d.hit0 : nullptr);
-    if (levels < 0) return levels;
-    if (prim_id || hit) {
-        hh.resize(n);
-        CU(cudaMemcpyAsync(hh.data(), d.hit0, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
-    }
-    CU(cudaMemcpyAsync(ha.data(), d.acc, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
     CU(cudaStreamSynchronize(d.stream));
     for (int i = 0; i < n; ++i) {
-        rgb[3 * i] = ha[i].x; rgb[3 * i + 1] = ha[i].y; rgb[3 * i + 2] = ha[i].z;
-        if (prim_id) memcpy(&prim_id[i], &hh[i].w, 4);
-        if (hit) { hit[3 * i] = hh[i].x; hit[3 * i + 1] = hh[i].y; hit[3 * i + 2] = hh[i].z; }
+        rgb[3 * i] = out[i].x; rgb[3 * i + 1] = out[i].y; rgb[3 * i + 2] = out[i].z;
+        if (prim_id) memcpy(&prim_id[i], &out[n + i].w, 4);
+        if (hit) { hit[3 * i] = out[n + i].x; hit[3 * i + 1] = out[n + i].y; hit[3 * i + 2] = out[n + i].z; }
     }
     return RT_OK;
+}
+
+int rt_trace(const rt_params* rp, int n, const float* origins, const float* dests, float* rgb, int32_t* prim_id, float* hit) {
+    // the framebuffer of the last frame is not touched by rt_trace (it stays downloadable); the counters are
+    g.stats_ready = false;
+    const int rc = rt_trace_impl(rp, n, origins, dests, rgb, prim_id, hit);
+    if (rc != RT_OK)
+        for (RtDevice& d : g.devs) { d.key_dirty = true; d.capturing = false; }
+    else g.stats_ready = true;
+    return rc;
 }
 
 int rt_set_option(int option, int value) {
     if (option == RT_OPT_TILE_CULLING) { g.tile_culling = value != 0; return RT_OK; }
     if (option == RT_OPT_PENCIL) { g.pencil = value != 0; return RT_OK; }
     if (option == RT_OPT_PENCIL_ANY) { g.pencil_any = value != 0; return RT_OK; }
+    if (option == RT_OPT_GRAPH) { g.graph_mode = value < 0 ? -1 : (value != 0); return RT_OK; }
     return fail(RT_ERR_INVALID, "unknown option %d", option);
 }
 
@@ -1164,7 +1356,7 @@ int rt_get_stats(rt_stats* out) {
     int rc = check_ready();
     if (rc) return rc;
     if (!out) return fail(RT_ERR_INVALID, "out is NULL");
-    if (!g.frame_ready) return fail(RT_ERR_STATE, "rt_get_stats before rt_render");
+    if (!g.stats_ready) return fail(RT_ERR_STATE, "rt_get_stats before a completed rt_render / rt_trace");
     rc = sync_all();
     if (rc) return rc;
     rc = collect_stats();

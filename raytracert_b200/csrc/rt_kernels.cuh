@@ -1325,8 +1325,13 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ FramePara
                 const v3 rn = e_normalize(ray);
                 const float check = e_dot(rn, normal);
                 if (check < 0.0f) {
-                    const float angle = acosf(check);
-                    if (angle <= 2.0f && angle > 0.0f) {                                       // :298 grazing hack
+                    // :297-298  `angle = acosf(check); if (angle <= 2 && angle > 0)`.  CUDA's acosf is not glibc's, and a 1-ulp
+                    // difference at angle == 2 would flip reflect <-> refract for that sample.  The branch is decided without
+                    // the libm call: for check < 0, glibc's acosf(check) <= 2.0f  <=>  check >= -0.416146934f (bits 0xbed51136),
+                    // checked exhaustively over every negative float in [-1, 0) against glibc 2.39 (acosf is monotone there;
+                    // tests/test_oracle_golden.py repeats the check around the threshold); angle > 0 always holds for
+                    // check < 0, and check < -1 (rounding) gives NaN <= 2 = false on the CPU, check >= T = false here.
+                    if (check >= __uint_as_float(0xbed51136u)) {                                // :298 grazing hack
                         reflect_ray(rn, Ppos, normal, point, dest);
                         K = M.Ks; nlvl = L1 + 1; spawn = true;
                     } else {
@@ -1415,6 +1420,19 @@ __global__ void k_place_rows(const float* __restrict__ local, float* __restrict_
         const uint32_t rem = (uint32_t)(i - (size_t)y * 3u * W);
         final_fb[i] = (y % G == rank) ? local[(size_t)(y / G) * 3u * W + rem] : 0.0f;
     }
+}
+
+// rt_trace: the caller's rays arrive packed, (origin, dest) = 2 float4 per ray; sets up the per-sample wavefront state
+// the primary scan of a frame would have written (level 0, throughput 1, colour 0).
+__global__ void k_init_trace(const float4* __restrict__ rays, int n, float4* __restrict__ ray_o, float4* __restrict__ ray_d,
+                             float4* __restrict__ thr, float4* __restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = rays[2 * i], t = rays[2 * i + 1];
+    ray_o[i] = make_float4(o.x, o.y, o.z, 0.f);
+    ray_d[i] = make_float4(t.x, t.y, t.z, __int_as_float(0));
+    thr[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Measured FP32 ceiling of the device (rt_probe_fp32_peak): 16 independent packed-FMA chains per thread whose

@@ -139,9 +139,10 @@ int main(int argc, char** argv) {
 
     std::vector<char> name(scene.begin(), scene.end());
     name.push_back(0);
+    // options persist across rt_init, and tile culling wants to be set BEFORE the upload (spatially sorted tiles)
+    if (cull && rt_set_option(RT_OPT_TILE_CULLING, 1) != RT_OK) { printf("%s\n", rt_last_error()); return 1; }  // same image, fewer tests
     init(name.data());  // main.cpp:258
     if (MyMesh.triangles.empty() && spheres.empty()) { printf("no geometry loaded from %s\n", scene.c_str()); return 1; }
-    if (cull && rt_set_option(RT_OPT_TILE_CULLING, 1) != RT_OK) { printf("%s\n", rt_last_error()); return 1; }  // same image, fewer tests
     if (!lights.empty()) MyLightPositions = lights;  // replaces the start-up light at the eye
     if (!spheres.empty()) {
         for (const SphereArg& s : spheres) {

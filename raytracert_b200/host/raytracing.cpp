@@ -37,7 +37,9 @@ static bool rt_ok(int rc, const char* what) {
     return false;
 }
 
-static void fill_params(rt_params& p) {
+// false: the frame cannot be described to the library (more lights than RT_MAX_LIGHTS; the reference's 'L' key has no
+// limit, main.cpp:334-336) -- an error, never a silently different image.
+static bool fill_params(rt_params& p) {
     memset(&p, 0, sizeof(p));
     p.width = WindowSize_X; p.height = WindowSize_Y;
     p.pixelfactor_x = pixelfactorX; p.pixelfactor_y = pixelfactorY;
@@ -47,11 +49,13 @@ static void fill_params(rt_params& p) {
     for (int k = 0; k < 3; ++k) p.camera[k] = MyCameraPosition[k];
     p.n_lights = (uint32_t)MyLightPositions.size();
     if (p.n_lights > RT_MAX_LIGHTS) {
-        printf("Warning: only the first %d of %u lights are used\n", RT_MAX_LIGHTS, p.n_lights);
-        p.n_lights = RT_MAX_LIGHTS;
+        printf("error: %u lights, librt_b200 renders at most %d (RT_MAX_LIGHTS)\n", p.n_lights, RT_MAX_LIGHTS);
+        RtFailed = true;
+        return false;
     }
     for (uint32_t i = 0; i < p.n_lights; ++i)
         for (int k = 0; k < 3; ++k) p.lights[i][k] = MyLightPositions[i][k];
+    return true;
 }
 
 void calculateNormals() {  // raytracing.cpp:78-86
@@ -102,14 +106,14 @@ Material getMaterial(int index) {  // raytracing.cpp:373-376
 
 bool performRayTracingBatch(int n, const float* origins, const float* dests, float* rgb, int* prim_id) {
     rt_params p;
-    fill_params(p);
+    if (!fill_params(p)) return false;
     return rt_ok(rt_trace(&p, n, origins, dests, rgb, prim_id, nullptr), "rt_trace");
 }
 
 Vec3Df trace(const Vec3Df& origin, const Vec3Df& dest, int lvl) {  // raytracing.cpp:381-406
     // a ray that starts at level `lvl` may still spawn max_lvl - lvl continuation rays
     rt_params p;
-    fill_params(p);
+    if (!fill_params(p)) return Vec3Df(0, 0, 0);
     p.max_lvl = max_lvl - lvl;
     if (p.max_lvl < 0) { p.max_lvl = 0; p.features &= ~(RT_REFLECTION | RT_REFRACTION); }
     float rgb[3] = {0, 0, 0};
@@ -123,7 +127,7 @@ Vec3Df performRayTracing(const Vec3Df& origin, const Vec3Df& dest) {  // raytrac
 
 bool renderFrame(const Vec3Df origin[4], const Vec3Df dest[4], float* rgb) {
     rt_params p;
-    fill_params(p);
+    if (!fill_params(p)) return false;
     // corner order of main.cpp:355-358: (0,0) (0,H-1) (W-1,0) (W-1,H-1)
     for (int c = 0; c < 4; ++c)
         for (int k = 0; k < 3; ++k) { p.corners[c * 6 + k] = origin[c][k]; p.corners[c * 6 + 3 + k] = dest[c][k]; }

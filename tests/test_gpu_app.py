@@ -67,3 +67,46 @@ def test_app_light_and_sample_keys(built, tmp_path, port):
     rgb, _, _ = port.render(cam.corners, 48, 40, 2, 2)
     d = np.abs(img.astype(int) - port.quantise(rgb).astype(int))
     assert d.max() <= 1
+
+
+def _device_count():
+    r = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True)
+    return sum(1 for l in r.stdout.splitlines() if l.startswith("GPU ")) if r.returncode == 0 else 0
+
+
+def test_single_process_multi_gpu_app(built, tmp_path):
+    """rt_init(n) -- one process drives n GPUs (ncclCommInitAll), what `rt_main --gpus N` and INTEGRATION.md use: rows
+    interleaved over the devices, one all-gather, de-interleave.  The PPM must be byte-identical to the --gpus 1 one.
+    Skips on a box with one GPU (the driver's SCALE run and tools/gpu scripts exercise it at 2/4/8)."""
+    n = _device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    args = ["--size", "96x70", "--pf", "2", "--lvl", "6", "--eye", "3.4,3.0,4.6", "--center", "0.4,0.2,0.2", "--light", "3,5,4"]
+    one, _ = run_app(tmp_path, *args, "--gpus", "1")
+    for g in sorted({2, min(n, 4), n}):
+        many, _ = run_app(tmp_path, *args, "--gpus", str(g))
+        assert np.array_equal(one, many), f"--gpus {g}: {int(np.count_nonzero(one != many))} bytes differ"
+
+
+def test_single_process_multi_gpu_ids(built, tmp_path):
+    """The same through the C ABI from Python in a fresh process: Renderer(n) against Renderer(1), float framebuffer bits
+    and per-sample ids (rt_download_framebuffer gathers the ids of every device in single-process mode)."""
+    n = _device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from raytracert_b200 import binding, host, scenes\n"
+        "s = scenes.balls_standin(grid=48, slices=24, stacks=12)\n"
+        "cam = host.Camera(120, 90, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0))\n"
+        "prm = binding.make_params(cam.corners, 120, 90, 2, 2, 3, 63, cam.eye, [(2.5, 4.0, 3.0)], want_prim_id=True)\n"
+        "out = {}\n"
+        f"for g in (1, 2, {n}):\n"
+        "    R = binding.Renderer(g); R.upload_scene(s); R.render(prm); out[g] = R.download(want_prim_id=True); st = R.stats(); R.shutdown()\n"
+        "    assert st['n_gpus'] == g\n"
+        "    assert np.array_equal(out[1][1], out[g][1]), g\n"
+        "    assert np.array_equal(out[1][0].view(np.uint32), out[g][0].view(np.uint32)), g\n"
+        "print('OK')\n")
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

@@ -570,3 +570,179 @@ def test_balls_with_sphere_primitives(gpu, port):
     assert np.array_equal(prim, prim_o)
     assert np.abs(rgb - rgb_o).max() <= RGB_TOL
     assert (st["primary_rays"], st["shadow_rays"], st["bounce_rays"]) == counts
+
+
+def test_pencil_without_the_clause_free_proof(gpu, port):
+    """RT_OPT_PENCIL_ANY (default on): scenes of LARGE triangles (cube, dodge, shadow_test: no scene-level clause-free
+    proof) still use the pencil filter; triangles whose plane passes through / next to the common point get "always
+    candidate" records.  rt_stats.variant bit 3 must say so, and ids, framebuffer bits and ray counts must equal the
+    option-off frame (generic kernels) and the reference fixture."""
+    from raytracert_b200 import binding
+    try:
+        for name in ("cube_default_64", "cube_oblique_96_pf2", "dodge_48x27", "dodge_32x18_pf2_lvl2", "shadow_test_64_pf2", "shadow_test_2lights_lvl3",
+                     "room_64_pf2_lvl4", "quirks_72_pf2"):
+            c = load_case(name)
+            s = load_scene(c["scene"])
+            gpu.set_option(binding.RT_OPT_PENCIL_ANY, 0)
+            rgb0, prim0 = gpu_render(gpu, s, c)
+            st0 = gpu.stats()
+            assert not (st0["variant"] & 8), name
+            gpu.set_option(binding.RT_OPT_PENCIL_ANY, 1)
+            rgb1, prim1 = gpu_render(gpu, s, c)
+            st1 = gpu.stats()
+            if not (st0["variant"] & 1):          # no clause-free proof: every pencil launch of this frame is a "no premise" one
+                assert (st1["variant"] & 8) == 8 * bool(st1["variant"] & 6), (name, st1["variant"])
+            assert np.array_equal(prim0, prim1) and np.array_equal(prim1, c["sample_prim"]), name
+            assert np.array_equal(bits(rgb0), bits(rgb1)), name
+            for k in ("primary_rays", "shadow_rays", "bounce_rays"):
+                assert st0[k] == st1[k], (name, k)
+        # the two reference scenes the option exists for must actually take the pencil kernels
+        for name in ("cube_oblique_96_pf2", "dodge_48x27"):
+            c = load_case(name)
+            gpu_render(gpu, load_scene(c["scene"]), c)
+            v = gpu.stats()["variant"]
+            assert (v & 8) and (v & 2), (name, v)
+    finally:
+        gpu.set_option(binding.RT_OPT_PENCIL_ANY, 1)
+
+
+def test_small_frames_replay_a_graph(gpu, port):
+    """RT_OPT_GRAPH (auto): a frame whose launches are tiny is captured once and replayed (rt_stats.variant bit 4); the image,
+    ids and ray counters are those of the directly launched frame; a changed camera / light / option re-captures."""
+    from raytracert_b200 import binding, host
+    s = load_scene("cube")
+    try:
+        for cam, lights in ((host.Camera(96, 80), None), (host.Camera(96, 80, (2.6, 2.4, 3.0), (.5, .5, .5)), [(3.0, 5.0, 4.0), (-2.0, 1.0, 4.0)])):
+            lights = [cam.eye] if lights is None else lights
+            c = dict(corners=cam.corners, W=96, H=80, pfx=2, pfy=1, max_lvl=10, features=63, eye=cam.eye, lights=lights)
+            gpu.set_option(binding.RT_OPT_GRAPH, 0)
+            rgb0, prim0 = gpu_render(gpu, s, c)
+            st0 = gpu.stats()
+            assert not (st0["variant"] & 16)
+            gpu.set_option(binding.RT_OPT_GRAPH, -1)
+            for rep in range(3):                 # capture, then two replays
+                rgb1, prim1 = gpu_render(gpu, s, c) if rep == 0 else (gpu.render(gpu.params), gpu.download(want_prim_id=True))[1]
+                st1 = gpu.stats()
+                assert st1["variant"] & 16
+                assert np.array_equal(prim0, prim1) and np.array_equal(bits(rgb0), bits(rgb1)), rep
+                for k in ("primary_rays", "shadow_rays", "bounce_rays", "n_launches", "n_levels"):
+                    assert st0[k] == st1[k], (rep, k)
+            port.set_scene(s); port.configure(cam.eye, lights, 63, 10)
+            rgb_o, _, prim_o = port.render(cam.corners, 96, 80, 2, 1, want_samples=True)
+            assert np.array_equal(prim1, prim_o) and np.abs(rgb1 - rgb_o).max() <= RGB_TOL
+        # a large frame is never captured in auto mode
+        from raytracert_b200 import scenes
+        big = scenes.balls_standin()
+        cam = host.Camera(400, 300, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0))
+        gpu_render(gpu, big, dict(corners=cam.corners, W=400, H=300, pfx=2, pfy=2, max_lvl=3, features=63, eye=cam.eye, lights=[(2.5, 4.0, 3.0)]))
+        assert not (gpu.stats()["variant"] & 16)
+    finally:
+        gpu.set_option(binding.RT_OPT_GRAPH, -1)
+
+
+def test_trace_single_rays_replay_a_graph(gpu):
+    """performRayTracing(origin, dest) is rt_trace with n = 1: repeated calls replay one captured graph (copies + wavefront)
+    and must return what the batch call returns for the same rays; a frame rendered in between stays downloadable."""
+    from raytracert_b200 import binding, host
+    z = np.load(GOLDEN + "/trace_shadow_test.npz")
+    s = load_scene("shadow_test")
+    gpu.upload_scene(s)
+    prm = binding.make_params([0] * 24, 1, 1, 1, 1, 10, 63, z["eye"], [z["eye"]])
+    rgb_b, prim_b, hit_b = gpu.trace(prm, z["origins"], z["dests"])
+    assert np.array_equal(prim_b, z["prim"])
+    cam = host.Camera(40, 30, (1, 5, 7), (1, 1.2, .7))
+    fp = binding.make_params(cam.corners, 40, 30, 1, 1, 3, 63, cam.eye, [cam.eye])
+    gpu.render(fp)
+    frame = gpu.download()
+    for i in range(0, 60):
+        rgb, prim, hit = gpu.trace(prm, z["origins"][i:i + 1], z["dests"][i:i + 1])
+        assert gpu.stats()["variant"] & 16
+        assert prim[0] == prim_b[i] and np.array_equal(bits(hit[0]), bits(hit_b[i]))
+        ok = np.isfinite(rgb_b[i])
+        assert np.array_equal(bits(rgb[0][ok]), bits(rgb_b[i][ok]))
+    gpu.params = fp
+    assert np.array_equal(bits(gpu.download()), bits(frame))      # rt_trace leaves the last framebuffer alone
+
+
+def test_records_follow_the_request(gpu, port):
+    """One rt_trace call with a very long ray makes the library rebuild its filter records with the grazing clause; the next
+    frame must get the clause-free records (and the pencil launches) back (the bounds used to only grow)."""
+    from raytracert_b200 import binding, host, scenes
+    s = scenes.balls_standin(grid=48, slices=24, stacks=12)
+    cam = host.Camera(64, 48, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0))
+    c = dict(corners=cam.corners, W=64, H=48, pfx=1, pfy=1, max_lvl=2, features=63, eye=cam.eye, lights=[(2.5, 4.0, 3.0)])
+    rgb0, prim0 = gpu_render(gpu, s, c)
+    v0 = gpu.stats()["variant"]
+    assert v0 & 1
+    prm = binding.make_params([0] * 24, 1, 1, 1, 1, 2, 63, cam.eye, [(2.5, 4.0, 3.0)])
+    o = np.array([[0.0, 900.0, 0.0]], np.float32); d = np.array([[0.0, 0.5, 0.0]], np.float32)
+    port.set_scene(s); port.configure(cam.eye, [(2.5, 4.0, 3.0)], 63, 2)
+    _, prim_o, _ = port.trace(o, d)
+    _, prim_t, _ = gpu.trace(prm, o, d)
+    assert np.array_equal(prim_t, prim_o)
+    assert not (gpu.stats()["variant"] & 1)          # the long ray needs the clause
+    gpu.render(binding.make_params(c["corners"], 64, 48, 1, 1, 2, 63, c["eye"], c["lights"], want_prim_id=True))
+    rgb1, prim1 = gpu.download(want_prim_id=True)
+    assert gpu.stats()["variant"] == v0
+    assert np.array_equal(prim0, prim1) and np.array_equal(bits(rgb0), bits(rgb1))
+
+
+def test_too_many_lights_is_an_error(gpu):
+    from raytracert_b200 import binding
+    with pytest.raises(ValueError):
+        binding.make_params([0] * 24, 4, 4, 1, 1, 1, 63, (0, 0, 4), [(0, 0, i) for i in range(binding.RT_MAX_LIGHTS + 1)])
+    p = binding.make_params([0] * 24, 4, 4, 1, 1, 1, 63, (0, 0, 4), [(0, 0, 4)])
+    p.n_lights = binding.RT_MAX_LIGHTS + 1
+    gpu.upload_scene(load_scene("cube"))
+    with pytest.raises(binding.RtError) as e:
+        gpu.render(p)
+    assert e.value.code == -2
+
+
+PIN_DIR = GOLDEN + "/pins"
+
+
+def _pin_check(gpu, workload):
+    """Renders a whole bench frame and compares it with the pin the UNMODIFIED reference produced for it
+    (tools/make_headline_pin.py): per-sample primary ids through their per-row CRCs (and sample by sample when the pin
+    carries the ids), u8 rows within 1/255."""
+    import zlib, os, sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    from raytracert_b200 import binding, host
+    path = os.path.join(PIN_DIR, workload + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} has not been generated")
+    z = np.load(path)
+    scene, W, H, pf, lvl, eye, center, lights, _ = bench.workload(workload)
+    cam = host.Camera(W, H, eye, center)
+    lights = [cam.eye] if lights is None else lights
+    assert (W, H, pf, lvl) == (int(z["W"]), int(z["H"]), int(z["pf"]), int(z["max_lvl"])) and np.array_equal(cam.corners, z["corners"])
+    gpu.upload_scene(scene)
+    gpu.render(binding.make_params(cam.corners, W, H, pf, pf, lvl, 63, cam.eye, lights, want_prim_id=True))
+    rgb, prim = gpu.download(want_prim_id=True)
+    u8 = gpu.download_u8()
+    rows = z["rows"]
+    prim = prim.reshape(H, W * pf * pf)
+    crc = np.array([zlib.crc32(prim[y].astype("<i4").tobytes()) for y in rows], np.uint32)
+    bad_rows = np.flatnonzero(crc != z["id_crc"])
+    msg = ""
+    if len(bad_rows) and "ids_z" in z.files:
+        ids = np.frombuffer(zlib.decompress(z["ids_z"].tobytes()), "<i4").reshape(len(rows), -1)
+        msg = f"{int(np.count_nonzero(ids != prim[rows]))} sample ids differ"
+    assert len(bad_rows) == 0, f"rows {rows[bad_rows][:10]} ... ({len(bad_rows)} rows) {msg}"
+    d = np.abs(u8[rows].astype(int) - z["u8"].astype(int))
+    assert d.max() <= 1, f"{int(np.count_nonzero(d > 1))} u8 values off by more than 1"
+    assert np.mean(np.any(d > 0, axis=2)) <= 0.01
+    return len(rows)
+
+
+def test_headline_frame_pinned_on_every_row(gpu):
+    """The 800x800x16 headline frame against the reference's own frame: all 800 rows, all 10.24 M sample ids."""
+    assert _pin_check(gpu, "balls") == 800
+
+
+def test_C3_frame_pinned_on_a_row_subset(gpu):
+    """C3 (dodgeColorTest 1920x1080x16): 64 rows spread over the frame against the reference's own rows."""
+    assert _pin_check(gpu, "dodge") >= 64

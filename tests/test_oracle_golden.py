@@ -90,3 +90,20 @@ def test_spheres_extension_is_consistent(port):
     n_sphere = np.count_nonzero(prim == s.n_triangles)
     # projected radius ~ 0.35 / 3.9 * (40 / (2 tan 25deg)) ~ 3.85 px -> ~46 px
     assert 30 <= n_sphere <= 64
+
+
+def test_refraction_angle_threshold_matches_libm():
+    """k_shade decides the reference's `acosf(check) <= 2` branch (raytracing.cpp:297-298) as `check >= T` with
+    T = bits 0xbed51136, so that CUDA's acosf (which is not glibc's) can never flip reflect <-> refract.  Check T against
+    this machine's libm (what the oracle and the reference build call): a window of 2e5 floats around T, a sweep of
+    the whole range [-1, 0) in coarse steps, and the out-of-domain side."""
+    import ctypes as C
+    m = C.CDLL("libm.so.6")
+    m.acosf.restype = C.c_float; m.acosf.argtypes = [C.c_float]
+    T = 0xbed51136
+    def f(bits):
+        return np.array([bits], np.uint32).view(np.float32)[0]
+    for b in list(range(T - 100000, T + 100000, 7)) + list(range(T - 64, T + 64)) + list(range(0x80000001, 0xbf800000, 1 << 14)):
+        x = f(b)
+        assert (m.acosf(x) <= 2.0) == (x >= f(T)), hex(b)
+    assert not (m.acosf(np.float32(-1.0000001)) <= 2.0)      # NaN: refraction branch on both sides
