@@ -128,6 +128,12 @@ def cpu_oracle():
     return pyoracle.PortOracle(), "port"
 
 
+def lattice_pitch(W, H):
+    """One fixed pitch per workload for every CPU timing of it (cpu_baseline at any N, --impl reference): about 1600
+    pixels of the frame (every 20th pixel of every 20th row for 800x800)."""
+    return max(1, int(round((W * H / 1600.0) ** 0.5)))
+
+
 def lattice_pixels(W, H, k):
     return len(range(k // 2, H, k)) * len(range(k // 2, W, k))
 
@@ -151,12 +157,28 @@ def cpu_sample(scene, cam, pf, lvl, lights, k, threads, count=True):
     return dt, sum(P.ray_counts()), lattice_pixels(cam.W, cam.H, k), kind
 
 
-def lattice_for_seconds(scene, cam, pf, lvl, lights, threads, seconds):
-    """Pick the lattice pitch k so that one timed sample takes about `seconds` (calibrated on a coarse lattice)."""
-    k0 = max(1, int(round((cam.W * cam.H / 512.0) ** 0.5)))
-    t0, _, n0, _ = cpu_sample(scene, cam, pf, lvl, lights, k0, threads, count=False)
-    target = max(64.0, n0 * seconds / max(t0, 1e-4))
-    return max(1, int(np.ceil((cam.W * cam.H / target) ** 0.5)))
+def config_for(name, desc, scene, W, H, pf, lvl, n_lights, n_gpus):
+    """`config` of the JSON line -- static description of the workload only, identical in both arms."""
+    return {"workload": desc, "name": name, "triangles": int(scene.n_triangles), "width": W, "height": H, "rays_per_pixel": pf * pf,
+            "max_lvl": lvl, "lights": n_lights, "features": "ambient+diffuse+specular+reflection+shadows+refraction (all toggles on)",
+            "parallelism": f"rows interleaved over {n_gpus} GPU(s), scene replicated"}
+
+
+def cpu_baseline_block(scene, cam, pf, lvl, lights, threads):
+    """The reference's CPU path on this box: all host threads on the fixed lattice, plus a 1-thread figure on a 16x
+    sparser lattice of the same frame (SURVEY 8d asks for both)."""
+    W, H = cam.W, cam.H
+    k = lattice_pitch(W, H)
+    dt, r, npix, kind = cpu_sample(scene, cam, pf, lvl, lights, k, threads)
+    k1 = 4 * k
+    dt1, r1, npix1, _ = cpu_sample(scene, cam, pf, lvl, lights, k1, 1)
+    what = "the reference's own raytracing.cpp/mesh.cpp (-O2 -ffp-contract=off), OpenMP over pixels in the harness" if kind == "reference" \
+        else "plain-C port of the reference (oracle/rt_oracle.c), OpenMP over pixels"
+    return {"value": r / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": kind,
+            "sample": f"every {k}th pixel of every {k}th row of the same frame ({npix} of {W * H} pixels, all {pf * pf} sub-samples each), {dt:.1f} s; {what}",
+            "ms_per_frame_extrapolated": dt * 1e3 * W * H / npix,
+            "one_thread": {"value": r1 / dt1 / 1e6, "unit": "Mrays/s", "cores": 1,
+                           "sample": f"every {k1}th pixel of every {k1}th row ({npix1} pixels), {dt1:.1f} s"}}
 
 
 def run_reference(args, name):
@@ -169,8 +191,7 @@ def run_reference(args, name):
     cam = host.Camera(W, H, eye, center)
     lights = [cam.eye] if lights is None else lights
     threads = os.cpu_count() or 1
-    # each step costs a timed sample + the untimed ray count: keep the whole run near 2.5 minutes
-    k = lattice_for_seconds(scene, cam, pf, lvl, lights, threads, 150.0 / (args.steps + args.warmup + 1))
+    k = lattice_pitch(W, H)   # the same lattice as the product arm's cpu_baseline
     times, rays, npix, kind = [], 0, 0, "port"
     for i in range(args.warmup + args.steps):
         dt, r, npix, kind = cpu_sample(scene, cam, pf, lvl, lights, k, threads, count=(i == 0))   # same lattice, same rays every step
@@ -181,14 +202,73 @@ def run_reference(args, name):
     mrays = rays / sec / 1e6
     sample = (f"every {k}th pixel of every {k}th row of the same frame per step ({npix} of {W * H} pixels, all {pf * pf} sub-samples each), "
               f"{threads} OpenMP threads over pixels in the harness; ms_per_step is the sample's time scaled by {W * H}/{npix}")
+    k1 = 4 * k
+    dt1, r1, npix1, _ = cpu_sample(scene, cam, pf, lvl, lights, k1, 1)
     line = {"impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * W * H / npix,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "name": name},
-            "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
+            "config": config_for(name, desc, scene, W, H, pf, lvl, len(lights), args.gpus),
+            "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample,
+                             "one_thread": {"value": r1 / dt1 / 1e6, "unit": "Mrays/s", "cores": 1,
+                                            "sample": f"every {k1}th pixel of every {k1}th row ({npix1} pixels), {dt1:.1f} s"}},
             "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def pin_path(name):
+    return os.path.join(ROOT, "tests", "golden", "pins", name + ".npz")
+
+
+def parity_block(R, name, prm_ids, rank, world, single_process):
+    """Compares one more frame (rendered after the timed region, with per-sample ids kept) with the frame the UNMODIFIED
+    reference produced for this workload (tests/golden/pins/<name>.npz, tools/make_headline_pin.py).  Ids: every rank
+    checks its own rows (per-row CRC, and sample by sample), the counts are summed over the ranks.  u8 image: rank 0, on
+    the frame as the all-gather + de-interleave assembled it.  Returns the block (rank 0) or None."""
+    import zlib
+    path = pin_path(name)
+    if not os.path.exists(path):
+        return {"against": None, "note": f"no pin for workload {name} (tests/golden/pins)"}
+    z = np.load(path)
+    rows = z["rows"].astype(np.int64)
+    H, W = int(z["H"]), int(z["W"])
+    R.render(prm_ids)
+    rgb, prim = R.download(want_prim_id=True)
+    prim = prim.reshape(H, -1)
+    mine = rows if (single_process or world == 1) else rows[rows % world == rank]
+    idx = {int(y): i for i, y in enumerate(rows)}
+    ids = np.frombuffer(zlib.decompress(z["ids_z"].tobytes()), "<i4").reshape(len(rows), -1) if "ids_z" in z.files else None
+    bad_rows = bad_ids = 0
+    for y in mine:
+        if np.uint32(zlib.crc32(prim[y].astype("<i4").tobytes())) != z["id_crc"][idx[int(y)]]:
+            bad_rows += 1
+            if ids is not None:
+                bad_ids += int(np.count_nonzero(ids[idx[int(y)]] != prim[y]))
+    counts = np.array([len(mine), bad_rows, bad_ids], np.float64)
+    if world > 1 and not single_process:
+        import torch
+        import torch.distributed as td
+        t = torch.tensor(counts, dtype=torch.float64, device="cuda" if td.get_backend() == "nccl" else "cpu")
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+        counts = t.cpu().numpy()
+    if rank != 0:
+        return None
+    u8 = R.download_u8()
+    d = np.abs(u8[rows].astype(np.int32) - z["u8"].astype(np.int32))
+    return {"against": f"tests/golden/pins/{name}.npz -- the unmodified reference (oracle/_ref) on the whole frame",
+            "rows_checked": int(counts[0]), "rows_in_frame": H, "id_rows_mismatching": int(counts[1]), "id_mismatches": int(counts[2]) if ids is not None else None,
+            "samples_checked": int(counts[0]) * prim.shape[1], "u8_off_by_more_than_1": int(np.count_nonzero(d > 1)),
+            "u8_pixels_differing_frac": float(np.mean(np.any(d > 0, axis=2))), "float_rgb_max_abs_diff_note": "colour differs from the reference only through CUDA powf vs glibc powf (<= 2e-7)",
+            "n_gpus": world}
+
+
+def kernel_counters(name):
+    """Per-kernel ncu counters of this workload (profiles/r2_kernel_counters.json, written from ncu captures by
+    tools/ncu_counters.py): measured, but NOT in this run."""
+    p = os.path.join(ROOT, "profiles", "r2_kernel_counters.json")
+    if not os.path.exists(p):
+        return {}, None
+    return json.load(open(p)).get(name, {}), "profiles/r2_kernel_counters.json"
 
 
 def main():
@@ -198,9 +278,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="balls")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive all --gpus N devices from THIS process (rt_init(N), ncclCommInitAll: the C++ drop-in's mode) instead of one torchrun rank per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run comparison with the reference's pinned frame")
     ap.add_argument("--no-accelerated", action="store_true", help="skip the separately reported tile-culling frames (profiling runs)")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     args = ap.parse_args()
     guard_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -209,38 +291,59 @@ def main():
 
     import torch
     from raytracert_b200 import binding, dist, host
-    R, rank, world = dist.make_renderer()
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if world == 1 and args.gpus > 1:
-        raise SystemExit("for --gpus N > 1 launch with torchrun (one rank per GPU)")
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    single = bool(args.single_process)
+    if single:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            raise SystemExit("--single-process is not a torchrun mode")
+        R, rank, world = binding.Renderer(args.gpus), 0, args.gpus
+    else:
+        R, rank, world = dist.make_renderer()
+        if world != args.gpus and world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("for --gpus N > 1 launch with torchrun (one rank per GPU), or pass --single-process")
+    local = 0 if single else int(os.environ.get("LOCAL_RANK", "0"))
+    my_devices = list(range(world)) if single else [local]
     torch.cuda.set_device(local)
     scene, W, H, pf, lvl, eye, center, lights, desc = workload(args.workload)
     cam = host.Camera(W, H, eye, center)
     lights = [cam.eye] if lights is None else lights
     R.upload_scene(scene)
     prm = binding.make_params(cam.corners, W, H, pf, pf, lvl, binding.RT_ALL_FEATURES, cam.eye, lights)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
+    flush = [torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{i}") for i in my_devices]   # > 126 MB L2, one per driven device
+    multi_rank = world > 1 and not single
 
     def barrier():
-        if world > 1:
+        if multi_rank:
             import torch.distributed as td
             td.barrier()
-        torch.cuda.synchronize()
+        for i in my_devices:
+            torch.cuda.synchronize(i)
         R.sync()
+
+    e2e_parts = {"upload_ms": [], "render_ms": [], "download_ms": []}
 
     def frame_ms(e2e=False):
         """One timed frame.  Device-resident: events on the library's stream around rt_render.  e2e: host buffers in,
         host framebuffer out, through the public calls (rt_upload_scene + rt_render + rt_download_framebuffer)."""
-        flush.zero_(); torch.cuda.synchronize()       # L2 flush between timed iterations (outside the timed region)
+        for f in flush:                               # L2 flush between timed iterations (outside the timed region)
+            f.zero_()
+        for i in my_devices:
+            torch.cuda.synchronize(i)
         if not e2e:
             R.event_record(0); R.render(prm, sync=False); R.event_record(1); R.sync()
             return R.event_elapsed_ms(0, 1)
         barrier()                                     # ranks start the step together (the all-gather would otherwise absorb their skew)
-        t = time.perf_counter()
-        R.upload_scene(scene); R.render(prm); R.download_into(fb_host)
-        return (time.perf_counter() - t) * 1e3
+        t0 = time.perf_counter()
+        R.upload_scene(scene)
+        t1 = time.perf_counter()
+        R.render(prm)
+        t2 = time.perf_counter()
+        R.download_into(fb_host)
+        t3 = time.perf_counter()
+        for k, v in zip(("upload_ms", "render_ms", "download_ms"), (t1 - t0, t2 - t1, t3 - t2)):
+            e2e_parts[k].append(v * 1e3)
+        return (t3 - t0) * 1e3
 
     fb_pinned = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory()   # the D2H target of the e2e steps is pinned host memory
     fb_host = fb_pinned.numpy()
@@ -257,6 +360,9 @@ def main():
     st = R.stats()
     fp32_probe = R.probe_fp32_peak()   # measured packed-FMA ceiling of this device, for context beside the nominal peak
     # end-to-end through the public API with host buffers (scene H2D + frame + framebuffer D2H every step)
+    frame_ms(e2e=True)                 # one untimed e2e step (first use of the staging buffers)
+    for v in e2e_parts.values():
+        v.clear()
     e2e_steps = [frame_ms(e2e=True) for _ in range(max(3, min(args.steps, 5)))]
     fb_brute = fb_host.copy()
     # opt-in extra (not the contract path): conservative tile culling, same image bit for bit, reported separately
@@ -273,17 +379,23 @@ def main():
         cull_identical = bool(np.array_equal(fb_host.view(np.uint32), fb_brute.view(np.uint32)))
         R.set_option(binding.RT_OPT_TILE_CULLING, 0)
         R.upload_scene(scene)
+    # parity against the reference's own frame, at every N (after the timed region; ids kept for this one frame)
+    parity = None
+    if not args.no_parity:
+        prm_ids = binding.make_params(cam.corners, W, H, pf, pf, lvl, binding.RT_ALL_FEATURES, cam.eye, lights, want_prim_id=True)
+        parity = parity_block(R, args.workload, prm_ids, rank, world, single)
 
     ms_dev = float(np.mean(per_step))
     ms_e2e = float(np.mean(e2e_steps))
     ms_cull = float(np.mean(cull_steps))
+    parts = [float(np.mean(e2e_parts[k])) for k in ("upload_ms", "render_ms", "download_ms")]
     counts = np.array([st["primary_rays"], st["shadow_rays"], st["bounce_rays"], st["exact_evals"]], np.float64)
     kinds = np.array([st["ms_trace"], st["ms_shadow"], st["ms_shade"], st["ms_resolve"], st["ms_gather"], st["ms_trace_primary"]], np.float64)
-    if world > 1:
+    if multi_rank:
         import torch.distributed as td
-        t = torch.tensor([ms_dev, ms_e2e, ms_cull] + list(kinds), dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([ms_dev, ms_e2e, ms_cull] + parts + list(kinds), dtype=torch.float64, device=f"cuda:{local}")
         td.all_reduce(t, op=td.ReduceOp.MAX)
-        ms_dev, ms_e2e, ms_cull, kinds = float(t[0]), float(t[1]), float(t[2]), t[3:].cpu().numpy()
+        ms_dev, ms_e2e, ms_cull, parts, kinds = float(t[0]), float(t[1]), float(t[2]), [float(x) for x in t[3:6]], t[6:].cpu().numpy()
         c = torch.tensor(counts, dtype=torch.float64, device=f"cuda:{local}")
         td.all_reduce(c, op=td.ReduceOp.SUM)
         counts = c.cpu().numpy()
@@ -294,6 +406,7 @@ def main():
         peaks, peak_src = measured_peaks()
         sms = torch.cuda.get_device_properties(local).multi_processor_count
         fp32_peak = sms * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12           # TFLOP/s per GPU at max clock
+        ncu, ncu_src = kernel_counters(args.workload)
         # Scan kernels of the last frame.  Algorithmic flops = 42 per (ray, triangle) test (the minimal ray-dependent
         # form of rayIntersectTriangle for a GENERAL ray) x rays x triangles; every kernel performs every test of the reference.
         #   k_trace generic  : bounce levels (and the primary level when the pencil filter does not apply): 27 executed flop / test
@@ -304,60 +417,60 @@ def main():
         ms_primary = float(kinds[5])
         ms_bounce = float(kinds[0] - kinds[5])
 
-        def kernel_row(name, rays_gpu, ms, executed):
+        def kernel_row(key, name, rays_gpu, ms, executed):
             a = FLOPS_PER_TEST * rays_gpu * ntri / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-            return {"kernel": name, "ms": ms, "tests_per_s": rays_gpu * ntri / (ms * 1e-3) if ms > 0 else 0.0, "achieved": a, "frac": a / fp32_peak,
-                    "executed_flops_per_test": executed, "executed_frac": a * executed / FLOPS_PER_TEST / fp32_peak}
-        rows = [kernel_row("k_trace primary (%s filter)" % ("pencil" if pencil_primary else "generic"), counts[0] / world, ms_primary, 12 if pencil_primary else 27),
-                kernel_row("k_trace bounce levels (generic filter)", counts[2] / world, ms_bounce, 27),
-                kernel_row("k_shadow any-hit (%s filter)" % ("pencil" if pencil_shadow else "generic"), counts[1] / world, float(kinds[1]), 12 if pencil_shadow else 27)]
+            m = ncu.get(key, {})
+            return {"kernel": name, "ms": ms, "tests_per_s": rays_gpu * ntri / (ms * 1e-3) if ms > 0 else 0.0, "achieved": a,
+                    "algorithmic_ratio": a / fp32_peak,   # algorithmic flops / peak: NOT a pipe utilisation (the pencil kernels do a test in 12 flop; any-hit rays stop early)
+                    "hot_loop_flops_per_test": executed, "executed_frac_from_hot_loop": a * executed / FLOPS_PER_TEST / fp32_peak,
+                    "fma_pipe_active_ncu": m.get("fma_pipe_cycles_active_pct"), "issue_active_ncu": m.get("issue_active_pct"),
+                    "dram_bytes_ncu": m.get("dram_bytes"), "ncu_launch": m.get("launch")}
+        rows = [kernel_row("primary", "k_trace primary (%s filter)" % ("pencil" if pencil_primary else "generic"), counts[0] / world, ms_primary, 12 if pencil_primary else 27),
+                kernel_row("bounce", "k_trace bounce levels (generic filter)", counts[2] / world, ms_bounce, 27),
+                kernel_row("shadow", "k_shadow any-hit (%s filter)" % ("pencil" if pencil_shadow else "generic"), counts[1] / world, float(kinds[1]), 12 if pencil_shadow else 27)]
         dom = max(rows, key=lambda r: r["ms"])
         ach = dom["achieved"]
         roof = {"bound": "fp32", "kernel": dom["kernel"] + " -- the launch kind with the largest share of the frame", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach / fp32_peak,
+                # executed at the pipe: the hot loop's instruction mix x the measured test rate, and ncu's own FMA-pipe counter
+                "executed_frac": dom["executed_frac_from_hot_loop"], "fma_pipe_active_ncu": dom["fma_pipe_active_ncu"],
                 # rt_probe_fp32_peak(): what a register-resident FFMA/FFMA2 loop sustains on this device right now (TFLOP/s)
                 "peak_fma_loop_measured": fp32_probe, "frac_of_measured_fma_loop": ach / fp32_probe if fp32_probe > 0 else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of that kind (level-1 bounce scan of chunk 0,
-                # 4.34 M rays, 134.6 ms), one `ncu --set full` capture of this command (profiles/r1h_k_trace_bounce_full.txt);
-                # only meaningful for the default workload
-                "traffic": 182.7e6 if args.workload == "balls" and world == 1 else None, "traffic_unit": "B per launch (level-1 bounce scan, chunk 0)",
-                "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of that kind, from an ncu capture of this workload
+                # (not measured in this run); null when there is no capture for the workload / GPU count
+                "traffic": dom["dram_bytes_ncu"] if world == 1 else None, "traffic_source": ncu_src, "traffic_launch": dom["ncu_launch"],
+                "peak_source": f"{sms} SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock; no FP32 entry there, so the nominal figure at the measured max clock)",
                 "frac_at_measured_clock": (ach / (fp32_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])) if clocks.get("sm_mhz") else None,
-                "executed_flops_per_test": dom["executed_flops_per_test"], "executed_frac": dom["executed_frac"],
-                "frame_achieved": FLOPS_PER_TEST * rays * ntri / world / (ms_dev * 1e-3) / 1e12,
                 "by_kernel": rows,
-                "note": "achieved/frac count 42 algorithmic flop per test (general-ray form, SURVEY 8d). The pencil kernels do the same tests "
-                        "with 12 executed flop in the hot loop (rays through a common point need no origin arithmetic; the distance clause runs in the cold path), so their algorithmic rate -- and "
-                        "frame_achieved -- can exceed the FP32 peak; executed_frac is the FMA-pipe-level figure for every row.",
+                "note": "achieved/frac count 42 algorithmic flop per test (general-ray form, SURVEY 8d) for the dominant launch kind. by_kernel[].algorithmic_ratio is the same "
+                        "quotient per kind and is not a utilisation: the pencil kernels do a test in 12 executed flop (rays through a common point need no origin arithmetic), "
+                        "any-hit rays stop at their first occluder. The pipe-level figures are executed_frac_from_hot_loop and fma_pipe_active_ncu.",
                 "ms_by_kernel": dict(zip(["k_trace", "k_shadow", "k_shade", "k_resolve", "gather", "k_trace_primary"], [float(x) for x in kinds]))}
         line = {"metric": METRIC, "value": rays / ms_dev / 1e3, "unit": "Mrays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "name": args.workload, "triangles": ntri, "rays_per_frame": rays,
-                           "primary": counts[0], "shadow": counts[1], "bounce": counts[2], "exact_reevaluations": counts[3],
-                           "primary_mrays_per_s": counts[0] / ms_dev / 1e3, "parallelism": f"rows interleaved over {world} GPU(s)",
-                           "filter": {"primary": "pencil" if variant & 2 else "generic", "shadow": "pencil" if variant & 4 else "generic", "bounce": "generic",
-                                      "clause_free": bool(variant & 1)},
-                           "l2": "flushed between timed iterations (256 MiB write)", "wall_s_timed_region": t_wall},
+                "config": config_for(args.workload, desc, scene, W, H, pf, lvl, len(lights), world),
+                "run": {"mode": "single process, rt_init(N)" if single else "one process per GPU (torchrun), rt_init_rank", "rays_per_frame": rays,
+                        "primary": counts[0], "shadow": counts[1], "bounce": counts[2], "exact_reevaluations": counts[3],
+                        "primary_mrays_per_s": counts[0] / ms_dev / 1e3,
+                        "filter": {"primary": "pencil" if variant & 2 else "generic", "shadow": "pencil" if variant & 4 else "generic", "bounce": "generic",
+                                   "clause_free": bool(variant & 1), "pencil_without_premise": bool(variant & 8), "graph_replay": bool(variant & 16)},
+                        "l2": "flushed between timed iterations (256 MiB write per device)", "wall_s_timed_region": t_wall},
                 "clocks": clocks,
                 "e2e": {"value": rays / ms_e2e / 1e3, "unit": "Mrays/s", "ms_per_step": ms_e2e, "ms_steps_rank0": [round(x, 2) for x in e2e_steps],
+                        "upload_ms": parts[0], "render_ms": parts[1], "download_ms": parts[2],
                         "h2d_bytes_per_step": int(ntri * (4 * 16 + 4) + scene.materials.shape[0] * 64 + 432), "d2h_bytes_per_step": int(fb_host.nbytes),
-                        "path": "rt_upload_scene + rt_render + rt_download_framebuffer with host buffers, every step"},
+                        "path": "rt_upload_scene + rt_render + rt_download_framebuffer with host buffers, every step (max over ranks of each part)"},
                 "gpu_launches": int(st["n_launches"]) * args.steps,
                 "accelerated": {"option": "RT_OPT_TILE_CULLING (opt-in; not the brute-force contract path, not used for value/e2e/roofline)",
                                 "ms_per_step": ms_cull, "value": rays / ms_cull / 1e3, "unit": "Mrays/s", "image_bit_identical_to_brute_force": cull_identical},
+                "parity": parity,
                 "roofline": roof}
-        if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
-            k = lattice_for_seconds(scene, cam, pf, lvl, lights, threads, args.cpu_seconds)
-            dt, r, npix, kind = cpu_sample(scene, cam, pf, lvl, lights, k, threads)
-            line["cpu_baseline"] = {"value": r / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": kind,
-                                    "sample": f"every {k}th pixel of every {k}th row of the same frame ({npix} of {W * H} pixels, all {pf * pf} sub-samples "
-                                              f"each), {dt:.1f} s; the reference's own raytracing.cpp/mesh.cpp (-O2 -ffp-contract=off), OpenMP over pixels in the harness",
-                                    "ms_per_frame_extrapolated": dt * 1e3 * W * H / npix}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_block(scene, cam, pf, lvl, lights, os.cpu_count() or 1)
         emit(line)
     R.shutdown()
-    if world > 1:
+    if multi_rank:
         import torch.distributed as td
         td.barrier()
         td.destroy_process_group()

@@ -151,20 +151,22 @@ class Renderer:
     def upload_scene(self, scene):
         """scene: raytracert_b200.host.Scene (flat numpy arrays as the C++ flatten produces them)."""
         n = scene.n_triangles
-        v0, v1, v2 = scene.corner(0), scene.corner(1), scene.corner(2)
-        nrm = np.zeros((n, 4), np.float32)
-        nrm[:, :3] = scene.normals
-        tm = np.ascontiguousarray(scene.tri_material, np.uint32)
-        mats = (RtMaterial * len(scene.materials))()
-        for i, m in enumerate(scene.materials):
-            for k in range(3):
-                mats[i].Kd[k], mats[i].Ka[k], mats[i].Ks[k] = float(m[k]), float(m[4 + k]), float(m[8 + k])
-            mats[i].Ns, mats[i].Ni, mats[i].Tr, mats[i].flags = float(m[3]), float(m[7]), float(m[11]), int(m[12])
-        sph = (RtSphere * max(1, len(scene.spheres)))()
-        for i, s in enumerate(scene.spheres):
-            for k in range(3):
-                sph[i].center[k] = float(s[k])
-            sph[i].radius, sph[i].material = float(s[3]), int(s[4])
+        f = scene.flat()          # SoA float4 host buffers, flattened once per scene (host/flatten.h in the C++ drop-in)
+        v0, v1, v2, nrm, tm = f["v0"], f["v1"], f["v2"], f["normal"], f["tri_material"]
+        packed = getattr(scene, "_rt_packed", None)
+        if packed is None or packed[2] is not scene.spheres or packed[3] is not scene.materials:
+            mats = (RtMaterial * len(scene.materials))()
+            for i, m in enumerate(scene.materials):
+                for k in range(3):
+                    mats[i].Kd[k], mats[i].Ka[k], mats[i].Ks[k] = float(m[k]), float(m[4 + k]), float(m[8 + k])
+                mats[i].Ns, mats[i].Ni, mats[i].Tr, mats[i].flags = float(m[3]), float(m[7]), float(m[11]), int(m[12])
+            sph = (RtSphere * max(1, len(scene.spheres)))()
+            for i, s in enumerate(scene.spheres):
+                for k in range(3):
+                    sph[i].center[k] = float(s[k])
+                sph[i].radius, sph[i].material = float(s[3]), int(s[4])
+            packed = scene._rt_packed = (mats, sph, scene.spheres, scene.materials)
+        mats, sph = packed[:2]
         sc = RtScene(n, v0.ctypes.data, v1.ctypes.data, v2.ctypes.data, nrm.ctypes.data, tm.ctypes.data,
                      len(scene.materials), C.cast(mats, C.c_void_p), len(scene.spheres),
                      C.cast(sph, C.c_void_p) if len(scene.spheres) else None)

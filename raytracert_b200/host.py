@@ -63,6 +63,19 @@ class Scene:
         out[:, :3] = self.vertices[self.indices[:, k]]
         return out
 
+    def flat(self):
+        """The scene as the SoA float4 host buffers of ``rt_scene`` (what host/flatten.h produces once per load in the C++
+        drop-in): corners v0/v1/v2, normal, material index.  Built once and kept -- these ARE the host buffers every
+        rt_upload_scene call reads."""
+        f = getattr(self, "_flat", None)
+        if f is None:
+            n = self.n_triangles
+            nrm = np.zeros((n, 4), np.float32)
+            nrm[:, :3] = self.normals
+            f = self._flat = dict(v0=self.corner(0), v1=self.corner(1), v2=self.corner(2), normal=nrm,
+                                  tri_material=np.ascontiguousarray(self.tri_material, np.uint32))
+        return f
+
     def save(self, path):
         np.savez_compressed(path, vertices=self.vertices, indices=self.indices, tri_material=self.tri_material,
                             normals=self.normals, materials=self.materials, names=np.array(self.names),

@@ -204,6 +204,11 @@ int main() {
     }
     cudaMemcpy(rec, h, sizeof(h), cudaMemcpyHostToDevice);
     run<2, 8, 0, 2>("packed rp2 j8 minb2 (shipped)", rec, out, cyc);
+    run<3, 8, 0, 2>("packed rp3 j8 minb2", rec, out, cyc);
+    run<4, 8, 0, 2>("packed rp4 j8 minb2", rec, out, cyc);
+    run<4, 4, 0, 2>("packed rp4 j4 minb2", rec, out, cyc);
+    run<4, 8, 0, 1>("packed rp4 j8 minb1", rec, out, cyc);
+    run<6, 4, 0, 1>("packed rp6 j4 minb1", rec, out, cyc);
     run<2, 8, 1, 2>("scalar rp2 j8 minb2", rec, out, cyc);
     run<2, 8, 2, 2>("packed FMA only rp2 j8 minb2 (7 ops)", rec, out, cyc);
     run<4, 8, 1, 2>("scalar rp4 j8 minb2", rec, out, cyc);
