@@ -128,10 +128,10 @@ def cpu_oracle():
     return pyoracle.PortOracle(), "port"
 
 
-def lattice_pitch(W, H):
+def lattice_pitch(W, H, pixels=1600.0):
     """One fixed pitch per workload for every CPU timing of it (cpu_baseline at any N, --impl reference): about 1600
     pixels of the frame (every 20th pixel of every 20th row for 800x800)."""
-    return max(1, int(round((W * H / 1600.0) ** 0.5)))
+    return max(1, int(round((W * H / pixels) ** 0.5)))
 
 
 def lattice_pixels(W, H, k):
@@ -164,11 +164,11 @@ def config_for(name, desc, scene, W, H, pf, lvl, n_lights, n_gpus):
             "parallelism": f"rows interleaved over {n_gpus} GPU(s), scene replicated"}
 
 
-def cpu_baseline_block(scene, cam, pf, lvl, lights, threads):
+def cpu_baseline_block(scene, cam, pf, lvl, lights, threads, pixels=1600.0):
     """The reference's CPU path on this box: all host threads on the fixed lattice, plus a 1-thread figure on a 16x
     sparser lattice of the same frame (SURVEY 8d asks for both)."""
     W, H = cam.W, cam.H
-    k = lattice_pitch(W, H)
+    k = lattice_pitch(W, H, pixels)
     dt, r, npix, kind = cpu_sample(scene, cam, pf, lvl, lights, k, threads)
     k1 = 4 * k
     dt1, r1, npix1, _ = cpu_sample(scene, cam, pf, lvl, lights, k1, 1)

@@ -110,9 +110,11 @@ typedef struct rt_stats {
     uint32_t variant;                                 /* bit 0: scan kernels without the grazing clause (fine mesh);
                                                        * bit 1: pencil filter on the primary rays; bit 2: on shadow rays;
                                                        * bit 3: pencil records built without the clause-free proof;
-                                                       * bit 4: the frame / batch was a CUDA-graph replay */
+                                                       * bit 4: the frame / batch was a CUDA-graph replay;
+                                                       * bit 5: reflection (mirror) pencils served level-1 continuation rays */
     float ms_trace_primary;                           /* the level-0 (primary ray) part of ms_trace */
-    uint32_t reserved;
+    float ms_trace_mirror;                            /* the part of ms_trace spent in mirror-pencil scans (RT_OPT_PENCIL_REFLECT) */
+    uint64_t mirror_rays;                             /* level-1 continuation rays served by a mirror pencil (part of bounce_rays) */
 } rt_stats;
 
 /* Single-process mode: use devices 0..n_gpus-1 of this box (n_gpus >= 1); rows are interleaved over
@@ -171,6 +173,12 @@ int rt_trace(const rt_params* params, int n, const float* origins, const float* 
  * that launch keeps the generic kernels); rt_stats.variant bit 3 says it was used.  0 = pencil launches only under the
  * clause-free proof.  Same filter + exact tiers, identical image and ids (tests/test_gpu_parity.py). */
 #define RT_OPT_PENCIL_ANY 3
+/* RT_OPT_PENCIL_REFLECT (default 1): the continuation rays of PRIMARY hits on a large group of coplanar triangles (a floor,
+ * a wall, water) are the mirror image of a pencil through the eye (reflection(), raytracing.cpp:277-285): they are filtered
+ * with pencil records around the mirrored eye instead of the generic filter.  Every such ray is checked against its pencil
+ * (distance of its line to the mirrored eye, chart, origin side) when it is spawned; a ray that fails takes the generic scan.
+ * At most 4 plane groups per scene; rt_stats.variant bit 5, rt_stats.mirror_rays.  Identical image and ids. */
+#define RT_OPT_PENCIL_REFLECT 5
 /* RT_OPT_GRAPH (default -1 = auto): small frames and small rt_trace batches (samples x triangles <= 4e9: the launch gaps
  * would dominate -- cube.obj at 800x800 is 44 launches for 0.6 ms) are replayed from a captured CUDA graph (every scan
  * launch has a fixed grid: persistent CTAs read their ray counts from device counters); rt_stats.variant bit 4.

@@ -95,6 +95,9 @@ struct RtDevice {
     uint32_t pencil_used = 0;               // rt_stats.variant bits of the last frame (2: primary rays, 4: shadow rays)
     // pencil filter (rt_pencil.h): slot 0 = records around the eye, slot 1 + l = around light l; rebuilt every frame
     float4* prec = nullptr; size_t cap_prec = 0;
+    // reflection pencils: plane group of every triangle, ray queues of the groups (kMaxMirrors x cap_samples)
+    uint8_t* tri_group = nullptr; size_t cap_group = 0;
+    uint32_t* q_mirror = nullptr; size_t cap_q_mirror = 0;
     float4* scene_box = nullptr;            // device: union of the tile boxes (k_scene_box)
     unsigned int* n_near = nullptr;         // device: "always candidate" records per pencil slot (RT_OPT_PENCIL_ANY)
     float box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0};   // host copy, valid while the generic records are
@@ -125,7 +128,7 @@ struct RtDevice {
     int num_sms = 148;
 };
 
-enum KernelKind { kKindTrace = 0, kKindShadow, kKindShade, kKindResolve, kKindGather, kKindTracePrimary, kNumKinds };
+enum KernelKind { kKindTrace = 0, kKindShadow, kKindShade, kKindResolve, kKindGather, kKindTracePrimary, kKindTraceMirror, kNumKinds };
 constexpr size_t kMaxTimedLaunches = 4096;  // beyond this a frame's launches are still counted, not timed
 
 struct Global {
@@ -139,6 +142,9 @@ struct Global {
     ScanConfig pscan = {2, 8, 2};    // shape of the pencil kernels
     bool tile_culling = false;       // RT_OPT_TILE_CULLING
     bool pencil = true;              // RT_OPT_PENCIL: common-point filter for primary / shadow rays where it applies
+    bool pencil_reflect = true;      // RT_OPT_PENCIL_REFLECT: mirror pencils for the level-1 continuation rays of planar reflectors
+    struct PlaneGroup { double n[3], d; uint32_t count; };
+    std::vector<PlaneGroup> planes;  // the (at most kMaxMirrors) largest groups of coplanar triangles of the scene; group id = index
     bool pencil_any = true;          // RT_OPT_PENCIL_ANY: also for scenes without the clause-free proof (near-plane triangles: always candidates)
     int graph_mode = -1;             // RT_OPT_GRAPH: -1 auto (small frames replay a captured CUDA graph), 0 never, 1 always
     bool allow_no_grazing = true;    // RT_B200_GRAZING=1 forces the grazing clause on (experiments)
@@ -181,6 +187,7 @@ struct PinnedStage {
 };
 PinnedStage<float4> g_stage_triv, g_stage_nm, g_stage_sph;
 PinnedStage<uint32_t> g_stage_perm;
+PinnedStage<uint8_t> g_stage_group;
 PinnedStage<rt_material> g_stage_mat;
 PinnedStage<float4> g_stage_rays, g_stage_out;   // rt_trace: rays in (origin, dest), results out (colour, level-0 hit)
 cudaEvent_t g_stage_event = nullptr;             // recorded after the last H2D copy out of the staging buffers
@@ -234,7 +241,7 @@ int create_device(RtDevice& d, int device, int rank) {
 void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
-    void* ptrs[] = {d.n_near, d.prec, d.scene_box, d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+    void* ptrs[] = {d.tri_group, d.q_mirror, d.n_near, d.prec, d.scene_box, d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
                     d.q_hit, d.key, d.hit0, d.trace_in, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -263,7 +270,7 @@ struct LaunchTimer {
     ~LaunchTimer() { if (timed) cudaEventRecord(d.kev[2 * (d.kev_kind.size() - 1) + 1], d.stream); }
 };
 
-enum { kScanPrimary = 0, kScanBounce = 1, kScanShadowAny = 2, kScanShadowNearest = 3, kScanPrimaryPencil = 4, kScanShadowPencil = 5 };
+enum { kScanPrimary = 0, kScanBounce = 1, kScanShadowAny = 2, kScanShadowNearest = 3, kScanPrimaryPencil = 4, kScanShadowPencil = 5, kScanBouncePencil = 6 };
 
 template <int RP, int J, int MINB, bool GRAZ, bool CULL>
 void launch_scan_gc(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
@@ -295,6 +302,7 @@ void dispatch_scan(const ScanConfig& c, int which, int num_sms, cudaStream_t st,
 template <int RP, int J, int MINB>
 void launch_pencil(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
     if (which == kScanPrimaryPencil) k_trace<RP, J, MINB, true, false, false, true><<<grid, kThreads, 0, st>>>(P, level);
+    else if (which == kScanBouncePencil) k_trace<RP, J, MINB, false, false, false, true><<<grid, kThreads, 0, st>>>(P, level);
     else k_shadow<RP, J, MINB, false, false, false, true><<<grid, kThreads, 0, st>>>(P, level);
 }
 void dispatch_pencil(const ScanConfig& c, int which, int num_sms, cudaStream_t st, const FrameParams& P, int level) {
@@ -325,6 +333,7 @@ void read_tuning_env() {
     if (const char* c = getenv("RT_B200_CULL")) g.tile_culling = atoi(c) != 0;   // same as rt_set_option(RT_OPT_TILE_CULLING, ..)
     if (const char* c = getenv("RT_B200_PENCIL")) g.pencil = atoi(c) != 0;       // same as rt_set_option(RT_OPT_PENCIL, ..)
     if (const char* c = getenv("RT_B200_PENCIL_ANY")) g.pencil_any = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_ANY, ..)
+    if (const char* c = getenv("RT_B200_PENCIL_REFLECT")) g.pencil_reflect = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_REFLECT, ..)
     if (const char* c = getenv("RT_B200_GRAPH")) g.graph_mode = atoi(c) < 0 ? -1 : (atoi(c) != 0);   // same as rt_set_option(RT_OPT_GRAPH, ..)
     if (const char* pe = getenv("RT_B200_PTUNE")) {
         ScanConfig c = g.pscan;
@@ -457,7 +466,10 @@ void fill_common(FrameParams& P, const RtDevice& d, const rt_params& rp, float e
     P.features = rp.features;
     P.max_lvl = rp.max_lvl;
     P.light_sel = -1;
+    P.mirror_sel = -1;
+    P.n_mirrors = 0;
 }
+
 
 // Pencil launches of one frame on one device (rt_pencil.h).  cam: the primary rays; light[l]: the shadow rays of light l.
 struct PencilPlan {
@@ -466,7 +478,22 @@ struct PencilPlan {
     bool no_premise = false;   // built without the clause-free proof (RT_OPT_PENCIL_ANY)
     PencilSetup cam_setup, light_setup[RT_MAX_LIGHTS];
     size_t slot_vec = 0;   // float4 per record slot
+    // reflection pencils: mirror[g] serves the level-1 continuation rays of plane group g (record slot mirror_slot0 + g)
+    int n_mirrors = 0;     // == number of plane groups when any of them qualifies (groups that do not get an impossible check)
+    bool mirror[kMaxMirrors] = {};
+    PencilSetup mirror_setup[kMaxMirrors];
+    MirrorCheck mirror_check[kMaxMirrors];
+    int mirror_slot0 = 0;
 };
+
+// Reflection pencils of this frame: what k_shade needs to route the level-1 continuation rays (level 0 only reads it).
+void apply_mirrors(FrameParams& P, const RtDevice& d, const PencilPlan& plan) {
+    P.n_mirrors = plan.n_mirrors;
+    P.tri_group = d.tri_group;
+    P.q_mirror = d.q_mirror;
+    P.q_mirror_stride = (uint32_t)d.cap_samples;
+    for (int k = 0; k < plan.n_mirrors; ++k) P.mirror[k] = plan.mirror_check[k];
+}
 
 void apply_pencil(FrameParams& P, const RtDevice& d, const PencilPlan& plan, int slot, const PencilSetup& S) {
     P.prec = d.prec + (size_t)slot * plan.slot_vec;
@@ -493,7 +520,8 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
         memcpy(k, &d.rec_gen, sizeof(uint64_t)); k += sizeof(uint64_t);
         memcpy(k, rp.corners, sizeof(rp.corners)); k += sizeof(rp.corners);
         memcpy(k, rp.lights, sizeof(rp.lights)); k += sizeof(rp.lights);
-        const uint32_t w[4] = {rp.n_lights, rp.features & RT_SHADOWS, (uint32_t)g.pencil_any, (uint32_t)g.any_transparent};
+        const uint32_t w[4] = {rp.n_lights, (rp.features & (RT_SHADOWS | RT_REFLECTION)) | (rp.max_lvl > 0 ? 1u << 16 : 0u),
+                               (uint32_t)g.pencil_any | ((uint32_t)g.pencil_reflect << 1), (uint32_t)g.any_transparent};
         memcpy(k, w, sizeof(w));
     }
     if (d.prec && key == d.plan_key && d.plan_blob.size() == sizeof(PencilPlan)) { memcpy(&plan, d.plan_blob.data(), sizeof(PencilPlan)); return RT_OK; }
@@ -524,10 +552,28 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
             plan.any_light = plan.any_light || plan.light[l];
         }
     if (!plan.cam && !plan.any_light) return RT_OK;
-    int rc = ensure(d.prec, d.cap_prec, plan.slot_vec * (1 + (shadows ? rp.n_lights : 0)));
+    // reflection pencils: the level-1 continuation rays of primary hits on a plane group leave the mirror image of the eye
+    plan.mirror_slot0 = 1 + (shadows ? (int)rp.n_lights : 0);
+    if (plan.cam && g.pencil_reflect && (rp.features & RT_REFLECTION) && rp.max_lvl > 0 && !g.planes.empty()) {
+        bool any = false;
+        for (size_t k = 0; k < g.planes.size() && k < (size_t)kMaxMirrors; ++k) {
+            // continuation rays are unit long (reflect_ray: dest = P + R, origin = P + 0.01 R)
+            plan.mirror[k] = g.planes[k].count >= 2 &&
+                             pencil_mirror_setup(plan.cam_setup, g.planes[k].n, g.planes[k].d, (double)d.M_built, d.box_lo, d.box_hi, plan.mirror_setup[k], plan.mirror_check[k]) &&
+                             proof_holds(plan.mirror_setup[k], 1.05);
+            if (!plan.mirror[k]) {   // not served: a check nothing passes
+                memset(&plan.mirror_check[k], 0, sizeof(MirrorCheck));
+                plan.mirror_check[k].w_max2 = -1.0f;
+            }
+            any = any || plan.mirror[k];
+        }
+        plan.n_mirrors = any ? (int)std::min(g.planes.size(), (size_t)kMaxMirrors) : 0;
+    }
+    int rc = ensure(d.prec, d.cap_prec, plan.slot_vec * (size_t)(plan.mirror_slot0 + plan.n_mirrors));
     if (rc) return rc;
-    if (!d.n_near) CU(cudaMalloc(&d.n_near, sizeof(unsigned int) * (1 + RT_MAX_LIGHTS)));
-    if (!premise) CU(cudaMemsetAsync(d.n_near, 0, sizeof(unsigned int) * (1 + RT_MAX_LIGHTS), d.stream));
+    constexpr int kNearWords = 1 + RT_MAX_LIGHTS + kMaxMirrors;
+    if (!d.n_near) CU(cudaMalloc(&d.n_near, sizeof(unsigned int) * kNearWords));
+    if (!premise) CU(cudaMemsetAsync(d.n_near, 0, sizeof(unsigned int) * kNearWords, d.stream));
     const int grid = (npad + 127) / 128;
     if (plan.cam)
         k_build_pencil<<<grid, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.cam_setup, d.prec, premise ? 1 : 0, d.n_near);
@@ -535,10 +581,14 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
         if (plan.light[l])
             k_build_pencil<<<grid, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.light_setup[l],
                                                        d.prec + (size_t)(1 + l) * plan.slot_vec, premise ? 1 : 0, d.n_near + 1 + l);
+    for (int k = 0; k < plan.n_mirrors; ++k)
+        if (plan.mirror[k])
+            k_build_pencil<<<grid, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.mirror_setup[k],
+                                                       d.prec + (size_t)(plan.mirror_slot0 + k) * plan.slot_vec, premise ? 1 : 0, d.n_near + 1 + RT_MAX_LIGHTS + k);
     CU(cudaGetLastError());
     if (!premise) {
         // too many "always candidate" records would turn the scan into an exact scan: such a launch keeps the generic kernels
-        unsigned int h_near[1 + RT_MAX_LIGHTS];
+        unsigned int h_near[kNearWords];
         CU(cudaMemcpyAsync(d.h_small + 16, d.n_near, sizeof(h_near), cudaMemcpyDeviceToHost, d.stream));
         CU(cudaStreamSynchronize(d.stream));
         memcpy(h_near, d.h_small + 16, sizeof(h_near));
@@ -548,6 +598,16 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
             if (h_near[1 + l] > kPencilMaxNear) plan.light[l] = false;
             plan.any_light = plan.any_light || plan.light[l];
         }
+        bool any_mirror = false;
+        for (int k = 0; k < plan.n_mirrors; ++k) {
+            if (plan.mirror[k] && h_near[1 + RT_MAX_LIGHTS + k] > kPencilMaxNear) {
+                plan.mirror[k] = false;
+                memset(&plan.mirror_check[k], 0, sizeof(MirrorCheck));
+                plan.mirror_check[k].w_max2 = -1.0f;
+            }
+            any_mirror = any_mirror || plan.mirror[k];
+        }
+        if (!any_mirror || !plan.cam) plan.n_mirrors = 0;
         plan.no_premise = plan.cam || plan.any_light;
     }
     d.plan_key = key;
@@ -563,6 +623,23 @@ int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullp
     const int levels = bounces ? std::min(P.max_lvl + 1, kMaxLevels - 2) : 1;
     const int grid_small = d.num_sms * 4;
     for (int level = 0; level < levels; ++level) {
+        if (level == 1 && plan && P.n_mirrors > 0 && !P.trace_api) {
+            // the queues k_shade filled at level 0: one pencil scan + finish per plane group around the mirrored eye
+            for (int gk = 0; gk < P.n_mirrors; ++gk) {
+                if (!plan->mirror[gk]) continue;
+                FrameParams Pm = P;
+                apply_pencil(Pm, d, *plan, plan->mirror_slot0 + gk, plan->mirror_setup[gk]);
+                Pm.mirror_sel = gk;
+                {
+                    LaunchTimer t(d, kKindTraceMirror);
+                    dispatch_pencil(g.pscan, kScanBouncePencil, d.num_sms, d.stream, Pm, level);
+                }
+                {
+                    LaunchTimer t(d, kKindShade);
+                    k_finish<false><<<grid_small, 256, 0, d.stream>>>(Pm, level);
+                }
+            }
+        }
         {
             LaunchTimer t(d, level == 0 ? kKindTracePrimary : kKindTrace);
             if (level == 0 && plan && plan->cam && !P.trace_api) {
@@ -687,6 +764,7 @@ int render_enqueue_impl(const rt_params* rp) {
 
     for (RtDevice& d : g.devs) {
         CU(cudaSetDevice(d.device));
+        (void)cudaGetLastError();   // see rt_trace
         d.kev_kind.clear();
         const uint32_t my_rows = (H > (uint32_t)d.rank) ? (H - d.rank + G - 1) / G : 0;
         const uint32_t nchunks = (my_rows + rows_per_chunk - 1) / rows_per_chunk;
@@ -694,8 +772,9 @@ int render_enqueue_impl(const rt_params* rp) {
         rc = build_records(d, M, direction_bound(*rp, true, nullptr, nullptr, 0)); if (rc) return rc;
         PencilPlan plan;
         rc = plan_pencil(d, *rp, g.tile_culling && d.ntiles <= kCullMaxTiles, plan); if (rc) return rc;
-        d.pencil_used = (plan.cam ? 2u : 0u) | (plan.any_light ? 4u : 0u) | (plan.no_premise ? 8u : 0u);
+        d.pencil_used = (plan.cam ? 2u : 0u) | (plan.any_light ? 4u : 0u) | (plan.no_premise ? 8u : 0u) | (plan.n_mirrors > 0 ? 32u : 0u);
         rc = ensure_chunk_state(d, chunk_cap, rp->want_prim_id != 0, (size_t)rows_per_rank * row_samples); if (rc) return rc;
+        if (plan.n_mirrors > 0) { rc = ensure(d.q_mirror, d.cap_q_mirror, (size_t)kMaxMirrors * d.cap_samples); if (rc) return rc; }
         rc = ensure_counters(d, std::max(1u, nchunks)); if (rc) return rc;
         size_t need_local = (size_t)rows_per_rank * W * 3;
         rc = ensure(d.fb_local, d.cap_local, need_local); if (rc) return rc;
@@ -725,6 +804,7 @@ int render_enqueue_impl(const rt_params* rp) {
                 P.nslots = P.tiles_x * ((P.nrows + 7) / 8) * 64u * spp;
                 P.sample_base = (unsigned long long)P.row0 * row_samples;
                 P.prim_out = rp->want_prim_id ? d.prim : nullptr;
+                if (plan.n_mirrors > 0) apply_mirrors(P, d, plan);
                 int levels = run_wavefront(d, P, nullptr, &plan);
                 if (levels < 0) return levels;
                 levels_done = levels;
@@ -748,7 +828,7 @@ int render_enqueue_impl(const rt_params* rp) {
             KeyWriter kw{key};
             kw.put(*rp); kw.put(d.rec_gen); kw.put_bytes(&plan, sizeof(plan));
             const void* ptrs[] = {d.rec, d.triv, d.normal_mat, d.materials, d.spheres, d.prec, d.tile_box, d.super_box, d.always_list, d.ray_o, d.ray_d,
-                                  d.thr, d.acc, d.hit, d.lit, d.q_ray, d.q_hit, d.key, d.counters, d.prim, d.fb_local};
+                                  d.thr, d.acc, d.hit, d.lit, d.q_ray, d.q_hit, d.key, d.counters, d.prim, d.fb_local, d.q_mirror, d.tri_group};
             kw.put(ptrs);
             const int cfg[] = {g.scan.rp, g.scan.j, g.scan.minb, g.pscan.rp, g.pscan.j, g.pscan.minb, (int)g.tile_culling, (int)G, d.rank, d.num_sms, (int)g.any_transparent};
             kw.put(cfg);
@@ -859,6 +939,7 @@ int collect_stats() {
                 if (shadows) st.shadow_rays += (uint64_t)cw[kCntHit + l] * rp.n_lights;
                 if (l > 0) st.bounce_rays += cw[kCntRay + l];
             }
+            for (int k = 0; k < kMaxMirrors; ++k) { st.bounce_rays += cw[kCntMirror + k]; st.mirror_rays += cw[kCntMirror + k]; }   // level-1 rays served by a mirror pencil
             st.exact_evals += (uint64_t)cw[kCntExact] | ((uint64_t)cw[kCntExact + 1] << 32);
         }
         float ms = 0.f;
@@ -867,7 +948,7 @@ int collect_stats() {
         for (size_t i = 0; i < d.kev_kind.size(); ++i)
             if (d.kev_kind[i] >= 0 && cudaEventElapsedTime(&ms, d.kev[2 * i], d.kev[2 * i + 1]) == cudaSuccess) by_kind[d.kev_kind[i]] += ms;
         if (getenv("RT_B200_LAUNCHLOG")) {   // per-launch device times of the frame, in launch order (diagnostics)
-            static const char* names[kNumKinds] = {"trace", "shadow", "shade/finish", "resolve", "gather", "trace_primary"};
+            static const char* names[kNumKinds] = {"trace", "shadow", "shade/finish", "resolve", "gather", "trace_primary", "trace_mirror"};
             for (size_t i = 0; i < d.kev_kind.size(); ++i)
                 if (d.kev_kind[i] >= 0 && cudaEventElapsedTime(&ms, d.kev[2 * i], d.kev[2 * i + 1]) == cudaSuccess && ms > 0.05f)
                     fprintf(stderr, "librt_b200: launch %3zu %-14s %9.3f ms\n", i, names[d.kev_kind[i]], ms);
@@ -876,16 +957,20 @@ int collect_stats() {
                 for (int l = 0; l < 6; ++l) fprintf(stderr, "librt_b200: chunk %d level %d: %u rays in, %u hits\n", c, l, l == 0 ? 0u : cw[kCntRay + l], cw[kCntHit + l]);
             }
         }
-        st.ms_trace = std::max(st.ms_trace, by_kind[kKindTrace] + by_kind[kKindTracePrimary]);
+        st.ms_trace = std::max(st.ms_trace, by_kind[kKindTrace] + by_kind[kKindTracePrimary] + by_kind[kKindTraceMirror]);
+        st.ms_trace_mirror = std::max(st.ms_trace_mirror, by_kind[kKindTraceMirror]);
         st.ms_trace_primary = std::max(st.ms_trace_primary, by_kind[kKindTracePrimary]);
         st.ms_shadow = std::max(st.ms_shadow, by_kind[kKindShadow]);
         st.ms_shade = std::max(st.ms_shade, by_kind[kKindShade]);
         st.ms_resolve = std::max(st.ms_resolve, by_kind[kKindResolve]);
         if (cudaEventElapsedTime(&ms, d.ev_phase[1], d.ev_phase[2]) == cudaSuccess) st.ms_gather = std::max(st.ms_gather, ms);
         st.n_launches = std::max(st.n_launches, (uint32_t)d.kev_kind.size());
-        st.variant |= (d.no_grazing ? 1u : 0u) | d.pencil_used | (d.used_graph ? 16u : 0u);
+        st.variant |= (d.no_grazing ? 1u : 0u) | d.pencil_used | (d.used_graph ? 16u : 0u);   // pencil_used carries bit 5 (32) for mirror pencils
     }
     st.tri_tests = (st.primary_rays + st.shadow_rays + st.bounce_rays) * (uint64_t)st.n_triangles;
+    // cudaEventElapsedTime on events a call never recorded (rt_trace records no frame phases) fails harmlessly above, but
+    // the runtime keeps the code as its "last error": drop it, or the next cudaGetLastError() after a launch reports it
+    (void)cudaGetLastError();
     return RT_OK;
 }
 
@@ -904,7 +989,7 @@ static void release_all() {
     g.scene_ready = g.frame_ready = g.stats_ready = false;
     if (g_stage_event) { cudaEventDestroy(g_stage_event); g_stage_event = nullptr; }
     g_stage_triv.release(); g_stage_nm.release(); g_stage_sph.release(); g_stage_perm.release(); g_stage_mat.release();
-    g_stage_rays.release(); g_stage_out.release();
+    g_stage_rays.release(); g_stage_out.release(); g_stage_group.release();
 }
 
 void rt_shutdown(void) {
@@ -912,6 +997,7 @@ void rt_shutdown(void) {
     g.tile_culling = false;
     g.pencil = true;
     g.pencil_any = true;
+    g.pencil_reflect = true;
     g.graph_mode = -1;
 }
 
@@ -1002,6 +1088,13 @@ int rt_upload_scene(const rt_scene* sc) {
     if (!triv.data() || !nm.data()) return fail(RT_ERR_CUDA, "out of host memory for the scene staging buffers");
     static std::vector<uint8_t> cls;
     cls.resize(n);
+    // plane groups (reflection pencils): heavy hitters among the quantised plane equations, one direct-mapped table pass
+    struct PlaneSlot { uint64_t key; uint32_t count; uint32_t first; };
+    constexpr uint32_t kPlaneSlots = 4096;
+    static std::vector<PlaneSlot> ptab;
+    static std::vector<uint64_t> pkey;
+    ptab.assign(kPlaneSlots, PlaneSlot{0, 0, 0});
+    pkey.resize(n);
     size_t cnt[4] = {0, 0, 0, 0};
     float extent = 0.f;
     double max_uuvv = 0.0;
@@ -1030,6 +1123,27 @@ int rt_upload_scene(const rt_scene* sc) {
         if (nz > (w == 1 ? ny : nx)) w = 2;   // NaN compares false: non-finite triangles land in class 0 (and are "always exact")
         cls[i] = (uint8_t)w;
         ++cnt[w];
+        {   // quantised plane (unit normal with a canonical sign, offset): coplanar triangles share the key (up to bin edges --
+            // a split group only serves fewer rays: every ray is checked against its pencil when it is routed, k_shade)
+            const float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+            const float l2n = cx * cx + cy * cy + cz * cz;
+            uint64_t key = 0;
+            if (l2n > 0.f && l2n < 1e30f) {
+                float inv = 1.0f / std::sqrt(l2n);
+                if (cx < 0.f || (cx == 0.f && (cy < 0.f || (cy == 0.f && cz < 0.f)))) inv = -inv;
+                const float qx = cx * inv, qy = cy * inv, qz = cz * inv, qd = qx * A[0] + qy * A[1] + qz * A[2];
+                const int64_t ix = (int64_t)std::lrintf(qx * 16384.f) + 16384, iy = (int64_t)std::lrintf(qy * 16384.f) + 16384, iz = (int64_t)std::lrintf(qz * 16384.f) + 16384;
+                const int64_t id = (int64_t)std::lrintf(std::fmin(std::fmax(qd * 1024.f, -2.0e6f), 2.0e6f)) + (1 << 21);
+                key = ((uint64_t)ix << 48) ^ ((uint64_t)iy << 32) ^ ((uint64_t)iz << 16) ^ ((uint64_t)id * 0x9E3779B97F4A7C15ull) | 1ull;
+            }
+            pkey[i] = key;
+            if (key) {
+                PlaneSlot& ps = ptab[(uint32_t)((key * 0xD6E8FEB86659FD93ull) >> 52)];
+                if (ps.key == key) ++ps.count;
+                else if (ps.count <= 1) { ps.key = key; ps.count = 1; ps.first = i; }
+                else --ps.count;   // Misra-Gries style: a heavy plane keeps its slot
+            }
+        }
         const double p2 = (double)(ux * ux + uy * uy + uz * uz) * (double)(vx * vx + vy * vy + vz * vz);
         max_uuvv = (p2 == p2) ? std::max(max_uuvv, p2) : INFINITY;   // NaN vertices: never claim the bound
         const float l2 = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
@@ -1037,6 +1151,38 @@ int rt_upload_scene(const rt_scene* sc) {
     }
     g.max_uv = (float)std::min(std::sqrt(max_uuvv) * 1.0001, 1e30);
     g.unit_normals = unit_normals;
+    // the (at most kMaxMirrors) heaviest planes become groups; exact membership counts in a second, cheap pass
+    g.planes.clear();
+    PinnedStage<uint8_t>& grp = g_stage_group;
+    grp.resize(std::max(n, 1u));
+    if (!grp.data()) return fail(RT_ERR_CUDA, "out of host memory for the scene staging buffers");
+    {
+        uint64_t top_key[kMaxMirrors]; uint32_t top_cnt[kMaxMirrors], top_first[kMaxMirrors]; int ntop = 0;
+        for (const PlaneSlot& ps : ptab) {
+            if (ps.count < 2 || !ps.key) continue;
+            int at = ntop < kMaxMirrors ? ntop++ : -1;
+            if (at < 0) { int w = 0; for (int k = 1; k < kMaxMirrors; ++k) if (top_cnt[k] < top_cnt[w]) w = k; if (top_cnt[w] < ps.count) at = w; }
+            if (at >= 0) { top_key[at] = ps.key; top_cnt[at] = ps.count; top_first[at] = ps.first; }
+        }
+        uint32_t members[kMaxMirrors] = {};
+        for (uint32_t i = 0; i < n; ++i) {
+            uint8_t gi = kNoGroup;
+            for (int k = 0; k < ntop; ++k) if (pkey[i] == top_key[k]) { gi = (uint8_t)k; ++members[k]; break; }
+            grp[i] = gi;
+        }
+        for (int k = 0; k < ntop; ++k) {   // the plane of the group: its first member's, in double
+            const uint32_t i = top_first[k];
+            const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i;
+            const double u[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]}, v[3] = {(double)C[0] - A[0], (double)C[1] - A[1], (double)C[2] - A[2]};
+            double nn[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+            const double l = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+            Global::PlaneGroup pg;
+            for (int a = 0; a < 3; ++a) pg.n[a] = l > 0.0 ? nn[a] / l : 0.0;
+            pg.d = pg.n[0] * A[0] + pg.n[1] * A[1] + pg.n[2] * A[2];
+            pg.count = members[k];
+            g.planes.push_back(pg);   // a degenerate first member (l == 0) fails pencil_mirror_setup later: the group is simply not served
+        }
+    }
     // group the triangles by class; stable inside a class, every class padded to whole tiles
     PinnedStage<uint32_t>& perm = g_stage_perm;
     int cls_tiles[3] = {0, 0, 0};
@@ -1129,8 +1275,10 @@ int rt_upload_scene(const rt_scene* sc) {
         CU(cudaMemcpyAsync(d.normal_mat, nm.data(), sizeof(float4) * nm.size(), cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.materials, mats.data(), sizeof(rt_material) * sc->n_materials, cudaMemcpyHostToDevice, d.stream));
         CU(cudaMemcpyAsync(d.spheres, sph.data(), sizeof(float4) * sph.size(), cudaMemcpyHostToDevice, d.stream));
+        rc = ensure(d.tri_group, d.cap_group, grp.size()); if (rc) return rc;
+        CU(cudaMemcpyAsync(d.tri_group, grp.data(), grp.size(), cudaMemcpyHostToDevice, d.stream));
         CU(cudaEventRecord(d.ev_stage, d.stream));
-        if (!g_stage_triv.pinned || !g_stage_nm.pinned || !g_stage_perm.pinned || !g_stage_mat.pinned || !g_stage_sph.pinned)
+        if (!g_stage_triv.pinned || !g_stage_nm.pinned || !g_stage_perm.pinned || !g_stage_mat.pinned || !g_stage_sph.pinned || !g_stage_group.pinned)
             CU(cudaStreamSynchronize(d.stream));   // pageable fallback: keep the old, synchronous behaviour
     }
     g.scene_ready = true;
@@ -1219,6 +1367,7 @@ static int rt_trace_impl(const rt_params* rp, int n, const float* origins, const
     if ((size_t)n > kMaxChunkSamples) return fail(RT_ERR_INVALID, "rt_trace: at most %u rays per call", kMaxChunkSamples);
     RtDevice& d = g.devs[0];
     CU(cudaSetDevice(d.device));
+    (void)cudaGetLastError();   // a stale code from an earlier, already reported failure must not be blamed on this call's launches
     d.kev_kind.clear();
     d.used_graph = false;
     float M = magnitude_bound(*rp, origins, 3 * n);
@@ -1319,6 +1468,8 @@ int rt_set_option(int option, int value) {
     if (option == RT_OPT_TILE_CULLING) { g.tile_culling = value != 0; return RT_OK; }
     if (option == RT_OPT_PENCIL) { g.pencil = value != 0; return RT_OK; }
     if (option == RT_OPT_PENCIL_ANY) { g.pencil_any = value != 0; return RT_OK; }
+    if (option == RT_OPT_PENCIL_REFLECT) { g.pencil_reflect = value != 0; return RT_OK; }
+    if (option == RT_OPT_PENCIL_REFLECT) { g.pencil_reflect = value != 0; return RT_OK; }
     if (option == RT_OPT_GRAPH) { g.graph_mode = value < 0 ? -1 : (value != 0); return RT_OK; }
     return fail(RT_ERR_INVALID, "unknown option %d", option);
 }

@@ -55,7 +55,10 @@ constexpr int kMaxLevels = 40;
 constexpr int kCntHit = 0;                 // [level] hits recorded by k_finish at that level
 constexpr int kCntRay = kMaxLevels;        // [level] rays queued for k_trace at that level
 constexpr int kCntExact = 2 * kMaxLevels;  // 64-bit: exact re-evaluations (2 words)
-constexpr int kCntWords = 2 * kMaxLevels + 4;
+constexpr int kMaxMirrors = 4;             // reflection pencils: plane groups served per frame (rt_pencil.h: pencil_mirror_setup)
+constexpr int kCntMirror = 2 * kMaxLevels + 4;   // [group] level-1 continuation rays routed to the mirror pencil of that plane group
+constexpr int kCntWords = 2 * kMaxLevels + 4 + kMaxMirrors;
+constexpr uint8_t kNoGroup = 0xff;
 
 struct FrameParams {
     // scene
@@ -107,7 +110,16 @@ struct FrameParams {
     int light_sel;              // k_shadow: >= 0 -> this launch handles only that light; -1 -> all lights (ray = hit * nlights + light)
     float pF[9];                // chart frame u, v, f: a ray is (x, y, 1) = dir / (dir.f) in it
     float p_wmax2;              // chart bound: 1 + x^2 + y^2 <= p_wmax2, else the ray is not filtered (exact path for everything)
+    // reflection pencils (level-1 continuation rays of primary hits on a plane group; rt_pencil.h)
+    int n_mirrors;              // plane groups with a mirror pencil this frame (0: none)
+    const uint8_t* tri_group;   // plane group of every triangle (kNoGroup: none); only read when n_mirrors > 0
+    uint32_t* q_mirror;         // ray queues of the groups, q_mirror_stride entries each
+    uint32_t q_mirror_stride;
+    int mirror_sel;             // >= 0: this k_trace / k_finish launch serves the ray queue of that group; -1: the ordinary queue
+    MirrorCheck mirror[kMaxMirrors];
 };
+__device__ __forceinline__ const uint32_t* ray_queue(const FrameParams& P) { return P.mirror_sel >= 0 ? P.q_mirror + (size_t)P.mirror_sel * P.q_mirror_stride : P.q_ray; }
+__device__ __forceinline__ uint32_t ray_queue_count(const FrameParams& P, int level) { return P.mirror_sel >= 0 ? P.counters[kCntMirror + P.mirror_sel] : P.counters[kCntRay + level]; }
 
 // ------------------------------------------------------------------------------------------------
 // Filter records
@@ -575,11 +587,8 @@ template <int RP>
 __device__ __forceinline__ bool pencil_set_slot(PencilRays<RP>& f, int k, const FrameParams& P, v3 O, v3 D, bool flip, float nearest0, bool live) {
     const float s = flip ? -1.0f : 1.0f;
     const float dx = s * (D.x - O.x), dy = s * (D.y - O.y), dz = s * (D.z - O.z);   // the sign of a float difference is exact
-    const float den = fmaf(dx, P.pF[6], fmaf(dy, P.pF[7], dz * P.pF[8]));
-    const float inv = __fdiv_rn(1.0f, den);
-    float x = fmaf(dx, P.pF[0], fmaf(dy, P.pF[1], dz * P.pF[2])) * inv;
-    float y = fmaf(dx, P.pF[3], fmaf(dy, P.pF[4], dz * P.pF[5])) * inv;
-    const bool ok = (den > 0.0f) && (fmaf(x, x, fmaf(y, y, 1.0f)) <= P.p_wmax2);     // NaN / inf fail both
+    float x, y;
+    const bool ok = pencil_chart_xy(P.pF, P.p_wmax2, dx, dy, dz, x, y);
     if (!ok) x = y = __int_as_float(0x7fc00000);
     float z = pencil_zhi(P, O, x, y, nearest0);
     if (!live) { x = y = 0.0f; z = 0.0f; }
@@ -957,15 +966,17 @@ __device__ __forceinline__ void fast_set_slot(FastRays<RP>& fr, int k, v3 O, v3 
 template <bool B, class X, class Y> struct SelectT { using type = X; };
 template <class X, class Y> struct SelectT<false, X, Y> { using type = Y; };
 
-// PENCIL (primary rays of a frame only, brute force): the pencil filter around the eye (P.prec, P.pE).
+// PENCIL (brute force): the pencil filter around the eye for the primary rays of a frame (P.prec, P.pE), or around the mirror
+// image of the eye for the queue of a plane group's level-1 continuation rays (P.mirror_sel >= 0; k_shade checked every one).
 template <int RP, int J, int MINB, bool PRIMARY, bool GRAZ, bool CULL, bool PENCIL = false>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant__ FrameParams P, int level) {
-    static_assert(!PENCIL || (PRIMARY && !CULL), "the pencil filter serves primary rays in the brute-force scan");
+    static_assert(!PENCIL || !CULL, "the pencil filter serves the brute-force scan");
     constexpr int R = 2 * RP;
     __shared__ ScanSmem sm;
     __shared__ CullStorage<CULL> csm;
     __shared__ ColdStorage<R, !CULL> cold;
-    const uint32_t count = PRIMARY ? P.nslots : P.counters[kCntRay + level];
+    const uint32_t count = PRIMARY ? P.nslots : ray_queue_count(P, level);
+    const uint32_t* __restrict__ queue = ray_queue(P);
     const uint32_t per_chunk = kThreads * R;
     const Split sp = make_split(count, per_chunk, P.ntiles, true);
     Pipe pipe;
@@ -997,7 +1008,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
                         P.acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 } else {
-                    if (!PRIMARY) s = P.q_ray[ray];
+                    if (!PRIMARY) s = queue[ray];
                     const float4 o = P.ray_o[s], d = P.ray_d[s];
                     O = mk3(o); D = mk3(d);
                 }
@@ -1039,7 +1050,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 template <bool PRIMARY>
 __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FrameParams P, int level) {
-    const uint32_t count = PRIMARY ? P.nslots : P.counters[kCntRay + level];
+    const uint32_t count = PRIMARY ? P.nslots : ray_queue_count(P, level);
+    const uint32_t* __restrict__ queue = ray_queue(P);
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounds = (count + stride - 1) / stride;
     const uint32_t all_lit = (P.nlights >= 32) ? 0xffffffffu : ((1u << P.nlights) - 1u);
@@ -1048,7 +1060,7 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FramePar
         bool hit_any = false;
         uint32_t s = 0;
         bool ok = i < count;
-        if (ok) { if (PRIMARY) ok = slot_to_sample(P, i, s); else s = P.q_ray[i]; }
+        if (ok) { if (PRIMARY) ok = slot_to_sample(P, i, s); else s = queue[i]; }
         if (ok) {
             const unsigned long long key = P.key[s];
             P.key[s] = kKeyEmpty;  // ready for the next level / frame
@@ -1264,6 +1276,7 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ FramePara
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t h = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
         bool spawn = false;
+        int group = -1;   // >= 0: the continuation ray goes to the queue of that plane group's mirror pencil
         uint32_t s = 0;
         if (h < count) {
             s = P.q_hit[h];
@@ -1364,6 +1377,15 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ FramePara
             } else if (fReflection && lvl < P.max_lvl) {                                      // Ks * reflection(..., lvl+1)
                 reflect_ray(ray, Ppos, normal, point, dest);
                 K = M.Ks; nlvl = lvl + 1; spawn = true;   // traced even when Ks == 0, like the reference
+                // reflection of a PRIMARY ray off a triangle of a plane group: the mirror pencil of that plane takes the ray if
+                // (checked here, on the ray as built) its line passes through the mirror image of the eye (rt_pencil.h)
+                if (P.n_mirrors > 0 && level == 0 && idx < P.ntri) {
+                    const uint32_t g = P.tri_group[idx];
+                    if (g < (uint32_t)P.n_mirrors) {
+                        const float Of[3] = {point.x, point.y, point.z}, Df[3] = {dest.x, dest.y, dest.z};
+                        if (pencil_mirror_accepts(P.mirror[g], Of, Df)) group = (int)g;
+                    }
+                }
             }
             if (spawn) {
                 P.ray_o[s] = make_float4(point.x, point.y, point.z, 0.f);
@@ -1371,7 +1393,9 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ FramePara
                 P.thr[s] = make_float4(__fmul_rn(th.x, K.x), __fmul_rn(th.y, K.y), __fmul_rn(th.z, K.z), 0.f);
             }
         }
-        warp_append(spawn, s, P.q_ray, &P.counters[kCntRay + level + 1]);
+        warp_append(spawn && group < 0, s, P.q_ray, &P.counters[kCntRay + level + 1]);
+        for (int g = 0; g < P.n_mirrors; ++g)   // (0 unless this is level 0 of a frame with mirror pencils)
+            warp_append(spawn && group == g, s, P.q_mirror + (size_t)g * P.q_mirror_stride, &P.counters[kCntMirror + g]);
     }
 }
 

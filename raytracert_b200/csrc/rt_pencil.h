@@ -396,4 +396,81 @@ inline bool pencil_light_setup(const float L[3], const float box_lo[3], const fl
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Reflection pencils: the continuation rays of PRIMARY hits on one plane n.X = d (|n| = 1) -- a floor, a wall, the
+// water of the stand-in scene: many coplanar triangles -- leave the mirror image E* of the eye, because reflection()
+// (raytracing.cpp:277-285) mirrors a line through the eye about that plane.  The chart is the mirrored camera chart.
+// Nothing here relies on an error analysis of the reflection arithmetic: k_shade routes a continuation ray to this
+// pencil only after pencil_mirror_accepts() has CHECKED, in float, that its line passes within delta/2 of E*, that
+// its direction lies in the chart and that E* is at least lam_min behind its origin; every other ray takes the generic
+// scan.  delta >= 4*delta_cam + 64u*max(M, lam_max) keeps the check's own rounding (<= 32u*lam_max) inside the other half.
+// ------------------------------------------------------------------------------------------------
+struct MirrorCheck {       // what pencil_mirror_accepts needs, 16 floats
+    float E[3], half_delta2;   // E* (float), (delta / 2)^2
+    float F[9];                // chart frame u, v, f (float)
+    float w_max2, lam_min2, pad;
+};
+
+inline bool pencil_mirror_setup(const PencilSetup& cam, const double n[3], double d, double M_scene, const float* box_lo, const float* box_hi,
+                                PencilSetup& S, MirrorCheck& C) {
+    const double nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (!(fabs(nl - 1.0) < 1e-6) || !isfinite(d)) return false;
+    const double sd = n[0] * cam.E[0] + n[1] * cam.E[1] + n[2] * cam.E[2] - d;   // signed distance of the eye to the plane
+    const double h = fabs(sd);
+    auto mirror_vec = [&](const double v[3], double out[3]) {
+        const double t = 2.0 * (v[0] * n[0] + v[1] * n[1] + v[2] * n[2]);
+        for (int k = 0; k < 3; ++k) out[k] = v[k] - t * n[k];
+    };
+    for (int k = 0; k < 3; ++k) S.E[k] = cam.E[k] - 2.0 * sd * n[k];
+    double f[3];
+    mirror_vec(cam.ff, f);
+    const double fl = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+    for (int k = 0; k < 3; ++k) f[k] /= fl;
+    pencil_frame(S, f);      // any orthonormal completion will do: the chart bound is rotation invariant
+    S.w_max = cam.w_max * (1.0 + 1e-4);
+    if (!(S.w_max < 8.0) || !(M_scene < 1e18)) return false;
+    S.lam_max = (box_lo && box_hi && box_lo[0] <= box_hi[0] && box_lo[1] <= box_hi[1] && box_lo[2] <= box_hi[2]) ? pencil_farthest_corner(S.E, box_lo, box_hi) : 0.0;
+    S.delta = 0.0;
+    pencil_finish_setup(S, M_scene);   // S.M, lam_max (if 0), theta, frame floats
+    S.delta = 4.0 * cam.delta + 64.0 * kPencilU * fmax(S.M, S.lam_max);
+    S.lam_slack = (float)((128.0 * kPencilU * S.M + 3.0 * S.delta) * 1.0001);
+    // the origins sit on the plane (+ the 0.01 offset along the reflected ray): at least ~h from E*; half of it is demanded
+    const double lam_min = 0.5 * h;
+    if (!(lam_min >= 2e-3 * S.M) || !(S.delta <= 1e-3 * S.M)) return false;
+    S.cos_g = fmax(kPencilCosMin, fmax(2.5 * S.delta / lam_min, 5.0 * S.theta));
+    for (int k = 0; k < 3; ++k) C.E[k] = S.Ef[k];
+    for (int k = 0; k < 9; ++k) C.F[k] = S.F[k];
+    C.half_delta2 = (float)(0.25 * S.delta * S.delta * 0.999);
+    C.w_max2 = S.w_max2;
+    C.lam_min2 = (float)(lam_min * lam_min * 1.001);
+    C.pad = 0.f;
+    return true;
+}
+
+// Chart coordinates of a ray in the frame F (pencil_set_slot, k_shade and the CPU replay share this): false = not representable.
+RT_HD bool pencil_chart_xy(const float F[9], float w_max2, float dx, float dy, float dz, float& x, float& y) {
+    const float den = fmaf(dx, F[6], fmaf(dy, F[7], dz * F[8]));
+#ifdef __CUDA_ARCH__
+    const float inv = __fdiv_rn(1.0f, den);
+#else
+    const float inv = 1.0f / den;
+#endif
+    x = fmaf(dx, F[0], fmaf(dy, F[1], dz * F[2])) * inv;
+    y = fmaf(dx, F[3], fmaf(dy, F[4], dz * F[5])) * inv;
+    return (den > 0.0f) && (fmaf(x, x, fmaf(y, y, 1.0f)) <= w_max2);     // NaN / inf fail both
+}
+
+// Does the line through O and D (the continuation ray k_shade just built) belong to the mirror pencil?  Float arithmetic;
+// |(O - E*) x dir| is evaluated to within 8u|O - E*||dir|, i.e. the distance to within 32u*lam_max < delta/2.
+RT_HD bool pencil_mirror_accepts(const MirrorCheck& C, const float O[3], const float D[3]) {
+    const float dx = D[0] - O[0], dy = D[1] - O[1], dz = D[2] - O[2];
+    const float ox = O[0] - C.E[0], oy = O[1] - C.E[1], oz = O[2] - C.E[2];
+    float x, y;
+    if (!pencil_chart_xy(C.F, C.w_max2, dx, dy, dz, x, y)) return false;
+    const float cx = oy * dz - oz * dy, cy = oz * dx - ox * dz, cz = ox * dy - oy * dx;
+    const float c2 = cx * cx + cy * cy + cz * cz, d2 = dx * dx + dy * dy + dz * dz, o2 = ox * ox + oy * oy + oz * oz;
+    const float od = ox * dx + oy * dy + oz * dz;
+    return (c2 <= C.half_delta2 * d2) && (od > 0.0f) && (o2 >= C.lam_min2) && (o2 < 1e30f);
+}
+
 }  // namespace rt

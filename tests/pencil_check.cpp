@@ -54,6 +54,8 @@ static long long g_near_plane = 0;
 extern "C" {
 
 void pencil_check_set_premise(int on) { g_premise = on; }
+static double g_plane[4] = {0, 1, 0, 0};
+void pencil_check_set_plane(double nx, double ny, double nz, double d) { g_plane[0] = nx; g_plane[1] = ny; g_plane[2] = nz; g_plane[3] = d; }
 long long pencil_check_near_planes(void) { return g_near_plane; }
 
 // mode 2 (groundwork for reflection pencils): rays leaving a common point that the caller describes
@@ -69,7 +71,18 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
     PencilSetup S;
     memset(&S, 0, sizeof(S));
     bool ok;
+    MirrorCheck MC;
+    memset(&MC, 0, sizeof(MC));
+    const bool mirror_mode = (mode == 3);
     if (mode == 0) ok = pencil_camera_setup(setup24, M_scene, nullptr, nullptr, S);
+    else if (mode == 3) {
+        // mode 3: the SHIPPED reflection pencil -- camera `setup24` mirrored about the plane of pencil_check_set_plane(); only rays
+        // pencil_mirror_accepts() lets through are filtered (k_shade routes the others to the generic scan: counted as unsafe)
+        PencilSetup cam;
+        memset(&cam, 0, sizeof(cam));
+        ok = pencil_camera_setup(setup24, M_scene, nullptr, nullptr, cam) && pencil_mirror_setup(cam, g_plane, g_plane[3], M_scene, nullptr, nullptr, S, MC);
+        mode = 0;
+    }
     else if (mode == 1) ok = pencil_light_setup(setup24, setup24 + 3, setup24 + 6, M_scene, S);
     else {
         double f[3] = {setup24[3], setup24[4], setup24[5]};
@@ -112,6 +125,7 @@ int pencil_check(int mode, const float* setup24, double M_scene, int ntri, const
 #pragma omp parallel for schedule(dynamic, 16) reduction(+ : pairs, ref_hits, cands, viol, graz, unsafe)
     for (int r = 0; r < nrays; ++r) {
         const float *O = rays + 6 * r, *D = O + 3;
+        if (mirror_mode && !pencil_mirror_accepts(MC, O, D)) { ++unsafe; continue; }
         // pencil_set_slot (rt_kernels.cuh)
         const float sgn = mode == 1 ? -1.0f : 1.0f;
         const float dx = sgn * (D[0] - O[0]), dy = sgn * (D[1] - O[1]), dz = sgn * (D[2] - O[2]);

@@ -110,3 +110,26 @@ def test_single_process_multi_gpu_ids(built, tmp_path):
         "print('OK')\n")
     r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_trace_and_stats_before_any_frame(built):
+    """A fresh process that never renders a frame: rt_trace, rt_get_stats (which queries frame-phase events nobody recorded),
+    rt_trace again with and without the graph replay -- the stale CUDA error code of the event query must not surface."""
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from raytracert_b200 import binding, host\n"
+        f"z = np.load({os.path.join(GOLDEN, 'trace_shadow_test.npz')!r})\n"
+        f"s = host.Scene.load({os.path.join(GOLDEN, 'scenes', 'shadow_test.npz')!r})\n"
+        "R = binding.Renderer(1); R.upload_scene(s)\n"
+        "prm = binding.make_params([0] * 24, 1, 1, 1, 1, 10, 63, z['eye'], [z['eye']])\n"
+        "for g in (0, -1, 0, 1):\n"
+        "    R.set_option(binding.RT_OPT_GRAPH, g)\n"
+        "    for n in (1, 7, 1):\n"
+        "        rgb, prim, hit = R.trace(prm, z['origins'][:n], z['dests'][:n])\n"
+        "        assert np.array_equal(prim, z['prim'][:n]), (g, n)\n"
+        "        st = R.stats()\n"
+        "        assert bool(st['variant'] & 16) == (g != 0), (g, st['variant'])\n"
+        "R.shutdown(); print('OK')\n")
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

@@ -746,3 +746,50 @@ def test_headline_frame_pinned_on_every_row(gpu):
 def test_C3_frame_pinned_on_a_row_subset(gpu):
     """C3 (dodgeColorTest 1920x1080x16): 64 rows spread over the frame against the reference's own rows."""
     assert _pin_check(gpu, "dodge") >= 64
+
+
+def test_reflection_pencils_are_invisible(gpu, port):
+    """RT_OPT_PENCIL_REFLECT (default on): level-1 continuation rays of primary hits on a plane group (the stand-in's water,
+    the floor / walls of the mirror room, cube faces) are scanned with pencil records around the mirrored eye.  The frame
+    -- ids, float RGB bits, ray counts -- must equal the option-off frame and the oracle; rt_stats must report the rays."""
+    from raytracert_b200 import binding, host, scenes
+    big = scenes.balls_standin()
+    cases = [
+        ("balls", big, host.Camera(200, 160, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0)), 2, 3, [(2.5, 4.0, 3.0)], True),
+        ("balls_low", big, host.Camera(160, 100, (0.2, 0.75, 4.6), (0.0, 0.62, 0.0)), 2, 3, [(2.5, 4.0, 3.0)], True),
+        ("balls_default_camera", big, host.Camera(160, 120), 1, 3, [(0.0, 0.0, 4.0)], None),           # eye IN the water plane: no mirror pencil possible
+        ("room", scenes.mirror_room(n=16), host.Camera(96, 72, (0.3, 1.6, 4.2), (0, 0.8, 0)), 2, 6, [(1.5, 2.8, 2.5)], True),
+        ("cube", load_scene("cube"), host.Camera(96, 96, (2.6, 2.4, 3.0), (.5, .5, .5)), 2, 10, [(3.0, 5.0, 4.0)], True),
+        ("dodge", load_scene("dodge"), host.Camera(96, 54, (.75, .55, 1.1), (.07, 0, .23)), 1, 10, [(.75, .55, 1.1)], None),
+    ]
+    try:
+        for name, s, cam, pf, lvl, lights, expect in cases:
+            lights = np.asarray(lights, np.float32)
+            c = dict(corners=cam.corners, W=cam.W, H=cam.H, pfx=pf, pfy=pf, max_lvl=lvl, features=63, eye=cam.eye, lights=lights)
+            gpu.set_option(binding.RT_OPT_PENCIL_REFLECT, 0)
+            rgb0, prim0 = gpu_render(gpu, s, c)
+            st0 = gpu.stats()
+            assert not (st0["variant"] & 32) and st0["mirror_rays"] == 0, name
+            gpu.set_option(binding.RT_OPT_PENCIL_REFLECT, 1)
+            rgb1, prim1 = gpu_render(gpu, s, c)
+            st1 = gpu.stats()
+            if expect:
+                assert (st1["variant"] & 32) and st1["mirror_rays"] > 0, (name, st1["variant"], st1["mirror_rays"])
+            elif expect is None and name == "balls_default_camera":
+                assert st1["mirror_rays"] == 0, name
+            assert np.array_equal(prim0, prim1), name
+            assert np.array_equal(bits(rgb0), bits(rgb1)), f"{name}: {np.count_nonzero(bits(rgb0) != bits(rgb1))} framebuffer words differ"
+            for k in ("primary_rays", "shadow_rays", "bounce_rays"):
+                assert st0[k] == st1[k], (name, k, st0[k], st1[k])
+            port.set_scene(s); port.configure(cam.eye, lights, 63, lvl); port.reset_counts()
+            rgb_o, _, prim_o = port.render(cam.corners, cam.W, cam.H, pf, pf, want_samples=True)
+            assert np.array_equal(prim1, prim_o), name
+            assert np.abs(rgb1 - rgb_o).max() <= RGB_TOL, name
+            assert (st1["primary_rays"], st1["shadow_rays"], st1["bounce_rays"]) == port.ray_counts(), name
+        # the headline scene: about a quarter of the level-1 rays leave the water
+        c = dict(corners=cases[0][2].corners, W=200, H=160, pfx=2, pfy=2, max_lvl=3, features=63, eye=cases[0][2].eye, lights=np.asarray([(2.5, 4.0, 3.0)], np.float32))
+        gpu_render(gpu, big, c)
+        st = gpu.stats()
+        assert st["mirror_rays"] > 0.15 * st["bounce_rays"], (st["mirror_rays"], st["bounce_rays"])
+    finally:
+        gpu.set_option(binding.RT_OPT_PENCIL_REFLECT, 1)

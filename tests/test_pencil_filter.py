@@ -36,6 +36,7 @@ def checker(port):
     L = C.CDLL(SO)
     L.pencil_check.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(Result)]
     L.pencil_check_near_planes.restype = C.c_longlong
+    L.pencil_check_set_plane.argtypes = [C.c_double] * 4
     pair_fn = C.cast(port.L.orc_ray_triangle, C.c_void_p)
 
     def run(mode, setup, M, tris, rays, inv_scale=1.0, premise=True):
@@ -53,6 +54,7 @@ def checker(port):
             L.pencil_check_set_premise(1)
         return r
     run.near_planes = 0
+    run.set_plane = lambda n, d: L.pencil_check_set_plane(float(n[0]), float(n[1]), float(n[2]), float(d))
     return run
 
 
@@ -385,6 +387,67 @@ def test_reflection_pencil_around_the_mirrored_eye(checker, port):
         res = checker(2, setup, M, tris, brays, scale)
         assert res.setup_ok and res.violations == 0 and res.grazing_skipped == 0 and res.unsafe_rays == 0
     assert res.candidates < 3 * len(brays)              # about one per ray: the triangle it starts on
+
+
+def reflected_rays(rays, hit, normals):
+    """Continuation rays exactly as reflection() / addOffset() build them (raytracing.cpp:266-285), in float32."""
+    f = np.float32
+    P = hit.astype(f)
+    ray = (rays[:, 3:] - rays[:, :3]).astype(f)
+    r = (ray * (f(1) / np.sqrt((ray * ray).sum(1, dtype=f)).astype(f))[:, None]).astype(f)
+    nf = normals.astype(f)
+    R = (r - (f(2) * (nf * r).sum(1, dtype=f))[:, None] * nf).astype(f)
+    dest = (P + R).astype(f)
+    off = (dest - P).astype(f)
+    off = (off * (f(1) / np.sqrt((off * off).sum(1, dtype=f)).astype(f))[:, None]).astype(f)
+    return np.concatenate([(P + off * f(0.01)).astype(f), dest], axis=1).astype(f)
+
+
+@pytest.mark.parametrize("case", ["water_default", "water_low_camera", "room_floor", "room_wall", "cube_face"])
+def test_shipped_mirror_pencil_is_sound(checker, port, case):
+    """RT_OPT_PENCIL_REFLECT as shipped: pencil_mirror_setup() (camera pencil mirrored about a plane group) + the runtime check
+    pencil_mirror_accepts() k_shade applies to every continuation ray.  Level-1 continuation rays of the primary hits -- on the
+    plane AND elsewhere (those must be refused by the check or be harmless) -- go through the records around the mirrored eye;
+    no pair the reference accepts may be filtered out; rays reflected off the plane itself must (almost all) be accepted."""
+    from raytracert_b200 import host, scenes
+    if case.startswith("water"):
+        s = scenes.balls_standin(grid=48, slices=24, stacks=12)
+        cam = host.Camera(96, 96, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0)) if case == "water_default" else host.Camera(96, 64, (0.2, 0.75, 4.6), (0.0, 0.62, 0.0))
+        n, d, premise = (0.0, 1.0, 0.0), 0.0, True
+    elif case.startswith("room"):
+        s = scenes.mirror_room(n=12)
+        cam = host.Camera(64, 48, (0.3, 1.6, 4.2), (0, 0.8, 0))
+        n, d, premise = ((0.0, 1.0, 0.0), 0.0, False) if case == "room_floor" else ((0.0, 0.0, 1.0), float(s.vertices[:, 2].min()), False)
+    else:
+        from conftest import load_scene
+        s = load_scene("cube")
+        cam = host.Camera(64, 64, (2.6, 2.4, 3.0), (.5, .5, .5))
+        n, d, premise = (0.0, 1.0, 0.0), 1.0, False
+    tris = tri_array(s)
+    M = magnitude_bound(s, cam.corners)
+    rays = primary_rays(cam.corners, cam.W, cam.H, 2, 1)
+    port.set_scene(s)
+    port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
+    _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+    ok = prim >= 0
+    brays = reflected_rays(rays[ok], hit[ok], s.normals[prim[ok]])
+    t = tris.reshape(-1, 3, 3)[prim[ok]]
+    on_plane = np.all(np.abs(t @ np.asarray(n, np.float64) - d) < 1e-6, axis=1)
+    checker.set_plane(n, d)
+    try:
+        for scale in (1.0, 1.0 + 3 * 2.0 ** -24):
+            res = checker(3, cam.corners, M, tris, brays, scale, premise=premise)
+            assert res.setup_ok, case
+            assert res.violations == 0, f"{case}: {res.violations} accepted pairs filtered out (ray {res.first_bad_ray}, triangle {res.first_bad_tri})"
+        if on_plane.sum() > 50:
+            res_on = checker(3, cam.corners, M, tris, brays[on_plane], 1.0, premise=premise)
+            assert res_on.unsafe_rays <= 0.02 * on_plane.sum(), f"{case}: the check refuses {res_on.unsafe_rays} of {on_plane.sum()} rays reflected off the plane"
+            assert res_on.violations == 0
+        if (~on_plane).sum() > 50:      # rays off other surfaces: nearly all must be refused (they do not pass through E*)
+            res_off = checker(3, cam.corners, M, tris, brays[~on_plane], 1.0, premise=premise)
+            assert res_off.violations == 0
+    finally:
+        checker.set_plane((0, 1, 0), 0)
 
 
 def bounce_like_rays(tris, rng, n):

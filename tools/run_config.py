@@ -18,6 +18,7 @@ ap.add_argument("--workload", default="sphere1m")
 ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--lattice", type=int, default=0, help="oracle check on every k-th pixel of every k-th row (0 = ~150 pixels)")
 ap.add_argument("--modes", default="brute_force,tile_culling", help="comma list of brute_force, tile_culling")
+ap.add_argument("--cpu-pixels", type=float, default=0, help="> 0: also time the CPU reference on a lattice of about this many pixels (all cores + 1 thread)")
 args = ap.parse_args()
 R, rank, world = dist.make_renderer()
 scene, W, H, pf, lvl, eye, center, lights, desc = bench.workload(args.workload)
@@ -50,8 +51,21 @@ for mode, cull in (("brute_force", 0), ("tile_culling", 1)):
     else:
         m = float(np.mean(ms))
     frames[mode] = R.download(want_prim_id=(world == 1))
-    out[mode] = {"ms_per_frame": m, "Mrays_per_s": rays / m / 1e3, "rays": rays, "tests_per_s": rays * scene.n_triangles / (m * 1e-3),
-                 "fp32_algorithmic_tflops_per_gpu": 42 * rays * scene.n_triangles / (m * 1e-3) / 1e12 / world}
+    out[mode] = {"ms_per_frame": m, "Mrays_per_s": rays / m / 1e3, "rays": rays, "tests_per_s": rays * scene.n_triangles / (m * 1e-3), "variant": st["variant"]}
+    if not cull:
+        # executed FP32 at the pipe: hot-loop flops per test (12 pencil / 27 generic) x this rank's tests of each launch kind
+        v = st["variant"]
+        cnt = np.array([st["primary_rays"], st["bounce_rays"], st["shadow_rays"]], np.float64)
+        kinds = np.array([st["ms_trace_primary"], st["ms_trace"] - st["ms_trace_primary"], st["ms_shadow"]], np.float64)
+        if world > 1:
+            c = torch.tensor(cnt, dtype=torch.float64, device="cuda"); td.all_reduce(c, op=td.ReduceOp.SUM); cnt = c.cpu().numpy()
+            k_ = torch.tensor(kinds, dtype=torch.float64, device="cuda"); td.all_reduce(k_, op=td.ReduceOp.MAX); kinds = k_.cpu().numpy()
+        peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        alg = 42 * rays * scene.n_triangles / (m * 1e-3) / 1e12 / world
+        ex = ((12 if v & 2 else 27) * cnt[0] + 27 * cnt[1] + (12 if v & 4 else 27) * cnt[2]) * scene.n_triangles / (m * 1e-3) / 1e12 / world
+        out[mode].update({"fp32_algorithmic_tflops_per_gpu": alg, "algorithmic_ratio": alg / peak, "fp32_executed_tflops_per_gpu": ex,
+                          "executed_frac_of_fp32_peak": ex / peak, "ms_primary_bounce_shadow": [float(x) for x in kinds],
+                          "rays_primary_bounce_shadow": [float(x) for x in cnt]})
 if rank == 0:
     a = frames[modes[0]]
     rgb = a[0] if world == 1 else a
@@ -71,6 +85,8 @@ if rank == 0:
     if world == 1:
         po = prim_o.reshape(H, W, pf * pf)[np.ix_(ys, xs)]; pg = a[1].reshape(H, W, pf * pf)[np.ix_(ys, xs)]
         out["oracle_lattice"]["id_mismatches"] = int(np.count_nonzero(po != pg))
+    if args.cpu_pixels > 0:
+        out["cpu_baseline"] = bench.cpu_baseline_block(scene, cam, pf, lvl, lights, os.cpu_count() or 1, args.cpu_pixels)
     print(json.dumps(out), flush=True)
 R.shutdown()
 if world > 1:
