@@ -184,6 +184,10 @@ int rt_trace(const rt_params* params, int n, const float* origins, const float* 
  * launch has a fixed grid: persistent CTAs read their ray counts from device counters); rt_stats.variant bit 4.
  * 0 = never, 1 = always.  A replayed frame reports no per-kernel times (rt_stats.ms_trace .. ms_resolve are 0). */
 #define RT_OPT_GRAPH 4
+/* RT_OPT_SMALL_TRACE (default 1): rt_trace batches of at most 32 rays (and at most 1e5 ray-triangle pairs per level) -- the
+ * drop-in performRayTracing(origin, dest) call is a batch of one -- run the whole recursion in ONE kernel launch of one
+ * thread block with exact tests only (k_trace_small) instead of four launches per level.  0 = always the wavefront kernels. */
+#define RT_OPT_SMALL_TRACE 6
 int rt_set_option(int option, int value);
 
 int rt_get_stats(rt_stats* out);

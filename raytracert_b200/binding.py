@@ -19,6 +19,7 @@ RT_OPT_PENCIL = 2
 RT_OPT_PENCIL_ANY = 3
 RT_OPT_GRAPH = 4
 RT_OPT_PENCIL_REFLECT = 5
+RT_OPT_SMALL_TRACE = 6
 
 
 class RtMaterial(C.Structure):

@@ -24,7 +24,7 @@ using namespace rt;
 // (tools/tune.py sweeps them on the GPU).
 #define RT_SCAN_CONFIGS(X) X(2, 8, 2) X(1, 16, 4)
 // The pencil kernels keep 6 registers per ray pair instead of 14, so they have their own shapes (RT_B200_PTUNE="rp,j,minb").
-#define RT_PENCIL_CONFIGS(X) X(2, 8, 2) X(1, 16, 4)   // more rays per thread would need > 48 KB of (static) shared memory for the cold state
+#define RT_PENCIL_CONFIGS(X) X(2, 8, 2) X(1, 16, 4) X(4, 4, 2) X(3, 4, 2)   // rp >= 3: scalar hot loop (rt_kernels.cuh: pencil_ray_hot), cold state in dynamic shared memory
 struct ScanConfig { int rp, j, minb; };
 constexpr uint32_t kMaxChunkSamples = 1u << 23;  // 8 Mi samples per wavefront chunk (84 B of state each)
 
@@ -146,6 +146,7 @@ struct Global {
     struct PlaneGroup { double n[3], d; uint32_t count; };
     std::vector<PlaneGroup> planes;  // the (at most kMaxMirrors) largest groups of coplanar triangles of the scene; group id = index
     bool pencil_any = true;          // RT_OPT_PENCIL_ANY: also for scenes without the clause-free proof (near-plane triangles: always candidates)
+    bool small_trace = true;         // RT_B200_SMALL_TRACE=0 keeps small rt_trace batches on the multi-launch wavefront (tests / A-B)
     int graph_mode = -1;             // RT_OPT_GRAPH: -1 auto (small frames replay a captured CUDA graph), 0 never, 1 always
     bool allow_no_grazing = true;    // RT_B200_GRAZING=1 forces the grazing clause on (experiments)
     float max_uv = 0.f;              // max over the triangles of |v1-v0| * |v2-v0| (see build_records)
@@ -155,6 +156,9 @@ struct Global {
     float scene_extent = 0.f;   // max |coordinate| over the scene
     bool any_transparent = false;
     rt_params last;             // params of the last frame
+    rt_params last_trace;       // params of the last rt_trace call
+    bool stats_of_trace = false;   // the counters describe an rt_trace call (of last_trace_n rays), not a frame
+    int last_trace_n = 0;
     uint32_t rows_per_rank = 0;
     rt_stats stats = {};
     std::vector<uint32_t> host_counters;
@@ -272,13 +276,33 @@ struct LaunchTimer {
 
 enum { kScanPrimary = 0, kScanBounce = 1, kScanShadowAny = 2, kScanShadowNearest = 3, kScanPrimaryPencil = 4, kScanShadowPencil = 5, kScanBouncePencil = 6 };
 
+// Every scan kernel takes its shared memory (TMA ring, cold per-ray state, culling lists) as one dynamic block; the
+// attribute is raised once per kernel instantiation and device (> 48 KB needs the opt-in).
+template <class K>
+void launch_kernel_smem(K kernel, size_t smem, int grid, cudaStream_t st, const FrameParams& P, int level) {
+    // (K is the same function-pointer type for every kernel: the bookkeeping is keyed by the pointer's value)
+    static std::vector<std::pair<const void*, uint64_t>> raised;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    uint64_t* mask = nullptr;
+    for (auto& e : raised) if (e.first == fn) { mask = &e.second; break; }
+    if (!mask) { raised.emplace_back(fn, 0ull); mask = &raised.back().second; }
+    if (dev >= 0 && dev < 64 && !((*mask >> dev) & 1ull)) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        *mask |= 1ull << dev;
+    }
+    kernel<<<grid, kThreads, smem, st>>>(P, level);
+}
+
 template <int RP, int J, int MINB, bool GRAZ, bool CULL>
 void launch_scan_gc(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
+    constexpr size_t smem = sizeof(KernelSmem<2 * RP, CULL>);
     switch (which) {
-        case 0: k_trace<RP, J, MINB, true, GRAZ, CULL><<<grid, kThreads, 0, st>>>(P, level); break;
-        case 1: k_trace<RP, J, MINB, false, GRAZ, CULL><<<grid, kThreads, 0, st>>>(P, level); break;
-        case 2: k_shadow<RP, J, MINB, false, GRAZ, CULL><<<grid, kThreads, 0, st>>>(P, level); break;
-        default: k_shadow<RP, J, MINB, true, GRAZ, CULL><<<grid, kThreads, 0, st>>>(P, level); break;
+        case 0: launch_kernel_smem(k_trace<RP, J, MINB, true, GRAZ, CULL>, smem, grid, st, P, level); break;
+        case 1: launch_kernel_smem(k_trace<RP, J, MINB, false, GRAZ, CULL>, smem, grid, st, P, level); break;
+        case 2: launch_kernel_smem(k_shadow<RP, J, MINB, false, GRAZ, CULL>, smem, grid, st, P, level); break;
+        default: launch_kernel_smem(k_shadow<RP, J, MINB, true, GRAZ, CULL>, smem, grid, st, P, level); break;
     }
 }
 template <int RP, int J, int MINB>
@@ -301,9 +325,10 @@ void dispatch_scan(const ScanConfig& c, int which, int num_sms, cudaStream_t st,
 
 template <int RP, int J, int MINB>
 void launch_pencil(int which, int grid, cudaStream_t st, const FrameParams& P, int level) {
-    if (which == kScanPrimaryPencil) k_trace<RP, J, MINB, true, false, false, true><<<grid, kThreads, 0, st>>>(P, level);
-    else if (which == kScanBouncePencil) k_trace<RP, J, MINB, false, false, false, true><<<grid, kThreads, 0, st>>>(P, level);
-    else k_shadow<RP, J, MINB, false, false, false, true><<<grid, kThreads, 0, st>>>(P, level);
+    constexpr size_t smem = sizeof(KernelSmem<2 * RP, false>);
+    if (which == kScanPrimaryPencil) launch_kernel_smem(k_trace<RP, J, MINB, true, false, false, true>, smem, grid, st, P, level);
+    else if (which == kScanBouncePencil) launch_kernel_smem(k_trace<RP, J, MINB, false, false, false, true>, smem, grid, st, P, level);
+    else launch_kernel_smem(k_shadow<RP, J, MINB, false, false, false, true>, smem, grid, st, P, level);
 }
 void dispatch_pencil(const ScanConfig& c, int which, int num_sms, cudaStream_t st, const FrameParams& P, int level) {
 #define RT_X(RP, J, MINB) if (c.rp == RP && c.j == J && c.minb == MINB) return launch_pencil<RP, J, MINB>(which, num_sms * MINB, st, P, level);
@@ -334,6 +359,7 @@ void read_tuning_env() {
     if (const char* c = getenv("RT_B200_PENCIL")) g.pencil = atoi(c) != 0;       // same as rt_set_option(RT_OPT_PENCIL, ..)
     if (const char* c = getenv("RT_B200_PENCIL_ANY")) g.pencil_any = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_ANY, ..)
     if (const char* c = getenv("RT_B200_PENCIL_REFLECT")) g.pencil_reflect = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_REFLECT, ..)
+    if (const char* c = getenv("RT_B200_SMALL_TRACE")) g.small_trace = atoi(c) != 0;
     if (const char* c = getenv("RT_B200_GRAPH")) g.graph_mode = atoi(c) < 0 ? -1 : (atoi(c) != 0);   // same as rt_set_option(RT_OPT_GRAPH, ..)
     if (const char* pe = getenv("RT_B200_PTUNE")) {
         ScanConfig c = g.pscan;
@@ -744,6 +770,8 @@ struct KeyWriter {
 // Frames whose launches are short enough for the launch gaps to matter (C1: 44 launches for 0.6 ms of frame) are replayed
 // from a captured CUDA graph.  Every scan launch has a fixed grid (persistent CTAs read their ray counts from device
 // counters), so the whole wavefront -- all chunks, all levels, the resolve -- is capturable as it is.
+constexpr int kSmallTraceRays = 32;        // rt_trace batches up to this size ...
+constexpr double kSmallTraceTests = 1e5;   // ... and this many (ray, triangle) pairs per level take the single-launch path (measured: tools/trace_latency.py)
 constexpr double kGraphMaxTests = 4e9;   // samples x triangles below which RT_OPT_GRAPH = auto captures the frame
 
 int render_enqueue_impl(const rt_params* rp) {
@@ -893,6 +921,7 @@ int render_enqueue_impl(const rt_params* rp) {
     g.rows_per_rank = rows_per_rank;
     g.frame_ready = true;
     g.stats_ready = true;
+    g.stats_of_trace = false;
     return RT_OK;
 }
 
@@ -923,16 +952,17 @@ int collect_stats() {
     st.n_levels = levels;
     st.n_gpus = (uint32_t)g.world;
     st.rank = g.devs.empty() ? 0 : (uint32_t)g.devs[0].rank;
-    const rt_params& rp = g.last;
+    const rt_params& rp = g.stats_of_trace ? g.last_trace : g.last;
     const bool shadows = (rp.features & RT_SHADOWS) && rp.n_lights > 0;
     for (RtDevice& d : g.devs) {
+        if (g.stats_of_trace && &d != &g.devs[0]) break;   // rt_trace runs on the first device only
         CU(cudaSetDevice(d.device));
         st.n_triangles = (uint32_t)d.ntri;
         g.host_counters.resize((size_t)kCntWords * d.counters_slots);
         CU(cudaMemcpy(g.host_counters.data(), d.counters, sizeof(uint32_t) * g.host_counters.size(), cudaMemcpyDeviceToHost));
         const uint32_t H = rp.height, G = (uint32_t)g.world;
         const uint32_t my_rows = (H > (uint32_t)d.rank) ? (H - d.rank + G - 1) / G : 0;
-        st.primary_rays += (uint64_t)my_rows * rp.width * rp.pixelfactor_x * rp.pixelfactor_y;
+        st.primary_rays += g.stats_of_trace ? (uint64_t)g.last_trace_n : (uint64_t)my_rows * rp.width * rp.pixelfactor_x * rp.pixelfactor_y;
         for (int c = 0; c < d.frame_chunks; ++c) {
             const uint32_t* cw = &g.host_counters[(size_t)c * kCntWords];
             for (int l = 0; l < kMaxLevels; ++l) {
@@ -998,6 +1028,7 @@ void rt_shutdown(void) {
     g.pencil = true;
     g.pencil_any = true;
     g.pencil_reflect = true;
+    g.small_trace = true;
     g.graph_mode = -1;
 }
 
@@ -1395,6 +1426,8 @@ static int rt_trace_impl(const rt_params* rp, int n, const float* origins, const
     P.nslots = (uint32_t)n;
     P.G = 1;
     float4* out = g_stage_out.data();
+    // a handful of rays (the drop-in performRayTracing call is n = 1): everything in one launch of one CTA, exact tests only
+    const bool small = g.small_trace && n <= kSmallTraceRays && (double)n * (double)std::max(d.ntri, 1) <= kSmallTraceTests;
     // one H2D copy in, the wavefront (the level-0 hit records are copied aside on the device before the bounces
     // overwrite them), two D2H copies out -- all in stream order
     auto body = [&]() -> int {
@@ -1402,8 +1435,17 @@ static int rt_trace_impl(const rt_params* rp, int n, const float* origins, const
         CU(cudaMemsetAsync(d.counters, 0, sizeof(uint32_t) * kCntWords, d.stream));
         k_init_trace<<<(n + 255) / 256, 256, 0, d.stream>>>(d.trace_in, n, d.ray_o, d.ray_d, d.thr, d.acc);
         CU(cudaGetLastError());
-        const int levels = run_wavefront(d, P, want_hit ? d.hit0 : nullptr);
-        if (levels < 0) return levels;
+        if (small) {
+            // single-launch path (rt_kernels.cuh: k_trace_small): one CTA carries the batch through every level
+            const bool bounces = (P.features & (RT_REFLECTION | RT_REFRACTION)) != 0;
+            const int levels = bounces ? std::min(P.max_lvl + 1, kMaxLevels - 2) : 1;
+            LaunchTimer t(d, kKindTrace);
+            k_trace_small<<<1, kSmallThreads, 0, d.stream>>>(P, levels, want_hit ? d.hit0 : nullptr, g.any_transparent ? 1 : 0);
+            CU(cudaGetLastError());
+        } else {
+            const int levels = run_wavefront(d, P, want_hit ? d.hit0 : nullptr);
+            if (levels < 0) return levels;
+        }
         CU(cudaMemcpyAsync(out, d.acc, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
         if (want_hit) CU(cudaMemcpyAsync(out + n, d.hit0, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
         return RT_OK;
@@ -1418,7 +1460,7 @@ static int rt_trace_impl(const rt_params* rp, int n, const float* origins, const
         KeyWriter kw{key};
         rt_params rk = *rp;
         memset(rk.corners, 0, sizeof(rk.corners)); rk.width = rk.height = rk.pixelfactor_x = rk.pixelfactor_y = 0; rk.want_prim_id = 0;   // ignored by rt_trace
-        kw.put(rk); kw.put(d.rec_gen); kw.put(n); kw.put(want_hit); kw.put(P.eps_r);
+        kw.put(rk); kw.put(d.rec_gen); kw.put(n); kw.put(want_hit); kw.put(P.eps_r); kw.put(small);
         const void* ptrs[] = {d.rec, d.triv, d.normal_mat, d.materials, d.spheres, d.tile_box, d.super_box, d.always_list, d.ray_o, d.ray_d, d.thr, d.acc,
                               d.hit, d.lit, d.q_ray, d.q_hit, d.key, d.counters, d.trace_in, d.hit0, in, out};
         kw.put(ptrs);
@@ -1460,7 +1502,7 @@ int rt_trace(const rt_params* rp, int n, const float* origins, const float* dest
     const int rc = rt_trace_impl(rp, n, origins, dests, rgb, prim_id, hit);
     if (rc != RT_OK)
         for (RtDevice& d : g.devs) { d.key_dirty = true; d.capturing = false; }
-    else g.stats_ready = true;
+    else { g.stats_ready = true; g.stats_of_trace = true; g.last_trace = *rp; g.last_trace_n = n; }
     return rc;
 }
 
@@ -1470,6 +1512,7 @@ int rt_set_option(int option, int value) {
     if (option == RT_OPT_PENCIL_ANY) { g.pencil_any = value != 0; return RT_OK; }
     if (option == RT_OPT_PENCIL_REFLECT) { g.pencil_reflect = value != 0; return RT_OK; }
     if (option == RT_OPT_PENCIL_REFLECT) { g.pencil_reflect = value != 0; return RT_OK; }
+    if (option == RT_OPT_SMALL_TRACE) { g.small_trace = value != 0; return RT_OK; }
     if (option == RT_OPT_GRAPH) { g.graph_mode = value < 0 ? -1 : (value != 0); return RT_OK; }
     return fail(RT_ERR_INVALID, "unknown option %d", option);
 }

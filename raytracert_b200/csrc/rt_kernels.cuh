@@ -358,6 +358,15 @@ template <int R> struct ColdStorage<R, false> { __device__ ColdSmem<R>* get() { 
 template <bool CULL> struct CullStorage { CullSmem s; __device__ CullSmem& get() { return s; } __device__ const unsigned short* list() { return s.list; } };
 template <> struct CullStorage<false> { __device__ CullSmem& get() { return *reinterpret_cast<CullSmem*>(this); } __device__ const unsigned short* list() { return nullptr; } };
 
+// Everything a scan kernel keeps in shared memory, as ONE block of dynamic shared memory (the 8-rays-per-thread pencil
+// shape needs 57 KB: more than the 48 KB a kernel may declare statically).
+template <int R, bool CULL> struct KernelSmem {
+    ScanSmem sm;
+    CullStorage<CULL> csm;
+    ColdStorage<R, !CULL> cold;
+};
+extern __shared__ __align__(128) unsigned char rt_dyn_smem[];
+
 // Work decomposition of one scan launch.  count rays -> nchunks chunks of kThreads*R rays; when there are fewer chunks
 // than CTAs the triangle tiles are split into `parts` ranges of `len` tiles each (the record array carries kPadTiles
 // "never" tiles, so the last range may run past ntiles).  Work item w = chunk * parts + part; CTA b takes items
@@ -633,6 +642,16 @@ __device__ __forceinline__ void pencil_pair_hot(const PencilRays<RP>& f, int p, 
     s1 = __float_as_uint(a.y) | __float_as_uint(b.y) | __float_as_uint(c.y);
 }
 
+// The same three weights for ONE ray with scalar FMAs (3 register operands per instruction instead of 4-5): with 8 rays per
+// thread the record loads amortise and the loop is issue-bound rather than register-bandwidth-bound (tools/ubench/pencil.cu:
+// 4.21e12 against 3.59e12 tests/s for the packed 4-ray shape).
+__device__ __forceinline__ uint32_t pencil_ray_hot(float x, float y, const float4& q0, const float4& q1, const float4& q2) {
+    const float a = fmaf(q0.x, x, fmaf(q0.y, y, q0.z));
+    const float b = fmaf(q1.x, x, fmaf(q1.y, y, q1.z));
+    const float c = fmaf(q2.x, x, fmaf(q2.y, y, q2.z));
+    return __float_as_uint(a) | __float_as_uint(b) | __float_as_uint(c);
+}
+
 // Ray-side hooks of the cold path, one overload per filter.
 struct GenericBand { float eps_r2; };   // what the ray-side hook of the generic filter needs
 template <int RP>
@@ -763,13 +782,21 @@ __device__ __forceinline__ void scan_tile_pencil(const float4* rec, PencilRays<R
         for (int j = 0; j < J; j += 2) {   // two triangles per step: acc & u & u' is one LOP3
             const float4 q0 = rec[(jb + j) * kRecVec + 0], q1 = rec[(jb + j) * kRecVec + 1], q2 = rec[(jb + j) * kRecVec + 2];
             const float4 r0 = rec[(jb + j + 1) * kRecVec + 0], r1 = rec[(jb + j + 1) * kRecVec + 1], r2 = rec[(jb + j + 1) * kRecVec + 2];
+            if constexpr (RP >= 3) {   // scalar form (same IEEE FMAs, same order, same bits as the packed one)
 #pragma unroll
-            for (int p = 0; p < RP; ++p) {
-                uint32_t s0, s1, u0, u1;
-                pencil_pair_hot<RP>(fr, p, q0, q1, q2, s0, s1);
-                pencil_pair_hot<RP>(fr, p, r0, r1, r2, u0, u1);
-                acc[2 * p] &= s0 & u0;
-                acc[2 * p + 1] &= s1 & u1;
+                for (int k = 0; k < R; ++k) {
+                    const float x = (k & 1) ? fr.x[k / 2].y : fr.x[k / 2].x, y = (k & 1) ? fr.y[k / 2].y : fr.y[k / 2].x;
+                    acc[k] &= pencil_ray_hot(x, y, q0, q1, q2) & pencil_ray_hot(x, y, r0, r1, r2);
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < RP; ++p) {
+                    uint32_t s0, s1, u0, u1;
+                    pencil_pair_hot<RP>(fr, p, q0, q1, q2, s0, s1);
+                    pencil_pair_hot<RP>(fr, p, r0, r1, r2, u0, u1);
+                    acc[2 * p] &= s0 & u0;
+                    acc[2 * p + 1] &= s1 & u1;
+                }
             }
         }
         uint32_t all = 0xffffffffu;
@@ -972,9 +999,10 @@ template <int RP, int J, int MINB, bool PRIMARY, bool GRAZ, bool CULL, bool PENC
 __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant__ FrameParams P, int level) {
     static_assert(!PENCIL || !CULL, "the pencil filter serves the brute-force scan");
     constexpr int R = 2 * RP;
-    __shared__ ScanSmem sm;
-    __shared__ CullStorage<CULL> csm;
-    __shared__ ColdStorage<R, !CULL> cold;
+    KernelSmem<R, CULL>& ks = *reinterpret_cast<KernelSmem<R, CULL>*>(rt_dyn_smem);
+    ScanSmem& sm = ks.sm;
+    CullStorage<CULL>& csm = ks.csm;
+    ColdStorage<R, !CULL>& cold = ks.cold;
     const uint32_t count = PRIMARY ? P.nslots : ray_queue_count(P, level);
     const uint32_t* __restrict__ queue = ray_queue(P);
     const uint32_t per_chunk = kThreads * R;
@@ -1048,15 +1076,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace(const __grid_constant_
 // point of the winner, tests the analytic spheres (after the triangles, strict <), writes the hit record,
 // arms the lit bits for k_shadow and appends hits to the queue (warp-aggregated).
 // ------------------------------------------------------------------------------------------------
+// (tid, stride): this thread's index among the `stride` threads that share the work -- the whole grid for k_finish, one
+// CTA for the single-launch path of small rt_trace batches (k_trace_small); every thread of a warp must call it.
 template <bool PRIMARY>
-__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FrameParams P, int level) {
+__device__ __forceinline__ void finish_rays(const FrameParams& P, int level, uint32_t tid, uint32_t stride) {
     const uint32_t count = PRIMARY ? P.nslots : ray_queue_count(P, level);
     const uint32_t* __restrict__ queue = ray_queue(P);
-    const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounds = (count + stride - 1) / stride;
     const uint32_t all_lit = (P.nlights >= 32) ? 0xffffffffu : ((1u << P.nlights) - 1u);
     for (uint32_t r = 0; r < rounds; ++r) {
-        const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t i = r * stride + tid;
         bool hit_any = false;
         uint32_t s = 0;
         bool ok = i < count;
@@ -1098,6 +1127,10 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FramePar
         }
     }
 }
+template <bool PRIMARY>
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FrameParams P, int level) {
+    finish_rays<PRIMARY>(P, level, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
 
 // ------------------------------------------------------------------------------------------------
 // k_shadow: one work item = (hit sample, light).  isShadow, raytracing.cpp:241-261.
@@ -1117,9 +1150,10 @@ template <int RP, int J, int MINB, bool NEAREST, bool GRAZ, bool CULL, bool PENC
 __global__ void __launch_bounds__(kThreads, MINB) k_shadow(const __grid_constant__ FrameParams P, int level) {
     static_assert(!PENCIL || (!NEAREST && !CULL), "the pencil filter serves any-hit shadow rays in the brute-force scan");
     constexpr int R = 2 * RP;
-    __shared__ ScanSmem sm;
-    __shared__ CullStorage<CULL> csm;
-    __shared__ ColdStorage<R, !CULL> cold;
+    KernelSmem<R, CULL>& ks = *reinterpret_cast<KernelSmem<R, CULL>*>(rt_dyn_smem);
+    ScanSmem& sm = ks.sm;
+    CullStorage<CULL>& csm = ks.csm;
+    ColdStorage<R, !CULL>& cold = ks.cold;
     const int lsel = P.light_sel;
     const uint32_t nl = lsel >= 0 ? 1u : (uint32_t)P.nlights;
     const uint32_t count = P.counters[kCntHit + level] * nl;
@@ -1267,14 +1301,13 @@ __device__ __forceinline__ void offset_point(v3 Ppos, v3 dest, v3& point) {  // 
     point = e_add(Ppos, off);
 }
 
-__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ FrameParams P, int level) {
+__device__ __forceinline__ void shade_hits(const FrameParams& P, int level, uint32_t tid, uint32_t stride) {
     const uint32_t count = P.counters[kCntHit + level];
-    const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounds = (count + stride - 1) / stride;
     const bool fAmbient = P.features & RT_AMBIENT, fDiffuse = P.features & RT_DIFFUSE, fSpecular = P.features & RT_SPECULAR;
     const bool fReflection = P.features & RT_REFLECTION, fShadows = P.features & RT_SHADOWS, fRefraction = P.features & RT_REFRACTION;
     for (uint32_t r = 0; r < rounds; ++r) {
-        const uint32_t h = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t h = r * stride + tid;
         bool spawn = false;
         int group = -1;   // >= 0: the continuation ray goes to the queue of that plane group's mirror pencil
         uint32_t s = 0;
@@ -1396,6 +1429,111 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ FramePara
         warp_append(spawn && group < 0, s, P.q_ray, &P.counters[kCntRay + level + 1]);
         for (int g = 0; g < P.n_mirrors; ++g)   // (0 unless this is level 0 of a frame with mirror pencils)
             warp_append(spawn && group == g, s, P.q_mirror + (size_t)g * P.q_mirror_stride, &P.counters[kCntMirror + g]);
+    }
+}
+__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ FrameParams P, int level) {
+    shade_hits(P, level, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_trace_small: the whole wavefront of a SMALL rt_trace batch in ONE launch of ONE CTA -- the drop-in
+// performRayTracing(origin, dest) call (raytracing.cpp:410-416) is a batch of one ray, and a dozen-level recursion costs
+// 4 launches per level otherwise.  No filter: with a handful of rays every (ray, triangle) pair simply goes through
+// exact_eval_tri, the triangles split over the CTA's threads, (distance, id) keys merged exactly like the scan kernels
+// merge theirs; finish_rays / shade_hits are the bodies of k_finish / k_shade, run by the same CTA between barriers
+// (global memory written by the CTA is visible to it after __syncthreads()).  hit0: level-0 hit records, copied aside.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 512;   // 128 registers per thread: shade_hits does not spill
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    return v;
+}
+__global__ void __launch_bounds__(kSmallThreads, 1) k_trace_small(const __grid_constant__ FrameParams P, int levels, float4* __restrict__ hit0, int shadow_nearest) {
+    __shared__ unsigned long long s_key;       // shadow ray in flight: (distance, id) of its nearest occluder
+    const uint32_t tid = threadIdx.x, T = blockDim.x;
+    const bool shadows = (P.features & RT_SHADOWS) && P.nlights > 0;
+    for (int level = 0; level < levels; ++level) {
+        const uint32_t count = level == 0 ? P.nslots : P.counters[kCntRay + level];
+        if (count == 0) break;   // uniform: nothing left to trace
+        // (1) nearest hit of every queued ray: triangles over threads
+        for (uint32_t r = 0; r < count; ++r) {
+            const uint32_t s = level == 0 ? r : P.q_ray[r];
+            const float4 o = P.ray_o[s], d = P.ray_d[s];
+            unsigned long long best = kKeyEmpty;
+            for (int tri = (int)tid; tri < P.ntri; tri += (int)T) {
+                const float4 e = exact_eval_tri(P.triv, tri, o.x, o.y, o.z, d.x, d.y, d.z);
+                if (e.w >= 0.0f && e.w < FLT_MAX) {   // what registers in intersectMesh (strict < from FLT_MAX, raytracing.cpp:164,183)
+                    const unsigned long long k = ((unsigned long long)__float_as_uint(e.w) << 32) | (unsigned int)tri;
+                    best = k < best ? k : best;
+                }
+            }
+            best = warp_min_u64(best);
+            if ((tid & 31u) == 0 && best != kKeyEmpty) atomicMin(&P.key[s], best);
+        }
+        if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)count * (unsigned long long)P.ntri);
+        __syncthreads();
+        // (2) hit records (spheres, always-exact list: none outstanding -- every triangle was evaluated exactly; the list is re-evaluated harmlessly)
+        if (level == 0) finish_rays<true>(P, 0, tid, T); else finish_rays<false>(P, level, tid, T);
+        __syncthreads();
+        const uint32_t nhit = P.counters[kCntHit + level];
+        if (level == 0 && hit0)
+            for (uint32_t i = tid; i < P.nsamples; i += T) hit0[i] = P.hit[i];
+        // (3) shadow rays: isShadow (raytracing.cpp:241-261), one (hit, light) pair at a time
+        if (shadows) {
+            for (uint32_t h = 0; h < nhit; ++h) {
+                const uint32_t s = P.q_hit[h];
+                const v3 O = e_add(mk3(P.hit[s]), mk3(0.1f, 0.1f, 0.1f));
+                for (int l = 0; l < P.nlights; ++l) {
+                    const v3 D = mk3(P.lights[l][0], P.lights[l][1], P.lights[l][2]);
+                    if (tid == 0) s_key = kKeyEmpty;
+                    __syncthreads();
+                    unsigned long long best = kKeyEmpty;
+                    for (int tri = (int)tid; tri < P.ntri; tri += (int)T) {
+                        const float4 e = exact_eval_tri(P.triv, tri, O.x, O.y, O.z, D.x, D.y, D.z);
+                        if (e.w >= 0.0f && e.w < FLT_MAX) {
+                            const unsigned long long k = ((unsigned long long)__float_as_uint(e.w) << 32) | (unsigned int)tri;
+                            best = k < best ? k : best;
+                        }
+                    }
+                    for (int sp = (int)tid; sp < P.nspheres; sp += (int)T) {   // spheres come after the triangles, strict <: id = ntri + sp loses ties
+                        const float4 c = P.spheres[2 * sp];
+                        v3 Is;
+                        if (exact_ray_sphere(O, D, mk3(c), c.w, Is)) {
+                            const float ds = e_distance(O, Is);
+                            if (ds >= 0.0f && ds < FLT_MAX) {
+                                const unsigned long long k = ((unsigned long long)__float_as_uint(ds) << 32) | (unsigned int)(P.ntri + sp);
+                                best = k < best ? k : best;
+                            }
+                        }
+                    }
+                    best = warp_min_u64(best);
+                    if ((tid & 31u) == 0 && best != kKeyEmpty) atomicMin(&s_key, best);
+                    __syncthreads();
+                    if (tid == 0) {
+                        const unsigned long long k = s_key;
+                        bool lit = true;
+                        if (k != kKeyEmpty) {
+                            lit = false;
+                            if (shadow_nearest) {   // the nearest occluder's material decides: transparent -> no shadow (:253-256)
+                                const int idx = (int)(unsigned int)(k & 0xffffffffull);
+                                const uint32_t m = (idx < P.ntri) ? __float_as_uint(P.normal_mat[idx].w) : __float_as_uint(P.spheres[2 * (idx - P.ntri) + 1].x);
+                                const float4 ks_tr = P.materials[4 * m + 2];
+                                const uint32_t flags = __float_as_uint(P.materials[4 * m + 3].x);
+                                lit = (flags & RT_HAS_TR) && (ks_tr.w < 1.0f);
+                            }
+                        }
+                        if (!lit) P.lit[s] &= ~(1u << l);
+                    }
+                    __syncthreads();
+                }
+            }
+            if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)nhit * P.nlights * (unsigned long long)P.ntri);
+        }
+        __syncthreads();
+        // (4) shading + continuation rays
+        shade_hits(P, level, tid, T);
+        __syncthreads();
     }
 }
 

@@ -775,8 +775,8 @@ def test_reflection_pencils_are_invisible(gpu, port):
             st1 = gpu.stats()
             if expect:
                 assert (st1["variant"] & 32) and st1["mirror_rays"] > 0, (name, st1["variant"], st1["mirror_rays"])
-            elif expect is None and name == "balls_default_camera":
-                assert st1["mirror_rays"] == 0, name
+            elif name == "balls_default_camera":      # the water group cannot be served (h = 0); a few rays off other small groups may be
+                assert st1["mirror_rays"] < 0.01 * st1["bounce_rays"], name
             assert np.array_equal(prim0, prim1), name
             assert np.array_equal(bits(rgb0), bits(rgb1)), f"{name}: {np.count_nonzero(bits(rgb0) != bits(rgb1))} framebuffer words differ"
             for k in ("primary_rays", "shadow_rays", "bounce_rays"):
@@ -793,3 +793,51 @@ def test_reflection_pencils_are_invisible(gpu, port):
         assert st["mirror_rays"] > 0.15 * st["bounce_rays"], (st["mirror_rays"], st["bounce_rays"])
     finally:
         gpu.set_option(binding.RT_OPT_PENCIL_REFLECT, 1)
+
+
+def test_small_trace_batches_take_one_launch(gpu, port):
+    """RT_OPT_SMALL_TRACE (default on): rt_trace batches of <= 32 rays run the whole recursion in one launch of one CTA
+    (k_trace_small, exact tests only).  Colour bits, primitive ids and hit points must equal the wavefront path's and the
+    oracle's -- on shadow_test (deep recursion), the glass room (refraction, transparent occluders: nearest-occluder shadow
+    rule), and the stand-in with analytic spheres."""
+    import ctypes as C
+    from raytracert_b200 import binding, scenes
+    z = np.load(GOLDEN + "/trace_shadow_test.npz")
+    glass = load_scene("glass")
+    balls = scenes.balls_with_sphere_primitives(grid=16)
+    rng = np.random.default_rng(5)
+    o2 = rng.uniform(-1.5, 1.5, (64, 3)).astype(np.float32); o2[:, 1] = rng.uniform(0.3, 2.5, 64); o2[:, 2] = rng.uniform(2.0, 4.0, 64)
+    d2 = (rng.uniform(-1.0, 1.0, (64, 3)) * np.array([1, 0.5, 1]) + np.array([0, 0.6, -0.5])).astype(np.float32)
+    o3 = o2 * np.array([1.5, 1.0, 1.2], np.float32) + np.array([0, 1.0, 1.0], np.float32)
+    d3 = (rng.uniform(-1.2, 1.2, (64, 3)) * np.array([1, 0.3, 1]) + np.array([0, 0.9, 0.0])).astype(np.float32)
+    try:
+        for name, s, eye, lights, lvl, o, d in (("shadow_test", load_scene("shadow_test"), z["eye"], [z["eye"]], 10, z["origins"][:96], z["dests"][:96]),
+                                                  ("glass", glass, (0.3, 1.6, 4.2), [(1.5, 2.8, 2.5), (-1.0, 2.0, 1.0)], 6, o2, d2),
+                                                  ("balls_spheres", balls, (0.0, 2.6, 5.2), [(2.5, 4.0, 3.0)], 3, o3, d3)):
+            gpu.upload_scene(s)
+            prm = binding.make_params([0] * 24, 1, 1, 1, 1, lvl, 63, eye, lights)
+            port.set_scene(s); port.configure(np.asarray(eye, np.float32), np.asarray(lights, np.float32), 63, lvl)
+            port.L.orc_set_spheres.argtypes = [C.c_int, C.c_void_p]
+            port.L.orc_set_spheres(len(s.spheres), s.spheres.ctypes.data)
+            rgb_o, prim_o, hit_o = port.trace(o, d)
+            gpu.set_option(binding.RT_OPT_SMALL_TRACE, 0)
+            rgb_w, prim_w, hit_w = gpu.trace(prm, o[:32], d[:32])
+            assert gpu.stats()["n_launches"] > 4
+            gpu.set_option(binding.RT_OPT_SMALL_TRACE, 1)
+            for lo, n in ((0, 1), (1, 1), (2, 5), (7, 25), (0, 32)):
+                rgb, prim, hit = gpu.trace(prm, o[lo:lo + n], d[lo:lo + n])
+                st = gpu.stats()
+                assert st["n_launches"] == 1, (name, st["n_launches"])
+                assert np.array_equal(prim, prim_o[lo:lo + n]), (name, lo, n)
+                assert np.array_equal(prim, prim_w[lo:lo + n]) and np.array_equal(bits(hit), bits(hit_w[lo:lo + n])), (name, lo, n)
+                ok = np.isfinite(rgb_w[lo:lo + n])
+                assert np.array_equal(bits(rgb[ok]), bits(rgb_w[lo:lo + n][ok])), (name, lo, n)
+                assert np.abs(rgb[ok] - rgb_o[lo:lo + n][ok]).max() <= RGB_TOL, (name, lo, n)
+            # ray counters of a small batch: primary = n, the rest as the oracle counts them
+            port.reset_counts(); port.trace(o[:8], d[:8])
+            gpu.trace(prm, o[:8], d[:8])
+            st = gpu.stats()
+            assert (st["shadow_rays"], st["bounce_rays"]) == port.ray_counts()[1:], name
+    finally:
+        gpu.set_option(binding.RT_OPT_SMALL_TRACE, 1)
+        port.L.orc_set_spheres(0, None)
