@@ -389,8 +389,8 @@ def main():
     ms_e2e = float(np.mean(e2e_steps))
     ms_cull = float(np.mean(cull_steps))
     parts = [float(np.mean(e2e_parts[k])) for k in ("upload_ms", "render_ms", "download_ms")]
-    counts = np.array([st["primary_rays"], st["shadow_rays"], st["bounce_rays"], st["exact_evals"]], np.float64)
-    kinds = np.array([st["ms_trace"], st["ms_shadow"], st["ms_shade"], st["ms_resolve"], st["ms_gather"], st["ms_trace_primary"]], np.float64)
+    counts = np.array([st["primary_rays"], st["shadow_rays"], st["bounce_rays"], st["exact_evals"], st["mirror_rays"]], np.float64)
+    kinds = np.array([st["ms_trace"], st["ms_shadow"], st["ms_shade"], st["ms_resolve"], st["ms_gather"], st["ms_trace_primary"], st["ms_trace_mirror"]], np.float64)
     if multi_rank:
         import torch.distributed as td
         t = torch.tensor([ms_dev, ms_e2e, ms_cull] + parts + list(kinds), dtype=torch.float64, device=f"cuda:{local}")
@@ -415,7 +415,8 @@ def main():
         variant = int(st["variant"])
         pencil_primary, pencil_shadow = bool(variant & 2), bool(variant & 4)
         ms_primary = float(kinds[5])
-        ms_bounce = float(kinds[0] - kinds[5])
+        ms_mirror = float(kinds[6])
+        ms_bounce = float(kinds[0] - kinds[5] - kinds[6])     # generic scans of the bounce levels
 
         def kernel_row(key, name, rays_gpu, ms, executed):
             a = FLOPS_PER_TEST * rays_gpu * ntri / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
@@ -426,7 +427,8 @@ def main():
                     "fma_pipe_active_ncu": m.get("fma_pipe_cycles_active_pct"), "issue_active_ncu": m.get("issue_active_pct"),
                     "dram_bytes_ncu": m.get("dram_bytes"), "ncu_launch": m.get("launch")}
         rows = [kernel_row("primary", "k_trace primary (%s filter)" % ("pencil" if pencil_primary else "generic"), counts[0] / world, ms_primary, 12 if pencil_primary else 27),
-                kernel_row("bounce", "k_trace bounce levels (generic filter)", counts[2] / world, ms_bounce, 27),
+                kernel_row("bounce", "k_trace bounce levels (generic filter)", (counts[2] - counts[4]) / world, ms_bounce, 27),
+                kernel_row("mirror", "k_trace level-1 rays of plane groups (mirror pencil)", counts[4] / world, ms_mirror, 12),
                 kernel_row("shadow", "k_shadow any-hit (%s filter)" % ("pencil" if pencil_shadow else "generic"), counts[1] / world, float(kinds[1]), 12 if pencil_shadow else 27)]
         dom = max(rows, key=lambda r: r["ms"])
         ach = dom["achieved"]
@@ -445,15 +447,16 @@ def main():
                 "note": "achieved/frac count 42 algorithmic flop per test (general-ray form, SURVEY 8d) for the dominant launch kind. by_kernel[].algorithmic_ratio is the same "
                         "quotient per kind and is not a utilisation: the pencil kernels do a test in 12 executed flop (rays through a common point need no origin arithmetic), "
                         "any-hit rays stop at their first occluder. The pipe-level figures are executed_frac_from_hot_loop and fma_pipe_active_ncu.",
-                "ms_by_kernel": dict(zip(["k_trace", "k_shadow", "k_shade", "k_resolve", "gather", "k_trace_primary"], [float(x) for x in kinds]))}
+                "ms_by_kernel": dict(zip(["k_trace", "k_shadow", "k_shade", "k_resolve", "gather", "k_trace_primary", "k_trace_mirror"], [float(x) for x in kinds]))}
         line = {"metric": METRIC, "value": rays / ms_dev / 1e3, "unit": "Mrays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_for(args.workload, desc, scene, W, H, pf, lvl, len(lights), world),
                 "run": {"mode": "single process, rt_init(N)" if single else "one process per GPU (torchrun), rt_init_rank", "rays_per_frame": rays,
-                        "primary": counts[0], "shadow": counts[1], "bounce": counts[2], "exact_reevaluations": counts[3],
+                        "primary": counts[0], "shadow": counts[1], "bounce": counts[2], "bounce_served_by_mirror_pencils": counts[4], "exact_reevaluations": counts[3],
                         "primary_mrays_per_s": counts[0] / ms_dev / 1e3,
-                        "filter": {"primary": "pencil" if variant & 2 else "generic", "shadow": "pencil" if variant & 4 else "generic", "bounce": "generic",
+                        "filter": {"primary": "pencil" if variant & 2 else "generic", "shadow": "pencil" if variant & 4 else "generic",
+                                   "bounce": "generic + mirror pencils" if variant & 32 else "generic",
                                    "clause_free": bool(variant & 1), "pencil_without_premise": bool(variant & 8), "graph_replay": bool(variant & 16)},
                         "l2": "flushed between timed iterations (256 MiB write per device)", "wall_s_timed_region": t_wall},
                 "clocks": clocks,

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -533,7 +534,8 @@ void apply_pencil(FrameParams& P, const RtDevice& d, const PencilPlan& plan, int
 // (no tile culling), the clause-free proof holds (pairs with |cos| < cos_min are certain misses in the reference), and
 // the geometric launch conditions of pencil_camera_setup / pencil_light_setup.
 int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
-    plan = PencilPlan();
+    memset(static_cast<void*>(&plan), 0, sizeof(plan));   // (the plan's bytes are part of the graph key: no stack garbage in unused entries)
+    new (&plan) PencilPlan;                               // default-initialisation: the member initialisers run, the rest stays zero
     // premise: the scene-level clause-free proof holds (pairs below cos_min are certain misses in the reference).  Without it
     // the pencil is used only under RT_OPT_PENCIL_ANY (experimental): near-plane triangles become "always candidate" records.
     const bool premise = d.no_grazing;
@@ -1163,8 +1165,10 @@ int rt_upload_scene(const rt_scene* sc) {
                 float inv = 1.0f / std::sqrt(l2n);
                 if (cx < 0.f || (cx == 0.f && (cy < 0.f || (cy == 0.f && cz < 0.f)))) inv = -inv;
                 const float qx = cx * inv, qy = cy * inv, qz = cz * inv, qd = qx * A[0] + qy * A[1] + qz * A[2];
-                const int64_t ix = (int64_t)std::lrintf(qx * 16384.f) + 16384, iy = (int64_t)std::lrintf(qy * 16384.f) + 16384, iz = (int64_t)std::lrintf(qz * 16384.f) + 16384;
-                const int64_t id = (int64_t)std::lrintf(std::fmin(std::fmax(qd * 1024.f, -2.0e6f), 2.0e6f)) + (1 << 21);
+                // round to nearest by truncating a positive number (components are in [-1, 1]; the offset is clamped)
+                const int64_t ix = (int64_t)(int)(qx * 16384.f + 16384.5f), iy = (int64_t)(int)(qy * 16384.f + 16384.5f), iz = (int64_t)(int)(qz * 16384.f + 16384.5f);
+                const float qdc = qd * 1024.f;
+                const int64_t id = (int64_t)(int)((qdc < -2.0e6f ? -2.0e6f : (qdc > 2.0e6f ? 2.0e6f : qdc)) + 2097152.5f);
                 key = ((uint64_t)ix << 48) ^ ((uint64_t)iy << 32) ^ ((uint64_t)iz << 16) ^ ((uint64_t)id * 0x9E3779B97F4A7C15ull) | 1ull;
             }
             pkey[i] = key;
@@ -1189,8 +1193,11 @@ int rt_upload_scene(const rt_scene* sc) {
     if (!grp.data()) return fail(RT_ERR_CUDA, "out of host memory for the scene staging buffers");
     {
         uint64_t top_key[kMaxMirrors]; uint32_t top_cnt[kMaxMirrors], top_first[kMaxMirrors]; int ntop = 0;
+        // a group must be worth a set of pencil records and two launches per frame: at least 2 triangles and 0.1 % of the scene
+        // (the two triangles of a cube face qualify; the planar quads of a finely tessellated sphere do not)
+        const uint32_t min_count = std::max(2u, n / 1000u);
         for (const PlaneSlot& ps : ptab) {
-            if (ps.count < 2 || !ps.key) continue;
+            if (ps.count + 16 < min_count || ps.count < 2 || !ps.key) continue;   // (the table's counts are lower bounds: exact counts below)
             int at = ntop < kMaxMirrors ? ntop++ : -1;
             if (at < 0) { int w = 0; for (int k = 1; k < kMaxMirrors; ++k) if (top_cnt[k] < top_cnt[w]) w = k; if (top_cnt[w] < ps.count) at = w; }
             if (at >= 0) { top_key[at] = ps.key; top_cnt[at] = ps.count; top_first[at] = ps.first; }
@@ -1210,7 +1217,7 @@ int rt_upload_scene(const rt_scene* sc) {
             Global::PlaneGroup pg;
             for (int a = 0; a < 3; ++a) pg.n[a] = l > 0.0 ? nn[a] / l : 0.0;
             pg.d = pg.n[0] * A[0] + pg.n[1] * A[1] + pg.n[2] * A[2];
-            pg.count = members[k];
+            pg.count = members[k] >= min_count ? members[k] : 0;   // count 0: never served (plan_pencil)
             g.planes.push_back(pg);   // a degenerate first member (l == 0) fails pencil_mirror_setup later: the group is simply not served
         }
     }
