@@ -25,7 +25,9 @@ def kind_of(name):
     args = [a.strip() for a in m.group(2).split(",")]
     if m.group(1) == "k_shadow":
         return "shadow"
-    return "primary" if args[3] in ("1", "true") else "bounce"
+    if args[3] in ("1", "true"):
+        return "primary"
+    return "mirror" if len(args) > 6 and args[6] in ("1", "true") else "bounce"   # queued rays through the pencil filter: a plane group's mirror pencil
 
 
 def main():

@@ -13,6 +13,8 @@ import numpy as np
 import bench
 from raytracert_b200 import binding, dist, host
 
+bench.guard_stdout()   # NCCL's banner and friends go to stderr; stdout carries the one JSON line only
+
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="sphere1m")
 ap.add_argument("--frames", type=int, default=1)
@@ -87,7 +89,7 @@ if rank == 0:
         out["oracle_lattice"]["id_mismatches"] = int(np.count_nonzero(po != pg))
     if args.cpu_pixels > 0:
         out["cpu_baseline"] = bench.cpu_baseline_block(scene, cam, pf, lvl, lights, os.cpu_count() or 1, args.cpu_pixels)
-    print(json.dumps(out), flush=True)
+    bench.emit(out)
 R.shutdown()
 if world > 1:
     import torch.distributed as td

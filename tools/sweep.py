@@ -12,7 +12,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
     os.environ["NCCL_DEBUG"] = "WARN"
 import numpy as np
+import bench
 from raytracert_b200 import binding, dist, host, scenes
+
+bench.guard_stdout()   # NCCL's banner and friends go to stderr; stdout carries the JSON rows only
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--sizes", default="512,1024,2048")
@@ -61,7 +64,7 @@ for W in [int(x) for x in args.sizes.split(",")]:
                 row[mode].update({"fp32_algorithmic_tflops_per_gpu": alg, "algorithmic_ratio": alg / PEAK, "fp32_executed_tflops_per_gpu": ex,
                                   "executed_frac_of_fp32_peak": ex / PEAK, "ms_primary_bounce_shadow": kinds})
         if rank == 0:
-            print(json.dumps(row), flush=True)
+            bench.emit(row)
 R.set_option(binding.RT_OPT_TILE_CULLING, 0)
 R.shutdown()
 if world > 1:
