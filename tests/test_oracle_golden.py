@@ -107,3 +107,34 @@ def test_refraction_angle_threshold_matches_libm():
         x = f(b)
         assert (m.acosf(x) <= 2.0) == (x >= f(T)), hex(b)
     assert not (m.acosf(np.float32(-1.0000001)) <= 2.0)      # NaN: refraction branch on both sides
+
+
+def test_headline_pin_is_the_bench_frame(port):
+    """tests/golden/pins/balls.npz (the whole 800x800x16 headline frame rendered by the unmodified reference,
+    tools/make_headline_pin.py) must describe the frame bench.py renders today: same scene bytes, camera, lights -- and the
+    port oracle, which the fixtures pin to the reference bit for bit, must reproduce one of its rows (ids and u8)."""
+    import os, sys, zlib
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    from raytracert_b200 import host
+    path = os.path.join(ROOT, "tests", "golden", "pins", "balls.npz")
+    if not os.path.exists(path):
+        pytest.skip("pin not generated")
+    z = np.load(path)
+    scene, W, H, pf, lvl, eye, center, lights, _ = bench.workload("balls")
+    cam = host.Camera(W, H, eye, center)
+    c = 0
+    for a in (scene.vertices, scene.indices, scene.tri_material, scene.materials):
+        c = zlib.crc32(np.ascontiguousarray(a).tobytes(), c)
+    assert np.uint32(c) == z["scene_crc"] and int(z["n_triangles"]) == scene.n_triangles
+    assert np.array_equal(cam.corners, z["corners"]) and np.array_equal(np.asarray(lights, np.float32), z["lights"])
+    assert (W, H, pf, lvl) == (int(z["W"]), int(z["H"]), int(z["pf"]), int(z["max_lvl"])) and len(z["rows"]) == H
+    y = 470
+    port.set_scene(scene); port.configure(cam.eye, lights, 63, lvl)
+    rgb, _, prim = port.render(cam.corners, W, H, pf, pf, y0=y, ystep=H, want_samples=True)
+    row_ids = prim.reshape(H, -1)[y]
+    assert np.uint32(zlib.crc32(row_ids.astype("<i4").tobytes())) == z["id_crc"][y]
+    ids = np.frombuffer(zlib.decompress(z["ids_z"].tobytes()), "<i4").reshape(H, -1)
+    assert np.array_equal(ids[y], row_ids)
+    assert np.array_equal(port.quantise(rgb[y]), z["u8"][y])
