@@ -255,7 +255,7 @@ def parity_block(R, name, prm_ids, rank, world, single_process):
         return None
     u8 = R.download_u8()
     d = np.abs(u8[rows].astype(np.int32) - z["u8"].astype(np.int32))
-    return {"against": f"tests/golden/pins/{name}.npz -- the unmodified reference (oracle/_ref) on the whole frame",
+    return {"against": f"tests/golden/pins/{name}.npz -- the unmodified reference (oracle/_ref), {len(rows)} of the frame's {H} rows",
             "rows_checked": int(counts[0]), "rows_in_frame": H, "id_rows_mismatching": int(counts[1]), "id_mismatches": int(counts[2]) if ids is not None else None,
             "samples_checked": int(counts[0]) * prim.shape[1], "u8_off_by_more_than_1": int(np.count_nonzero(d > 1)),
             "u8_pixels_differing_frac": float(np.mean(np.any(d > 0, axis=2))), "float_rgb_max_abs_diff_note": "colour differs from the reference only through CUDA powf vs glibc powf (<= 2e-7)",
