@@ -339,7 +339,8 @@ def main():
         t1 = time.perf_counter()
         R.render(prm)
         t2 = time.perf_counter()
-        R.download_into(fb_host)
+        if rank == 0:                                 # the frame is the job's result: one host reads it back (every rank holds it after the all-gather)
+            R.download_into(fb_host)
         t3 = time.perf_counter()
         for k, v in zip(("upload_ms", "render_ms", "download_ms"), (t1 - t0, t2 - t1, t3 - t2)):
             e2e_parts[k].append(v * 1e3)
@@ -375,7 +376,8 @@ def main():
         barrier()
         cull_steps = [frame_ms() for _ in range(max(3, min(args.steps, 10)))]
         barrier()
-        R.download_into(fb_host)
+        if rank == 0:
+            R.download_into(fb_host)
         cull_identical = bool(np.array_equal(fb_host.view(np.uint32), fb_brute.view(np.uint32)))
         R.set_option(binding.RT_OPT_TILE_CULLING, 0)
         R.upload_scene(scene)
@@ -463,7 +465,7 @@ def main():
                 "e2e": {"value": rays / ms_e2e / 1e3, "unit": "Mrays/s", "ms_per_step": ms_e2e, "ms_steps_rank0": [round(x, 2) for x in e2e_steps],
                         "upload_ms": parts[0], "render_ms": parts[1], "download_ms": parts[2],
                         "h2d_bytes_per_step": int(ntri * (4 * 16 + 4) + scene.materials.shape[0] * 64 + 432), "d2h_bytes_per_step": int(fb_host.nbytes),
-                        "path": "rt_upload_scene + rt_render + rt_download_framebuffer with host buffers, every step (max over ranks of each part)"},
+                        "path": "rt_upload_scene (every rank: the scene is replicated) + rt_render + rt_download_framebuffer (rank 0: the job's one result) with host buffers, every step; max over ranks of each part"},
                 "gpu_launches": int(st["n_launches"]) * args.steps,
                 "accelerated": {"option": "RT_OPT_TILE_CULLING (opt-in; not the brute-force contract path, not used for value/e2e/roofline)",
                                 "ms_per_step": ms_cull, "value": rays / ms_cull / 1e3, "unit": "Mrays/s", "image_bit_identical_to_brute_force": cull_identical},

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rt_kernels.cuh"
@@ -1126,63 +1127,103 @@ int rt_upload_scene(const rt_scene* sc) {
     constexpr uint32_t kPlaneSlots = 4096;
     static std::vector<PlaneSlot> ptab;
     static std::vector<uint64_t> pkey;
-    ptab.assign(kPlaneSlots, PlaneSlot{0, 0, 0});
     pkey.resize(n);
+    // The pass runs on up to 4 host threads over contiguous triangle ranges (it is the fixed cost of every end-to-end step:
+    // 1.3 ms single-threaded for the 44,672-triangle headline scene); every thread keeps its own bounds, class counts and plane
+    // table, merged below.
+    struct Part {
+        size_t cnt[4] = {0, 0, 0, 0};
+        float extent = 0.f;
+        double max_uuvv = 0.0;
+        bool unit_normals = true;
+        long long bad_tri = -1;
+        uint32_t bad_mat = 0;
+        std::vector<PlaneSlot> ptab;
+    };
+    const int nthreads = n >= 16384 ? (int)std::min(4u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    static std::vector<Part> parts;
+    parts.assign((size_t)nthreads, Part());
+    for (Part& P : parts) P.ptab.assign(kPlaneSlots, PlaneSlot{0, 0, 0});
+    auto work = [&](int t) {
+        Part& P = parts[(size_t)t];
+        const uint32_t i0 = (uint32_t)((uint64_t)n * t / nthreads), i1 = (uint32_t)((uint64_t)n * (t + 1) / nthreads);
+        for (uint32_t i = i0; i < i1; ++i) {
+            const uint32_t m = sc->tri_material[i];
+            if (m >= sc->n_materials) { if (P.bad_tri < 0) { P.bad_tri = (long long)i; P.bad_mat = m; } continue; }
+            const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i, *N = sc->normal + 4 * i;
+            triv[3 * i] = make_float4(A[0], A[1], A[2], 0.f);
+            triv[3 * i + 1] = make_float4(B[0], B[1], B[2], 0.f);
+            triv[3 * i + 2] = make_float4(C[0], C[1], C[2], 0.f);
+            float4 v = make_float4(N[0], N[1], N[2], 0.f);
+            memcpy(&v.w, &m, 4);
+            nm[i] = v;
+            float e = std::fmax(std::fmax(std::fabs(A[0]), std::fabs(A[1])), std::fabs(A[2]));
+            e = std::fmax(e, std::fmax(std::fmax(std::fabs(B[0]), std::fabs(B[1])), std::fabs(B[2])));
+            e = std::fmax(e, std::fmax(std::fmax(std::fabs(C[0]), std::fabs(C[1])), std::fabs(C[2])));   // fmax drops NaN operands
+            if (e <= FLT_MAX) P.extent = std::max(P.extent, e);
+            else  // an infinite coordinate: the finite ones still count
+                for (int k = 0; k < 3; ++k) { for (const float* p3 : {A, B, C}) if (std::isfinite(p3[k])) P.extent = std::max(P.extent, std::fabs(p3[k])); }
+            const float ux = B[0] - A[0], uy = B[1] - A[1], uz = B[2] - A[2];
+            const float vx = C[0] - A[0], vy = C[1] - A[1], vz = C[2] - A[2];
+            const float nx = std::fabs(uy * vz - uz * vy), ny = std::fabs(uz * vx - ux * vz), nz = std::fabs(ux * vy - uy * vx);
+            int w = 0;
+            if (ny > nx) w = 1;
+            if (nz > (w == 1 ? ny : nx)) w = 2;   // NaN compares false: non-finite triangles land in class 0 (and are "always exact")
+            cls[i] = (uint8_t)w;
+            ++P.cnt[w];
+            {   // quantised plane (unit normal with a canonical sign, offset): coplanar triangles share the key (up to bin edges --
+                // a split group only serves fewer rays: every ray is checked against its pencil when it is routed, k_shade)
+                const float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+                const float l2n = cx * cx + cy * cy + cz * cz;
+                uint64_t key = 0;
+                if (l2n > 0.f && l2n < 1e30f) {
+                    float inv = 1.0f / std::sqrt(l2n);
+                    if (cx < 0.f || (cx == 0.f && (cy < 0.f || (cy == 0.f && cz < 0.f)))) inv = -inv;
+                    const float qx = cx * inv, qy = cy * inv, qz = cz * inv, qd = qx * A[0] + qy * A[1] + qz * A[2];
+                    // round to nearest by truncating a positive number (components are in [-1, 1]; the offset is clamped)
+                    const int64_t ix = (int64_t)(int)(qx * 16384.f + 16384.5f), iy = (int64_t)(int)(qy * 16384.f + 16384.5f), iz = (int64_t)(int)(qz * 16384.f + 16384.5f);
+                    const float qdc = qd * 1024.f;
+                    const int64_t id = (int64_t)(int)((qdc < -2.0e6f ? -2.0e6f : (qdc > 2.0e6f ? 2.0e6f : qdc)) + 2097152.5f);
+                    key = ((uint64_t)ix << 48) ^ ((uint64_t)iy << 32) ^ ((uint64_t)iz << 16) ^ ((uint64_t)id * 0x9E3779B97F4A7C15ull) | 1ull;
+                }
+                pkey[i] = key;
+                if (key) {
+                    PlaneSlot& ps = P.ptab[(uint32_t)((key * 0xD6E8FEB86659FD93ull) >> 52)];
+                    if (ps.key == key) ++ps.count;
+                    else if (ps.count <= 1) { ps.key = key; ps.count = 1; ps.first = i; }
+                    else --ps.count;   // Misra-Gries style: a heavy plane keeps its slot
+                }
+            }
+            const double p2 = (double)(ux * ux + uy * uy + uz * uz) * (double)(vx * vx + vy * vy + vz * vz);
+            P.max_uuvv = (p2 == p2) ? std::max(P.max_uuvv, p2) : INFINITY;   // NaN vertices: never claim the bound
+            const float l2 = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+            if (!(l2 <= 1.00001f)) P.unit_normals = false;
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (std::thread& th : pool) th.join();
+    }
     size_t cnt[4] = {0, 0, 0, 0};
     float extent = 0.f;
     double max_uuvv = 0.0;
     bool unit_normals = true;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t m = sc->tri_material[i];
-        if (m >= sc->n_materials) return fail(RT_ERR_INVALID, "triangle %u uses material %u of %u", i, m, sc->n_materials);
-        const float *A = sc->v0 + 4 * i, *B = sc->v1 + 4 * i, *C = sc->v2 + 4 * i, *N = sc->normal + 4 * i;
-        triv[3 * i] = make_float4(A[0], A[1], A[2], 0.f);
-        triv[3 * i + 1] = make_float4(B[0], B[1], B[2], 0.f);
-        triv[3 * i + 2] = make_float4(C[0], C[1], C[2], 0.f);
-        float4 v = make_float4(N[0], N[1], N[2], 0.f);
-        memcpy(&v.w, &m, 4);
-        nm[i] = v;
-        float e = std::fmax(std::fmax(std::fabs(A[0]), std::fabs(A[1])), std::fabs(A[2]));
-        e = std::fmax(e, std::fmax(std::fmax(std::fabs(B[0]), std::fabs(B[1])), std::fabs(B[2])));
-        e = std::fmax(e, std::fmax(std::fmax(std::fabs(C[0]), std::fabs(C[1])), std::fabs(C[2])));   // fmax drops NaN operands
-        if (e <= FLT_MAX) extent = std::max(extent, e);
-        else  // an infinite coordinate: the finite ones still count
-            for (int k = 0; k < 3; ++k) { for (const float* p3 : {A, B, C}) if (std::isfinite(p3[k])) extent = std::max(extent, std::fabs(p3[k])); }
-        const float ux = B[0] - A[0], uy = B[1] - A[1], uz = B[2] - A[2];
-        const float vx = C[0] - A[0], vy = C[1] - A[1], vz = C[2] - A[2];
-        const float nx = std::fabs(uy * vz - uz * vy), ny = std::fabs(uz * vx - ux * vz), nz = std::fabs(ux * vy - uy * vx);
-        int w = 0;
-        if (ny > nx) w = 1;
-        if (nz > (w == 1 ? ny : nx)) w = 2;   // NaN compares false: non-finite triangles land in class 0 (and are "always exact")
-        cls[i] = (uint8_t)w;
-        ++cnt[w];
-        {   // quantised plane (unit normal with a canonical sign, offset): coplanar triangles share the key (up to bin edges --
-            // a split group only serves fewer rays: every ray is checked against its pencil when it is routed, k_shade)
-            const float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
-            const float l2n = cx * cx + cy * cy + cz * cz;
-            uint64_t key = 0;
-            if (l2n > 0.f && l2n < 1e30f) {
-                float inv = 1.0f / std::sqrt(l2n);
-                if (cx < 0.f || (cx == 0.f && (cy < 0.f || (cy == 0.f && cz < 0.f)))) inv = -inv;
-                const float qx = cx * inv, qy = cy * inv, qz = cz * inv, qd = qx * A[0] + qy * A[1] + qz * A[2];
-                // round to nearest by truncating a positive number (components are in [-1, 1]; the offset is clamped)
-                const int64_t ix = (int64_t)(int)(qx * 16384.f + 16384.5f), iy = (int64_t)(int)(qy * 16384.f + 16384.5f), iz = (int64_t)(int)(qz * 16384.f + 16384.5f);
-                const float qdc = qd * 1024.f;
-                const int64_t id = (int64_t)(int)((qdc < -2.0e6f ? -2.0e6f : (qdc > 2.0e6f ? 2.0e6f : qdc)) + 2097152.5f);
-                key = ((uint64_t)ix << 48) ^ ((uint64_t)iy << 32) ^ ((uint64_t)iz << 16) ^ ((uint64_t)id * 0x9E3779B97F4A7C15ull) | 1ull;
-            }
-            pkey[i] = key;
-            if (key) {
-                PlaneSlot& ps = ptab[(uint32_t)((key * 0xD6E8FEB86659FD93ull) >> 52)];
-                if (ps.key == key) ++ps.count;
-                else if (ps.count <= 1) { ps.key = key; ps.count = 1; ps.first = i; }
-                else --ps.count;   // Misra-Gries style: a heavy plane keeps its slot
-            }
+    ptab.assign(kPlaneSlots, PlaneSlot{0, 0, 0});
+    for (const Part& P : parts) {
+        if (P.bad_tri >= 0) return fail(RT_ERR_INVALID, "triangle %lld uses material %u of %u", P.bad_tri, P.bad_mat, sc->n_materials);
+        for (int c = 0; c < 4; ++c) cnt[c] += P.cnt[c];
+        extent = std::max(extent, P.extent);
+        max_uuvv = (P.max_uuvv == P.max_uuvv) ? std::max(max_uuvv, P.max_uuvv) : INFINITY;
+        unit_normals = unit_normals && P.unit_normals;
+        for (uint32_t k = 0; k < kPlaneSlots; ++k) {   // same hash, same slot: equal keys add up, otherwise the heavier plane stays
+            const PlaneSlot& ps = P.ptab[k];
+            PlaneSlot& out = ptab[k];
+            if (!ps.key || !ps.count) continue;
+            if (out.key == ps.key) out.count += ps.count;
+            else if (ps.count > out.count) out = ps;
         }
-        const double p2 = (double)(ux * ux + uy * uy + uz * uz) * (double)(vx * vx + vy * vy + vz * vz);
-        max_uuvv = (p2 == p2) ? std::max(max_uuvv, p2) : INFINITY;   // NaN vertices: never claim the bound
-        const float l2 = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
-        if (!(l2 <= 1.00001f)) unit_normals = false;
     }
     g.max_uv = (float)std::min(std::sqrt(max_uuvv) * 1.0001, 1e30);
     g.unit_normals = unit_normals;
