@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+N=8; O=gpurun_out/r2j; mkdir -p $O
+RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
+$RUN bench.py --gpus $N --steps 10 --warmup 3 > $O/C2_bench_n$N.json 2> $O/C2_bench_n$N.err; echo "C2 rc=$?" | tee -a $O/summary.txt
+python bench.py --gpus $N --single-process --steps 10 --warmup 3 --no-cpu-baseline --no-accelerated > $O/C2_bench_single_process_n$N.json 2> $O/C2_bench_single_process_n$N.err; echo "C2 single-process rc=$?" | tee -a $O/summary.txt
+$RUN bench.py --gpus $N --impl reference --steps 3 --warmup 1 > $O/C2_reference_arm_n$N.json 2> $O/C2_reference_arm_n$N.err; echo "reference arm rc=$?" | tee -a $O/summary.txt
