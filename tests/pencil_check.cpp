@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../raytracert_b200/csrc/rt_pencil.h"
+#include "../raytracert_b200/csrc/rt_tpencil.h"
 
 using namespace rt;
 
@@ -287,6 +288,104 @@ int generic_check(int mode, double M, float bmin, int ntri, const float* tri, in
     R.pairs = pairs; R.ref_hits = ref_hits; R.candidates = cands; R.violations = viol;
     R.first_bad_ray = bad_ray; R.first_bad_tri = bad_tri;
     *out = R;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thread pencils (rt_tpencil.h): continuation rays grouped by the triangle their primary ray hit; the rays of a group share
+// the mirror image of `eye` about that triangle's plane.  Replays what k_tp_route / k_trace_tp do: tp_mirror_point,
+// tp_accepts (a refused ray goes to the generic scan: counted as unsafe), groups of R accepted rays of one reflector in
+// input order, tp_thread_consts from the group's smallest lam_o, and for EVERY (ray, triangle) pair tp_orient + the hot
+// test (tp_weights / near) + the cold path's full test (tp_candidate) with the tightest admissible "nearest so far".
+// ray_tri[r]: the reflector of ray r.  out->candidates counts the HOT candidates (what enters the cold path),
+// out->grazing_skipped the pairs that pass the full test with no distance bound (what would be evaluated exactly at most).
+// ------------------------------------------------------------------------------------------------
+int tpencil_check(const double* eye3, double delta_cam, double M_scene, const float* box_lo, const float* box_hi, int ntri, const float* tri, int nrays,
+                  const float* rays, const int32_t* ray_tri, int R, pair_fn_t pair_fn, PencilCheckResult* out) {
+    PencilCheckResult res;
+    memset(&res, 0, sizeof(res));
+    res.first_bad_ray = res.first_bad_tri = -1;
+    TpSetup S;
+    memset(&S, 0, sizeof(S));
+    const bool ok = tp_setup(eye3, delta_cam, M_scene, box_lo, box_hi, S);
+    res.setup_ok = ok ? 1 : 0;
+    if (!ok) { *out = res; return 0; }
+    res.delta = S.delta; res.M = S.M; res.cos_g = S.cg_floor;
+    std::vector<float> rec((size_t)ntri * 24);
+    std::vector<uint8_t> state(ntri);   // 0 record, 1 always-exact (outside the filter), 2 never
+    for (int i = 0; i < ntri; ++i) {
+        const float *A = tri + 9 * i, *B = A + 3, *C = A + 6;
+        float* q = &rec[(size_t)24 * i];
+        const float u[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, v[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+        const float n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+        const float uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], uv = u[0] * v[0] + u[1] * v[1] + u[2] * v[2], vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+        const float Df = uv * uv - uu * vv;
+        if (n[0] == 0.f && n[1] == 0.f && n[2] == 0.f) { state[i] = 2; tp_never(q); ++res.never_recs; continue; }
+        const FilterTol t = filter_tolerances(A, B, C, dominant_axis(A, B, C), M_scene);
+        if (t.always || !(std::fabs(Df) > 0.f) || !std::isfinite(Df)) { state[i] = 1; tp_never(q); ++res.always_tris; continue; }
+        if (!tp_record(A, B, C, t.E0, t.E1, S, q)) { state[i] = 2; ++res.never_recs; }
+    }
+    // accepted rays per reflector, in input order
+    std::vector<std::vector<int>> by_tri(ntri);
+    std::vector<TpRay> tr(nrays);
+    std::vector<float> Es((size_t)ntri * 3, 0.f);
+    std::vector<uint8_t> has_E(ntri, 0);
+    int64_t unsafe = 0;
+    for (int r = 0; r < nrays; ++r) {
+        const int t = ray_tri[r];
+        if (t < 0 || t >= ntri) { ++unsafe; continue; }
+        const float* T = tri + 9 * t;
+        if (!has_E[t]) has_E[t] = tp_mirror_point(S.eye, S.centerf, T, T + 3, T + 6, &Es[(size_t)3 * t]) ? 1 : 2;
+        if (has_E[t] != 1 || !tp_accepts(S, &Es[(size_t)3 * t], rays + 6 * r, rays + 6 * r + 3, tr[r])) { ++unsafe; continue; }
+        by_tri[t].push_back(r);
+    }
+    std::vector<std::pair<int, int>> groups;   // (reflector, first index into by_tri[reflector])
+    for (int t = 0; t < ntri; ++t)
+        for (size_t g0 = 0; g0 < by_tri[t].size(); g0 += (size_t)R) groups.emplace_back(t, (int)g0);
+    int64_t pairs = 0, ref_hits = 0, cands = 0, viol = 0, full = 0;
+    int bad_ray = -1, bad_tri = -1;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : pairs, ref_hits, cands, viol, full)
+    for (size_t g = 0; g < groups.size(); ++g) {
+        const int t = groups[g].first;
+        const std::vector<int>& list = by_tri[t];
+        const size_t g0 = (size_t)groups[g].second, g1 = std::min(list.size(), g0 + (size_t)R);
+        const float* E = &Es[(size_t)3 * t];
+        float lam_min_thread = FLT_MAX;
+        for (size_t k = g0; k < g1; ++k) lam_min_thread = std::fmin(lam_min_thread, tr[list[k]].lam_o);
+        float cg, near_thr;
+        tp_thread_consts(S, lam_min_thread, cg, near_thr);
+        for (int i = 0; i < ntri; ++i) {
+            TpTri T;
+            tp_orient(&rec[(size_t)24 * i], E, near_thr, T);
+            const float* V = tri + 9 * i;
+            for (size_t k = g0; k < g1; ++k) {
+                const int r = list[k];
+                const float *O = rays + 6 * r, *D = O + 3;
+                ++pairs;
+                float dist = 0.f;
+                const int hit = pair_fn(O, D, V, V + 3, V + 6, &dist);
+                const bool hot = !(tp_weights(T, tr[r]) >> 31) || T.near_;
+                if (hot) ++cands;
+                const float lam_lo = nextafterf(tr[r].lam_o - S.lam_slack, -INFINITY);
+                if (tp_candidate(T, tr[r], FLT_MAX, lam_lo, cg)) ++full;
+                if (hit && dist < FLT_MAX) {
+                    ++ref_hits;
+                    if (state[i] == 1) continue;   // always-exact triangle: evaluated outside the filter
+                    const float nearest = nextafterf(dist, INFINITY);
+                    float lam_hi = round_up_sum(tr[r].lam_o, round_up_sum(nearest, S.lam_slack));
+                    if (!(lam_hi < FLT_MAX)) lam_hi = FLT_MAX;
+                    if (!hot || !tp_candidate(T, tr[r], lam_hi, lam_lo, cg)) {
+                        ++viol;
+#pragma omp critical
+                        if (bad_ray < 0) { bad_ray = r; bad_tri = i; }
+                    }
+                }
+            }
+        }
+    }
+    res.pairs = pairs; res.ref_hits = ref_hits; res.candidates = cands; res.violations = viol; res.grazing_skipped = full; res.unsafe_rays = unsafe;
+    res.first_bad_ray = bad_ray; res.first_bad_tri = bad_tri;
+    *out = res;
     return 0;
 }
 

@@ -21,6 +21,7 @@ from conftest import ROOT
 SO = os.path.join(ROOT, "raytracert_b200", "_build", "pencil_check.so")
 SRC = os.path.join(ROOT, "tests", "pencil_check.cpp")
 HDR = os.path.join(ROOT, "raytracert_b200", "csrc", "rt_pencil.h")
+HDR2 = os.path.join(ROOT, "raytracert_b200", "csrc", "rt_tpencil.h")
 
 
 class Result(C.Structure):
@@ -30,7 +31,7 @@ class Result(C.Structure):
 
 @pytest.fixture(scope="session")
 def checker(port):
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(HDR), os.path.getmtime(HDR2)):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", SO, SRC], check=True)
     L = C.CDLL(SO)
@@ -55,6 +56,18 @@ def checker(port):
         return r
     run.near_planes = 0
     run.set_plane = lambda n, d: L.pencil_check_set_plane(float(n[0]), float(n[1]), float(n[2]), float(d))
+    L.tpencil_check.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_void_p, C.POINTER(Result)]
+
+    def run_tp(eye, delta_cam, M, box_lo, box_hi, tris, rays, ray_tri, R=8):
+        eye = np.ascontiguousarray(eye, np.float64); lo = np.ascontiguousarray(box_lo, np.float32); hi = np.ascontiguousarray(box_hi, np.float32)
+        tris_ = np.ascontiguousarray(tris, np.float32).reshape(-1, 9); rays_ = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        rt = np.ascontiguousarray(ray_tri, np.int32)
+        r = Result()
+        L.tpencil_check(eye.ctypes.data, float(delta_cam), float(M), lo.ctypes.data, hi.ctypes.data, len(tris_), tris_.ctypes.data, len(rays_), rays_.ctypes.data,
+                        rt.ctypes.data, int(R), pair_fn, C.byref(r))
+        return r
+    run.thread_pencil = run_tp
     return run
 
 
@@ -224,7 +237,7 @@ def test_pencil_sound_on_the_balls_standin(checker, port):
 
 def test_pencil_sound_on_a_tessellated_sphere(checker, port):
     from raytracert_b200 import host, scenes
-    s = scenes.tessellated_sphere(slices=96, stacks=49)
+    s = scenes.tessellated_sphere(slices=96, stacks=49, ground=True)
     cam = host.Camera(48, 48, (1.2, 0.9, 2.6), (0.0, 0.0, 0.0))
     total, nl = check_frame(checker, port, s, cam, 48, 48, 2, [tuple(cam.eye), (0.0, 3.0, 0.0)], step=2)
     assert total["ref_hits"] > 1000 and nl == 2
@@ -448,6 +461,54 @@ def test_shipped_mirror_pencil_is_sound(checker, port, case):
             assert res_off.violations == 0
     finally:
         checker.set_plane((0, 1, 0), 0)
+
+
+@pytest.mark.parametrize("case", ["balls", "balls_low_camera", "sphere", "room", "cube", "dodge"])
+def test_thread_pencils_are_sound(checker, port, case):
+    """Thread pencils (rt_tpencil.h, RT_OPT_PENCIL_THREAD): the level-1 continuation rays of the primary hits on ONE triangle share
+    the mirror image of the eye about that triangle's plane.  Replay of what the kernels do -- mirror point, acceptance check,
+    groups of 8 accepted rays per reflector, record + on-the-fly orientation, hot test, full test with the tightest admissible
+    distance bound -- for EVERY (continuation ray, triangle) pair against the oracle: no accepted pair may be filtered out, most
+    rays must be accepted, and the hot test must stay selective."""
+    from conftest import load_scene
+    from raytracert_b200 import host, scenes
+    if case.startswith("balls"):
+        s = scenes.balls_standin(grid=48, slices=24, stacks=12)
+        cam = host.Camera(72, 72, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0)) if case == "balls" else host.Camera(72, 48, (0.2, 0.75, 4.6), (0.0, 0.62, 0.0))
+    elif case == "sphere":
+        s = scenes.tessellated_sphere(slices=96, stacks=49, ground=True)
+        cam = host.Camera(64, 64, (1.2, 0.9, 2.6), (0.0, 0.0, 0.0))
+    elif case == "room":
+        s = scenes.mirror_room(n=12)
+        cam = host.Camera(56, 42, (0.3, 1.6, 4.2), (0, 0.8, 0))
+    elif case == "cube":
+        s = load_scene("cube")
+        cam = host.Camera(48, 48, (2.6, 2.4, 3.0), (.5, .5, .5))
+    else:
+        s = load_scene("dodge")
+        cam = host.Camera(48, 27, (.75, .55, 1.1), (.07, 0, .23))
+    tris = tri_array(s)
+    M = magnitude_bound(s, cam.corners)
+    rays = primary_rays(cam.corners, cam.W, cam.H, 3, 1)        # 9 samples per pixel: several rays per facet
+    port.set_scene(s)
+    port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
+    _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+    ok = prim >= 0
+    brays = reflected_rays(rays[ok], hit[ok], s.normals[prim[ok]])
+    t = tris.reshape(-1, 9)
+    lo = t.reshape(-1, 3).min(axis=0) - 0.01; hi = t.reshape(-1, 3).max(axis=0) + 0.01
+    # the camera pencil's centre and delta, as plan_pencil has them (the eye itself is within ~1e-6 of it)
+    res = checker.thread_pencil(np.asarray(cam.eye, np.float64), 6e-6, M, lo, hi, tris, brays, prim[ok])
+    assert res.setup_ok, case
+    assert res.violations == 0, f"{case}: {res.violations} accepted pairs filtered out (ray {res.first_bad_ray}, triangle {res.first_bad_tri})"
+    n = len(brays)
+    assert res.unsafe_rays <= 0.05 * n, f"{case}: the acceptance check refuses {res.unsafe_rays} of {n} continuation rays"
+    assert res.ref_hits > 0 or case == "cube"        # (nothing to hit around a single convex cube)
+    # selectivity: hot candidates (cold-path entries) and what survives the full test (exact evaluations at most), per accepted ray
+    acc = n - res.unsafe_rays
+    print(f"{case}: {n} rays, {res.unsafe_rays} refused, hot candidates/ray {res.candidates / acc:.2f}, full-test survivors/ray {res.grazing_skipped / acc:.2f}, "
+          f"reference hits/ray {res.ref_hits / acc:.2f}, delta {res.delta:.2e}")
+    assert res.candidates <= 40 * acc and res.grazing_skipped <= 6 * acc
 
 
 def bounce_like_rays(tris, rng, n):
