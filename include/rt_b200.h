@@ -111,10 +111,14 @@ typedef struct rt_stats {
                                                        * bit 1: pencil filter on the primary rays; bit 2: on shadow rays;
                                                        * bit 3: pencil records built without the clause-free proof;
                                                        * bit 4: the frame / batch was a CUDA-graph replay;
-                                                       * bit 5: reflection (mirror) pencils served level-1 continuation rays */
+                                                       * bit 5: reflection (mirror) pencils served level-1 continuation rays;
+                                                       * bit 6: thread pencils did */
     float ms_trace_primary;                           /* the level-0 (primary ray) part of ms_trace */
     float ms_trace_mirror;                            /* the part of ms_trace spent in mirror-pencil scans (RT_OPT_PENCIL_REFLECT) */
     uint64_t mirror_rays;                             /* level-1 continuation rays served by a mirror pencil (part of bounce_rays) */
+    uint64_t thread_pencil_rays;                      /* level-1 continuation rays served by thread pencils (part of bounce_rays) */
+    float ms_trace_thread;                            /* the part of ms_trace spent in thread-pencil scans (RT_OPT_PENCIL_THREAD) */
+    uint32_t reserved;
 } rt_stats;
 
 /* Single-process mode: use devices 0..n_gpus-1 of this box (n_gpus >= 1); rows are interleaved over
@@ -184,6 +188,12 @@ int rt_trace(const rt_params* params, int n, const float* origins, const float* 
  * launch has a fixed grid: persistent CTAs read their ray counts from device counters); rt_stats.variant bit 4.
  * 0 = never, 1 = always.  A replayed frame reports no per-kernel times (rt_stats.ms_trace .. ms_resolve are 0). */
 #define RT_OPT_GRAPH 4
+/* RT_OPT_PENCIL_THREAD (default 0): the level-1 continuation rays of the primary hits on ANY triangle leave that triangle's own
+ * mirror image of the eye; grouped by reflector (8 rays per thread), they are scanned with per-thread pencil weights built on
+ * the fly from an E-independent record (rt_tpencil.h) instead of the generic filter.  Every ray is checked against its
+ * pencil when it is spawned; rays that do not fill a group take the generic scan.  rt_stats.variant bit 6,
+ * rt_stats.thread_pencil_rays.  Identical image and ids. */
+#define RT_OPT_PENCIL_THREAD 7
 /* RT_OPT_SMALL_TRACE (default 1): rt_trace batches of at most 32 rays (and at most 1e5 ray-triangle pairs per level) -- the
  * drop-in performRayTracing(origin, dest) call is a batch of one -- run the whole recursion in ONE kernel launch of one
  * thread block with exact tests only (k_trace_small) instead of four launches per level.  0 = always the wavefront kernels. */

@@ -20,6 +20,7 @@ RT_OPT_PENCIL_ANY = 3
 RT_OPT_GRAPH = 4
 RT_OPT_PENCIL_REFLECT = 5
 RT_OPT_SMALL_TRACE = 6
+RT_OPT_PENCIL_THREAD = 7
 
 
 class RtMaterial(C.Structure):
@@ -50,7 +51,8 @@ class RtStats(C.Structure):
                 ("ms_trace", C.c_float), ("ms_shadow", C.c_float), ("ms_shade", C.c_float), ("ms_resolve", C.c_float),
                 ("ms_gather", C.c_float), ("n_gpus", C.c_uint32), ("rank", C.c_uint32),
                 ("n_triangles", C.c_uint32), ("n_levels", C.c_uint32), ("n_launches", C.c_uint32), ("variant", C.c_uint32),
-                ("ms_trace_primary", C.c_float), ("ms_trace_mirror", C.c_float), ("mirror_rays", C.c_uint64)]
+                ("ms_trace_primary", C.c_float), ("ms_trace_mirror", C.c_float), ("mirror_rays", C.c_uint64),
+                ("thread_pencil_rays", C.c_uint64), ("ms_trace_thread", C.c_float), ("reserved", C.c_uint32)]
 
 
 EXPORTS = ["rt_init", "rt_init_rank", "rt_nccl_unique_id", "rt_upload_scene", "rt_render", "rt_render_async",

@@ -98,6 +98,10 @@ struct RtDevice {
     // pencil filter (rt_pencil.h): slot 0 = records around the eye, slot 1 + l = around light l; rebuilt every frame
     float4* prec = nullptr; size_t cap_prec = 0;
     // reflection pencils: plane group of every triangle, ray queues of the groups (kMaxMirrors x cap_samples)
+    // thread pencils (rt_tpencil.h): records (rebuilt with the pencil plan), pool / grouped queue (per chunk), per-triangle tables
+    float4* trec = nullptr; size_t cap_trec = 0;
+    uint32_t *tp_pool = nullptr, *q_tp = nullptr, *tp_group_tri = nullptr; size_t cap_tp = 0;
+    uint32_t *tp_hist = nullptr, *tp_off = nullptr, *tp_cursor = nullptr; size_t cap_tp_tri = 0;
     uint8_t* tri_group = nullptr; size_t cap_group = 0;
     uint32_t* q_mirror = nullptr; size_t cap_q_mirror = 0;
     float4* scene_box = nullptr;            // device: union of the tile boxes (k_scene_box)
@@ -130,7 +134,7 @@ struct RtDevice {
     int num_sms = 148;
 };
 
-enum KernelKind { kKindTrace = 0, kKindShadow, kKindShade, kKindResolve, kKindGather, kKindTracePrimary, kKindTraceMirror, kNumKinds };
+enum KernelKind { kKindTrace = 0, kKindShadow, kKindShade, kKindResolve, kKindGather, kKindTracePrimary, kKindTraceMirror, kKindTraceThread, kNumKinds };
 constexpr size_t kMaxTimedLaunches = 4096;  // beyond this a frame's launches are still counted, not timed
 
 struct Global {
@@ -144,6 +148,7 @@ struct Global {
     ScanConfig pscan = {2, 8, 2};    // shape of the pencil kernels
     bool tile_culling = false;       // RT_OPT_TILE_CULLING
     bool pencil = true;              // RT_OPT_PENCIL: common-point filter for primary / shadow rays where it applies
+    bool pencil_thread = false;      // RT_OPT_PENCIL_THREAD: per-thread pencils for the level-1 continuation rays of every other triangle
     bool pencil_reflect = true;      // RT_OPT_PENCIL_REFLECT: mirror pencils for the level-1 continuation rays of planar reflectors
     struct PlaneGroup { double n[3], d; uint32_t count; };
     std::vector<PlaneGroup> planes;  // the (at most kMaxMirrors) largest groups of coplanar triangles of the scene; group id = index
@@ -247,7 +252,7 @@ int create_device(RtDevice& d, int device, int rank) {
 void destroy_device(RtDevice& d) {
     cudaSetDevice(d.device);
     if (d.comm && g.nccl.CommDestroy) g.nccl.CommDestroy(d.comm);
-    void* ptrs[] = {d.tri_group, d.q_mirror, d.n_near, d.prec, d.scene_box, d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
+    void* ptrs[] = {d.trec, d.tp_pool, d.q_tp, d.tp_group_tri, d.tp_hist, d.tp_off, d.tp_cursor, d.tri_group, d.q_mirror, d.n_near, d.prec, d.scene_box, d.rec, d.perm, d.n_always, d.always_list, d.tile_box, d.super_box, d.triv, d.normal_mat, d.materials, d.spheres, d.ray_o, d.ray_d, d.thr, d.acc, d.hit, d.lit, d.q_ray,
                     d.q_hit, d.key, d.hit0, d.trace_in, d.counters, d.prim, d.fb_local, d.fb_gather, d.fb_final, d.fb_u8};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -362,6 +367,7 @@ void read_tuning_env() {
     if (const char* c = getenv("RT_B200_PENCIL_ANY")) g.pencil_any = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_ANY, ..)
     if (const char* c = getenv("RT_B200_PENCIL_REFLECT")) g.pencil_reflect = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_REFLECT, ..)
     if (const char* c = getenv("RT_B200_SMALL_TRACE")) g.small_trace = atoi(c) != 0;
+    if (const char* c = getenv("RT_B200_PENCIL_THREAD")) g.pencil_thread = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_THREAD, ..)
     if (const char* c = getenv("RT_B200_GRAPH")) g.graph_mode = atoi(c) < 0 ? -1 : (atoi(c) != 0);   // same as rt_set_option(RT_OPT_GRAPH, ..)
     if (const char* pe = getenv("RT_B200_PTUNE")) {
         ScanConfig c = g.pscan;
@@ -512,7 +518,31 @@ struct PencilPlan {
     PencilSetup mirror_setup[kMaxMirrors];
     MirrorCheck mirror_check[kMaxMirrors];
     int mirror_slot0 = 0;
+    // thread pencils: level-1 continuation rays of the primary hits on any other triangle (rt_tpencil.h)
+    bool tp = false;
+    TpSetup tp_setup;
 };
+
+// Thread pencils of this frame (buffers: ensure_tp).
+void apply_tp(FrameParams& P, const RtDevice& d, const PencilPlan& plan) {
+    P.tp_on = 1;
+    P.trec = d.trec;
+    P.tp = plan.tp_setup;
+    P.tp_pool = d.tp_pool; P.q_tp = d.q_tp; P.tp_group_tri = d.tp_group_tri;
+    P.tp_hist = d.tp_hist; P.tp_off = d.tp_off; P.tp_cursor = d.tp_cursor;
+}
+int ensure_tp(RtDevice& d) {
+    if (d.cap_tp < d.cap_samples) {
+        for (uint32_t** p : {&d.tp_pool, &d.q_tp, &d.tp_group_tri}) { if (*p) cudaFree(*p); *p = nullptr; CU(cudaMalloc(p, sizeof(uint32_t) * d.cap_samples)); }
+        d.cap_tp = d.cap_samples;
+    }
+    const size_t nt = (size_t)std::max(d.ntri, 1);
+    if (d.cap_tp_tri < nt) {
+        for (uint32_t** p : {&d.tp_hist, &d.tp_off, &d.tp_cursor}) { if (*p) cudaFree(*p); *p = nullptr; CU(cudaMalloc(p, sizeof(uint32_t) * nt)); }
+        d.cap_tp_tri = nt;
+    }
+    return RT_OK;
+}
 
 // Reflection pencils of this frame: what k_shade needs to route the level-1 continuation rays (level 0 only reads it).
 void apply_mirrors(FrameParams& P, const RtDevice& d, const PencilPlan& plan) {
@@ -550,7 +580,7 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
         memcpy(k, rp.corners, sizeof(rp.corners)); k += sizeof(rp.corners);
         memcpy(k, rp.lights, sizeof(rp.lights)); k += sizeof(rp.lights);
         const uint32_t w[4] = {rp.n_lights, (rp.features & (RT_SHADOWS | RT_REFLECTION)) | (rp.max_lvl > 0 ? 1u << 16 : 0u),
-                               (uint32_t)g.pencil_any | ((uint32_t)g.pencil_reflect << 1), (uint32_t)g.any_transparent};
+                               (uint32_t)g.pencil_any | ((uint32_t)g.pencil_reflect << 1) | ((uint32_t)g.pencil_thread << 2), (uint32_t)g.any_transparent};
         memcpy(k, w, sizeof(w));
     }
     if (d.prec && key == d.plan_key && d.plan_blob.size() == sizeof(PencilPlan)) { memcpy(&plan, d.plan_blob.data(), sizeof(PencilPlan)); return RT_OK; }
@@ -598,8 +628,15 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
         }
         plan.n_mirrors = any ? (int)std::min(g.planes.size(), (size_t)kMaxMirrors) : 0;
     }
+    if (plan.cam && g.pencil_thread && (rp.features & RT_REFLECTION) && rp.max_lvl > 0)
+        plan.tp = tp_setup(plan.cam_setup.E, plan.cam_setup.delta, (double)d.M_built, d.box_lo, d.box_hi, plan.tp_setup);
     int rc = ensure(d.prec, d.cap_prec, plan.slot_vec * (size_t)(plan.mirror_slot0 + plan.n_mirrors));
     if (rc) return rc;
+    if (plan.tp) {
+        rc = ensure(d.trec, d.cap_trec, (size_t)npad * kTpVec); if (rc) return rc;
+        k_build_trec<<<(npad + 127) / 128, 128, 0, d.stream>>>(d.triv, d.rec, npad, d.cls1 * kTile, d.cls2 * kTile, d.M_built, plan.tp_setup, d.trec);
+        CU(cudaGetLastError());
+    }
     constexpr int kNearWords = 1 + RT_MAX_LIGHTS + kMaxMirrors;
     if (!d.n_near) CU(cudaMalloc(&d.n_near, sizeof(unsigned int) * kNearWords));
     if (!premise) CU(cudaMemsetAsync(d.n_near, 0, sizeof(unsigned int) * kNearWords, d.stream));
@@ -667,6 +704,28 @@ int run_wavefront(RtDevice& d, const FrameParams& P, float4* level0_hits = nullp
                     LaunchTimer t(d, kKindShade);
                     k_finish<false><<<grid_small, 256, 0, d.stream>>>(Pm, level);
                 }
+            }
+        }
+        if (level == 1 && P.tp_on && !P.trace_api) {
+            // thread pencils: group the pool k_shade filled at level 0 by reflector, scan the groups, finish them; whatever did not
+            // fill a group has been appended to the ordinary queue, which the generic launch below serves
+            {
+                LaunchTimer t(d, kKindShade);
+                k_tp_offsets<<<1, 1024, 0, d.stream>>>(P);
+            }
+            {
+                LaunchTimer t(d, kKindShade);
+                k_tp_scatter<<<grid_small, 256, 0, d.stream>>>(P);
+            }
+            FrameParams Pt = P;
+            Pt.mirror_sel = kQueueTp;
+            {
+                LaunchTimer t(d, kKindTraceThread);
+                launch_kernel_smem(k_trace_tp<4, 2>, sizeof(TpSmem), d.num_sms * 2, d.stream, Pt, level);
+            }
+            {
+                LaunchTimer t(d, kKindShade);
+                k_finish<false><<<grid_small, 256, 0, d.stream>>>(Pt, level);
             }
         }
         {
@@ -803,9 +862,10 @@ int render_enqueue_impl(const rt_params* rp) {
         rc = build_records(d, M, direction_bound(*rp, true, nullptr, nullptr, 0)); if (rc) return rc;
         PencilPlan plan;
         rc = plan_pencil(d, *rp, g.tile_culling && d.ntiles <= kCullMaxTiles, plan); if (rc) return rc;
-        d.pencil_used = (plan.cam ? 2u : 0u) | (plan.any_light ? 4u : 0u) | (plan.no_premise ? 8u : 0u) | (plan.n_mirrors > 0 ? 32u : 0u);
+        d.pencil_used = (plan.cam ? 2u : 0u) | (plan.any_light ? 4u : 0u) | (plan.no_premise ? 8u : 0u) | (plan.n_mirrors > 0 ? 32u : 0u) | (plan.tp ? 64u : 0u);
         rc = ensure_chunk_state(d, chunk_cap, rp->want_prim_id != 0, (size_t)rows_per_rank * row_samples); if (rc) return rc;
         if (plan.n_mirrors > 0) { rc = ensure(d.q_mirror, d.cap_q_mirror, (size_t)kMaxMirrors * d.cap_samples); if (rc) return rc; }
+        if (plan.tp) { rc = ensure_tp(d); if (rc) return rc; }
         rc = ensure_counters(d, std::max(1u, nchunks)); if (rc) return rc;
         size_t need_local = (size_t)rows_per_rank * W * 3;
         rc = ensure(d.fb_local, d.cap_local, need_local); if (rc) return rc;
@@ -836,6 +896,11 @@ int render_enqueue_impl(const rt_params* rp) {
                 P.sample_base = (unsigned long long)P.row0 * row_samples;
                 P.prim_out = rp->want_prim_id ? d.prim : nullptr;
                 if (plan.n_mirrors > 0) apply_mirrors(P, d, plan);
+                if (plan.tp) {
+                    apply_tp(P, d, plan);
+                    CU(cudaMemsetAsync(d.tp_hist, 0, sizeof(uint32_t) * (size_t)std::max(d.ntri, 1), d.stream));
+                    CU(cudaMemsetAsync(d.tp_cursor, 0, sizeof(uint32_t) * (size_t)std::max(d.ntri, 1), d.stream));
+                }
                 int levels = run_wavefront(d, P, nullptr, &plan);
                 if (levels < 0) return levels;
                 levels_done = levels;
@@ -859,7 +924,7 @@ int render_enqueue_impl(const rt_params* rp) {
             KeyWriter kw{key};
             kw.put(*rp); kw.put(d.rec_gen); kw.put_bytes(&plan, sizeof(plan));
             const void* ptrs[] = {d.rec, d.triv, d.normal_mat, d.materials, d.spheres, d.prec, d.tile_box, d.super_box, d.always_list, d.ray_o, d.ray_d,
-                                  d.thr, d.acc, d.hit, d.lit, d.q_ray, d.q_hit, d.key, d.counters, d.prim, d.fb_local, d.q_mirror, d.tri_group};
+                                  d.thr, d.acc, d.hit, d.lit, d.q_ray, d.q_hit, d.key, d.counters, d.prim, d.fb_local, d.q_mirror, d.tri_group, d.trec, d.tp_pool, d.q_tp, d.tp_group_tri, d.tp_hist, d.tp_off, d.tp_cursor};
             kw.put(ptrs);
             const int cfg[] = {g.scan.rp, g.scan.j, g.scan.minb, g.pscan.rp, g.pscan.j, g.pscan.minb, (int)g.tile_culling, (int)G, d.rank, d.num_sms, (int)g.any_transparent};
             kw.put(cfg);
@@ -973,6 +1038,7 @@ int collect_stats() {
                 if (l > 0) st.bounce_rays += cw[kCntRay + l];
             }
             for (int k = 0; k < kMaxMirrors; ++k) { st.bounce_rays += cw[kCntMirror + k]; st.mirror_rays += cw[kCntMirror + k]; }   // level-1 rays served by a mirror pencil
+            st.bounce_rays += (uint64_t)cw[kCntTpGroups] * kTpR; st.thread_pencil_rays += (uint64_t)cw[kCntTpGroups] * kTpR;       // ... by thread pencils
             st.exact_evals += (uint64_t)cw[kCntExact] | ((uint64_t)cw[kCntExact + 1] << 32);
         }
         float ms = 0.f;
@@ -981,7 +1047,7 @@ int collect_stats() {
         for (size_t i = 0; i < d.kev_kind.size(); ++i)
             if (d.kev_kind[i] >= 0 && cudaEventElapsedTime(&ms, d.kev[2 * i], d.kev[2 * i + 1]) == cudaSuccess) by_kind[d.kev_kind[i]] += ms;
         if (getenv("RT_B200_LAUNCHLOG")) {   // per-launch device times of the frame, in launch order (diagnostics)
-            static const char* names[kNumKinds] = {"trace", "shadow", "shade/finish", "resolve", "gather", "trace_primary", "trace_mirror"};
+            static const char* names[kNumKinds] = {"trace", "shadow", "shade/finish", "resolve", "gather", "trace_primary", "trace_mirror", "trace_thread"};
             for (size_t i = 0; i < d.kev_kind.size(); ++i)
                 if (d.kev_kind[i] >= 0 && cudaEventElapsedTime(&ms, d.kev[2 * i], d.kev[2 * i + 1]) == cudaSuccess && ms > 0.05f)
                     fprintf(stderr, "librt_b200: launch %3zu %-14s %9.3f ms\n", i, names[d.kev_kind[i]], ms);
@@ -990,7 +1056,8 @@ int collect_stats() {
                 for (int l = 0; l < 6; ++l) fprintf(stderr, "librt_b200: chunk %d level %d: %u rays in, %u hits\n", c, l, l == 0 ? 0u : cw[kCntRay + l], cw[kCntHit + l]);
             }
         }
-        st.ms_trace = std::max(st.ms_trace, by_kind[kKindTrace] + by_kind[kKindTracePrimary] + by_kind[kKindTraceMirror]);
+        st.ms_trace = std::max(st.ms_trace, by_kind[kKindTrace] + by_kind[kKindTracePrimary] + by_kind[kKindTraceMirror] + by_kind[kKindTraceThread]);
+        st.ms_trace_thread = std::max(st.ms_trace_thread, by_kind[kKindTraceThread]);
         st.ms_trace_mirror = std::max(st.ms_trace_mirror, by_kind[kKindTraceMirror]);
         st.ms_trace_primary = std::max(st.ms_trace_primary, by_kind[kKindTracePrimary]);
         st.ms_shadow = std::max(st.ms_shadow, by_kind[kKindShadow]);
@@ -1031,6 +1098,7 @@ void rt_shutdown(void) {
     g.pencil = true;
     g.pencil_any = true;
     g.pencil_reflect = true;
+    g.pencil_thread = false;
     g.small_trace = true;
     g.graph_mode = -1;
 }
@@ -1565,6 +1633,7 @@ int rt_set_option(int option, int value) {
     if (option == RT_OPT_PENCIL_REFLECT) { g.pencil_reflect = value != 0; return RT_OK; }
     if (option == RT_OPT_PENCIL_REFLECT) { g.pencil_reflect = value != 0; return RT_OK; }
     if (option == RT_OPT_SMALL_TRACE) { g.small_trace = value != 0; return RT_OK; }
+    if (option == RT_OPT_PENCIL_THREAD) { g.pencil_thread = value != 0; return RT_OK; }
     if (option == RT_OPT_GRAPH) { g.graph_mode = value < 0 ? -1 : (value != 0); return RT_OK; }
     return fail(RT_ERR_INVALID, "unknown option %d", option);
 }

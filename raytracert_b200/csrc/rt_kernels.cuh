@@ -28,6 +28,7 @@
 #pragma once
 #include "rt_common.cuh"
 #include "rt_pencil.h"
+#include "rt_tpencil.h"
 #include "../../include/rt_b200.h"
 
 namespace rt {
@@ -57,7 +58,11 @@ constexpr int kCntRay = kMaxLevels;        // [level] rays queued for k_trace at
 constexpr int kCntExact = 2 * kMaxLevels;  // 64-bit: exact re-evaluations (2 words)
 constexpr int kMaxMirrors = 4;             // reflection pencils: plane groups served per frame (rt_pencil.h: pencil_mirror_setup)
 constexpr int kCntMirror = 2 * kMaxLevels + 4;   // [group] level-1 continuation rays routed to the mirror pencil of that plane group
-constexpr int kCntWords = 2 * kMaxLevels + 4 + kMaxMirrors;
+constexpr int kCntTpPool = 2 * kMaxLevels + 4 + kMaxMirrors;       // thread pencils: level-1 continuation rays accepted into the pool
+constexpr int kCntTpGroups = kCntTpPool + 1;                      // ... and the groups of kTpR rays formed from them
+constexpr int kCntWords = 2 * kMaxLevels + 4 + kMaxMirrors + 2;
+constexpr int kTpR = 8;                    // rays per thread of the thread-pencil scan
+constexpr int kQueueTp = 100;              // FrameParams::mirror_sel value that selects the thread-pencil queue
 constexpr uint8_t kNoGroup = 0xff;
 
 struct FrameParams {
@@ -117,9 +122,25 @@ struct FrameParams {
     uint32_t q_mirror_stride;
     int mirror_sel;             // >= 0: this k_trace / k_finish launch serves the ray queue of that group; -1: the ordinary queue
     MirrorCheck mirror[kMaxMirrors];
+    // thread pencils (rt_tpencil.h): level-1 continuation rays grouped by the triangle their primary ray hit
+    int tp_on;                  // k_shade (level 0) offers eligible continuation rays to the pool
+    const float4* trec;         // thread-pencil records: kTpVec float4 per record position (same positions / tiles as rec)
+    uint32_t* tp_pool;          // accepted rays (sample ids), unsorted
+    uint32_t* tp_hist;          // [ntri] accepted rays per reflector
+    uint32_t* tp_off;           // [ntri] first group of the reflector
+    uint32_t* tp_cursor;        // [ntri]
+    uint32_t* q_tp;             // grouped queue: kTpR consecutive entries share a reflector
+    uint32_t* tp_group_tri;     // reflector of every group
+    TpSetup tp;
 };
-__device__ __forceinline__ const uint32_t* ray_queue(const FrameParams& P) { return P.mirror_sel >= 0 ? P.q_mirror + (size_t)P.mirror_sel * P.q_mirror_stride : P.q_ray; }
-__device__ __forceinline__ uint32_t ray_queue_count(const FrameParams& P, int level) { return P.mirror_sel >= 0 ? P.counters[kCntMirror + P.mirror_sel] : P.counters[kCntRay + level]; }
+__device__ __forceinline__ const uint32_t* ray_queue(const FrameParams& P) {
+    if (P.mirror_sel == kQueueTp) return P.q_tp;
+    return P.mirror_sel >= 0 ? P.q_mirror + (size_t)P.mirror_sel * P.q_mirror_stride : P.q_ray;
+}
+__device__ __forceinline__ uint32_t ray_queue_count(const FrameParams& P, int level) {
+    if (P.mirror_sel == kQueueTp) return P.counters[kCntTpGroups] * (uint32_t)kTpR;
+    return P.mirror_sel >= 0 ? P.counters[kCntMirror + P.mirror_sel] : P.counters[kCntRay + level];
+}
 
 // ------------------------------------------------------------------------------------------------
 // Filter records
@@ -316,11 +337,12 @@ __device__ __noinline__ float4 exact_eval_tri(const float4* __restrict__ triv, i
 // copies.  There is no producer warp: the LAST warp to finish a stage re-arms its mbarrier and issues the
 // copy for the tile kStages iterations ahead, so nobody ever blocks on an "empty" barrier.
 // ------------------------------------------------------------------------------------------------
-struct __align__(128) ScanSmem {
-    float4 tiles[kStages][kTile * kRecVec];
+template <int VEC> struct __align__(128) ScanSmemV {
+    float4 tiles[kStages][kTile * VEC];
     unsigned long long full[kStages];
     unsigned int done[kStages];
 };
+using ScanSmem = ScanSmemV<kRecVec>;
 // tile culling only (CULL = true kernels): tiles some ray of this CTA can reach (bitmap), and the batch being streamed
 struct CullSmem {
     unsigned int need[kCullMaxTiles / 32];
@@ -360,8 +382,8 @@ template <> struct CullStorage<false> { __device__ CullSmem& get() { return *rei
 
 // Everything a scan kernel keeps in shared memory, as ONE block of dynamic shared memory (the 8-rays-per-thread pencil
 // shape needs 57 KB: more than the 48 KB a kernel may declare statically).
-template <int R, bool CULL> struct KernelSmem {
-    ScanSmem sm;
+template <int R, bool CULL, int VEC = kRecVec> struct KernelSmem {
+    ScanSmemV<VEC> sm;
     CullStorage<CULL> csm;
     ColdStorage<R, !CULL> cold;
 };
@@ -399,6 +421,7 @@ struct Pipe {
     unsigned int* done;
     const float4* tiles_ptr;
     const float4* rec;
+    uint32_t vec;          // float4 per record of the streamed array (kRecVec, or kTpVec for the thread-pencil records)
     uint32_t parts, len;   // see Split
     uint32_t total_iters;  // tiles this CTA will consume over its whole life (range mode) / end of the current batch (list mode)
     uint32_t it;           // next iteration
@@ -420,8 +443,9 @@ __device__ __forceinline__ void pipe_issue(const Pipe& p, uint32_t iter) {
     }
     // generic-proxy reads of this stage (all warps are past it) are ordered before the async-proxy write
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_arrive_expect_tx(bar, kTileBytes);
-    tma_bulk_g2s(p.tiles_addr + stage * kTileBytes, p.rec + (size_t)tile * kTile * kRecVec, kTileBytes, bar);
+    const uint32_t bytes = kTile * p.vec * (uint32_t)sizeof(float4);
+    mbar_arrive_expect_tx(bar, bytes);
+    tma_bulk_g2s(p.tiles_addr + stage * bytes, p.rec + (size_t)tile * kTile * p.vec, bytes, bar);
 }
 
 __device__ __forceinline__ uint32_t cta_items(uint32_t nitems) {
@@ -429,8 +453,9 @@ __device__ __forceinline__ uint32_t cta_items(uint32_t nitems) {
 }
 
 // list_mode: nothing is prefetched here; every batch is started by pipe_begin_batch().
-template <bool LIST>
-__device__ __forceinline__ void pipe_init(Pipe& p, ScanSmem& sm, const float4* rec, const Split& sp, const unsigned short* list) {
+template <bool LIST, int VEC = kRecVec>
+__device__ __forceinline__ void pipe_init(Pipe& p, ScanSmemV<VEC>& sm, const float4* rec, const Split& sp, const unsigned short* list) {
+    p.vec = VEC;
     p.tiles_addr = smem_u32(&sm.tiles[0][0]);
     p.full_addr = smem_u32(&sm.full[0]);
     p.done = sm.done;
@@ -467,7 +492,7 @@ __device__ __forceinline__ void pipe_begin_batch(Pipe& p, uint32_t n) {
 __device__ __forceinline__ const float4* pipe_acquire(const Pipe& p) {
     const uint32_t stage = p.it % kStages;
     mbar_wait(p.full_addr + stage * 8u, (p.it / kStages) & 1u);
-    return p.tiles_ptr + stage * (kTile * kRecVec);
+    return p.tiles_ptr + stage * (kTile * p.vec);
 }
 
 template <bool LIST>
@@ -1412,11 +1437,22 @@ __device__ __forceinline__ void shade_hits(const FrameParams& P, int level, uint
                 K = M.Ks; nlvl = lvl + 1; spawn = true;   // traced even when Ks == 0, like the reference
                 // reflection of a PRIMARY ray off a triangle of a plane group: the mirror pencil of that plane takes the ray if
                 // (checked here, on the ray as built) its line passes through the mirror image of the eye (rt_pencil.h)
-                if (P.n_mirrors > 0 && level == 0 && idx < P.ntri) {
-                    const uint32_t g = P.tri_group[idx];
-                    if (g < (uint32_t)P.n_mirrors) {
-                        const float Of[3] = {point.x, point.y, point.z}, Df[3] = {dest.x, dest.y, dest.z};
-                        if (pencil_mirror_accepts(P.mirror[g], Of, Df)) group = (int)g;
+                if ((P.n_mirrors > 0 || P.tp_on) && level == 0 && idx < P.ntri) {
+                    const float Of[3] = {point.x, point.y, point.z}, Df[3] = {dest.x, dest.y, dest.z};
+                    if (P.n_mirrors > 0) {
+                        const uint32_t g = P.tri_group[idx];
+                        if (g < (uint32_t)P.n_mirrors && pencil_mirror_accepts(P.mirror[g], Of, Df)) group = (int)g;
+                    }
+                    // ... or off any other triangle: its own mirror image of the eye, shared by the rays of a thread (rt_tpencil.h)
+                    if (group < 0 && P.tp_on) {
+                        const float4 A = P.triv[3 * idx], B = P.triv[3 * idx + 1], C = P.triv[3 * idx + 2];
+                        const float Af[3] = {A.x, A.y, A.z}, Bf[3] = {B.x, B.y, B.z}, Cf[3] = {C.x, C.y, C.z};
+                        float E[3];
+                        TpRay tr;
+                        if (tp_mirror_point(P.tp.eye, P.tp.centerf, Af, Bf, Cf, E) && tp_accepts(P.tp, E, Of, Df, tr)) {
+                            group = kQueueTp;
+                            atomicAdd(&P.tp_hist[idx], 1u);
+                        }
                     }
                 }
             }
@@ -1427,6 +1463,7 @@ __device__ __forceinline__ void shade_hits(const FrameParams& P, int level, uint
             }
         }
         warp_append(spawn && group < 0, s, P.q_ray, &P.counters[kCntRay + level + 1]);
+        if (P.tp_on && level == 0) warp_append(spawn && group == kQueueTp, s, P.tp_pool, &P.counters[kCntTpPool]);
         for (int g = 0; g < P.n_mirrors; ++g)   // (0 unless this is level 0 of a frame with mirror pencils)
             warp_append(spawn && group == g, s, P.q_mirror + (size_t)g * P.q_mirror_stride, &P.counters[kCntMirror + g]);
     }
@@ -1535,6 +1572,210 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_trace_small(const __grid_c
         shade_hits(P, level, tid, T);
         __syncthreads();
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Thread pencils (rt_tpencil.h): records, grouping, scan.
+// ------------------------------------------------------------------------------------------------
+// Records, position by position next to the generic ones ("never" there -- padding, degenerate, always-exact -- is "never" here).
+__global__ void k_build_trec(const float4* __restrict__ triv, const float4* __restrict__ rec, int npos, int c1_end, int c2_end, float M, const TpSetup S,
+                             float4* __restrict__ trec) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const float4 g3 = rec[4 * pos + 3];
+    float q[24];
+    tp_never(q);
+    if (g3.x != kBminNever) {
+        const uint32_t i = __float_as_uint(g3.y);
+        const int W = pos < c1_end ? 0 : (pos < c2_end ? 1 : 2);
+        const float4 A = triv[3 * i], B = triv[3 * i + 1], C = triv[3 * i + 2];
+        const float a3f[3] = {A.x, A.y, A.z}, b3f[3] = {B.x, B.y, B.z}, c3f[3] = {C.x, C.y, C.z};
+        const FilterTol t = filter_tolerances(a3f, b3f, c3f, W, (double)M);
+        if (!t.always) tp_record(a3f, b3f, c3f, t.E0, t.E1, S, q);
+    }
+    q[7] = g3.y;    // id
+    q[11] = g3.z;   // records in use in the tile (first record of a tile)
+#pragma unroll
+    for (int v = 0; v < kTpVec; ++v) trec[kTpVec * pos + v] = make_float4(q[4 * v], q[4 * v + 1], q[4 * v + 2], q[4 * v + 3]);
+}
+
+// One CTA: hist[t] accepted rays of reflector t -> groups of kTpR; exclusive scan of the group counts -> off[t];
+// group_tri[off[t] + g] = t; counters[kCntTpGroups] = number of groups.  (hist keeps the ray counts for k_tp_scatter.)
+__global__ void __launch_bounds__(1024) k_tp_offsets(const __grid_constant__ FrameParams P) {
+    __shared__ uint32_t part[1024];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int per = (P.ntri + T - 1) / T;
+    const int t0 = tid * per, t1 = min(P.ntri, t0 + per);
+    uint32_t sum = 0;
+    for (int t = t0; t < t1; ++t) sum += P.tp_hist[t] / (uint32_t)kTpR;
+    part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < T; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
+        P.counters[kCntTpGroups] = run;
+    }
+    __syncthreads();
+    uint32_t run = part[tid];
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t g = P.tp_hist[t] / (uint32_t)kTpR;
+        P.tp_off[t] = run;
+        for (uint32_t k = 0; k < g; ++k) P.tp_group_tri[run + k] = (uint32_t)t;
+        run += g;
+    }
+}
+
+// Pool -> grouped queue.  A reflector's rays beyond its last full group go to the ordinary level-1 queue (generic scan).
+__global__ void __launch_bounds__(256) k_tp_scatter(const __grid_constant__ FrameParams P) {
+    const uint32_t count = P.counters[kCntTpPool];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (count + stride - 1) / stride;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool spill = false;
+        uint32_t s = 0;
+        if (i < count) {
+            s = P.tp_pool[i];
+            const uint32_t t = __float_as_uint(P.hit[s].w);   // the level-0 hit record is still in place: the reflector
+            const uint32_t pos = atomicAdd(&P.tp_cursor[t], 1u);
+            const uint32_t lim = (P.tp_hist[t] / (uint32_t)kTpR) * (uint32_t)kTpR;
+            if (pos < lim) P.q_tp[(size_t)P.tp_off[t] * kTpR + pos] = s;
+            else spill = true;
+        }
+        warp_append(spill, s, P.q_ray, &P.counters[kCntRay + 1]);
+    }
+}
+
+// k_trace_tp: nearest hit of the grouped level-1 rays.  One thread = one group = kTpR rays sharing the mirror image of the eye about
+// their reflector's plane.  Same persistent CTAs, TMA ring (96-byte records), work items, cold state in shared memory and key
+// merge as k_trace; scalar hot loop: per triangle 21 FMAs + 9 sign flips build the thread's oriented weight vectors, per ray
+// 9 FMAs + LOP3s; the cold path rebuilds the block's mask with the full test (distance clauses, grazing clause of near planes).
+struct TpSmem {
+    KernelSmem<kTpR, false, kTpVec> ks;
+    float lam_o[kTpR][kThreads], lam_hi[kTpR][kThreads];   // per-ray state only the cold path reads
+};
+template <int J, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_trace_tp(const __grid_constant__ FrameParams P, int level) {
+    constexpr int R = kTpR;
+    static_assert(R * J <= 32, "candidate mask must fit 32 bits");
+    TpSmem& tsm = *reinterpret_cast<TpSmem*>(rt_dyn_smem);
+    KernelSmem<R, false, kTpVec>& ks = tsm.ks;
+    SmemCol<float> lam_o{tsm.lam_o}, lam_hi{tsm.lam_hi};
+    const uint32_t ngroups = P.counters[kCntTpGroups];
+    const Split sp = make_split(ngroups, kThreads, P.ntiles, true);
+    Pipe pipe;
+    pipe_init<false, kTpVec>(pipe, ks.sm, P.trec, sp, nullptr);
+    uint32_t n_exact = 0;
+    for (uint32_t item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
+        const uint32_t chunk = item / sp.parts, part = item - chunk * sp.parts;
+        ColdState<R, true> st(ks.cold.get());
+        auto& dist = st.dist; auto& best = st.best; auto& sid = st.sid;
+        const uint32_t g = chunk * kThreads + threadIdx.x;
+        const bool have = g < ngroups;
+        float wx[R], wy[R], wz[R];
+        float E[3] = {0.f, 0.f, 0.f};
+        uint32_t live = 0;
+        bool force_all = false;          // (cannot happen: the same function accepted these rays in k_shade) -> every triangle exact
+        float lam_min_thread = FLT_MAX;
+        if (have) {
+            const uint32_t t = P.tp_group_tri[g];
+            const float4 A = P.triv[3 * t], B = P.triv[3 * t + 1], C = P.triv[3 * t + 2];
+            const float Af[3] = {A.x, A.y, A.z}, Bf[3] = {B.x, B.y, B.z}, Cf[3] = {C.x, C.y, C.z};
+            if (!tp_mirror_point(P.tp.eye, P.tp.centerf, Af, Bf, Cf, E)) force_all = true;
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            sid[k] = 0; dist[k] = FLT_MAX; best[k] = -1; lam_hi[k] = FLT_MAX; lam_o[k] = 0.f;
+            wx[k] = wy[k] = wz[k] = 0.f;
+            if (have) {
+                const uint32_t s = P.q_tp[(size_t)g * R + k];
+                sid[k] = s;
+                const float4 o = P.ray_o[s], d = P.ray_d[s];
+                const float Of[3] = {o.x, o.y, o.z}, Df[3] = {d.x, d.y, d.z};
+                TpRay tr;
+                if (!tp_accepts(P.tp, E, Of, Df, tr)) force_all = true;
+                wx[k] = tr.wx; wy[k] = tr.wy; wz[k] = tr.wz; lam_o[k] = tr.lam_o;
+                lam_min_thread = fminf(lam_min_thread, tr.lam_o);
+                live |= 1u << k;
+            }
+        }
+        float cg = 1.0f, near_thr = 0.0f;
+        if (have) tp_thread_consts(P.tp, lam_min_thread, cg, near_thr);
+        if (force_all) near_thr = __int_as_float(0x7f800000);   // every plane is "near", and ...
+        if (force_all) cg = __int_as_float(0x7f800000);         // ... every pair "grazing": all candidates
+        const uint32_t deadmask = have ? 0u : 0x80000000u;
+        const int tile_begin = (int)(part * sp.len);
+        for (int tile = tile_begin; tile < tile_begin + (int)pipe.len; ++tile) {
+            const float4* rec = pipe_acquire(pipe);
+            if (__any_sync(0xffffffffu, live != 0u)) {
+                const int nvalid = __float_as_int(rec[2].w);
+#pragma unroll 1
+                for (int jb = 0; jb < nvalid; jb += J) {
+                    uint32_t acc[R];
+#pragma unroll
+                    for (int k = 0; k < R; ++k) acc[k] = 0xffffffffu;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        float q[24];
+#pragma unroll
+                        for (int v = 0; v < kTpVec; ++v) {
+                            const float4 f = rec[(jb + j) * kTpVec + v];
+                            q[4 * v] = f.x; q[4 * v + 1] = f.y; q[4 * v + 2] = f.z; q[4 * v + 3] = f.w;
+                        }
+                        TpTri T;
+                        tp_orient(q, E, near_thr, T);
+                        const uint32_t nearmask = T.near_ ? 0x7fffffffu : 0xffffffffu;
+#pragma unroll
+                        for (int k = 0; k < R; ++k) {
+                            TpRay tr; tr.wx = wx[k]; tr.wy = wy[k]; tr.wz = wz[k]; tr.lam_o = 0.f;
+                            acc[k] &= tp_weights(T, tr) & nearmask;
+                        }
+                    }
+                    uint32_t all = 0xffffffffu;
+#pragma unroll
+                    for (int k = 0; k < R; ++k) all &= acc[k];
+                    all |= deadmask;
+                    if ((int)all >= 0) {   // cold: full test for the block, then exact re-evaluation per candidate pair
+#pragma unroll 1
+                        for (int j = 0; j < J; ++j) {
+                            float q[24];
+#pragma unroll
+                            for (int v = 0; v < kTpVec; ++v) {
+                                const float4 f = rec[(jb + j) * kTpVec + v];
+                                q[4 * v] = f.x; q[4 * v + 1] = f.y; q[4 * v + 2] = f.z; q[4 * v + 3] = f.w;
+                            }
+                            TpTri T;
+                            tp_orient(q, E, near_thr, T);
+                            const int tri = (int)__float_as_uint(q[7]);
+#pragma unroll
+                            for (int k = 0; k < R; ++k) {   // (unrolled: the ray registers must not be indexed dynamically)
+                                if (!((live >> k) & 1u)) continue;
+                                TpRay tr; tr.wx = wx[k]; tr.wy = wy[k]; tr.wz = wz[k]; tr.lam_o = lam_o[k];
+                                const float lam_lo = __fsub_rd(tr.lam_o, P.tp.lam_slack);
+                                if (!tp_candidate(T, tr, lam_hi[k], lam_lo, cg)) continue;
+                                const float4 o = P.ray_o[sid[k]], d = P.ray_d[sid[k]];
+                                const float4 e = exact_eval_tri(P.triv, tri, o.x, o.y, o.z, d.x, d.y, d.z);
+                                ++n_exact;
+                                if (!(e.w < 0.0f) && (e.w < dist[k] || (e.w == dist[k] && tri < best[k]))) {   // (distance, id) order: raytracing.cpp:183
+                                    dist[k] = e.w;
+                                    best[k] = tri;
+                                    const float h = __fadd_ru(tr.lam_o, __fadd_ru(e.w, P.tp.lam_slack));
+                                    lam_hi[k] = (h < FLT_MAX) ? h : FLT_MAX;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            pipe_release<false>(pipe);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+            if (((live >> k) & 1u) && best[k] >= 0)
+                atomicMin(&P.key[sid[k]], ((unsigned long long)__float_as_uint(dist[k]) << 32) | (unsigned int)best[k]);
+    }
+    if (n_exact) atomicAdd(reinterpret_cast<unsigned long long*>(&P.counters[kCntExact]), (unsigned long long)n_exact);
 }
 
 // ------------------------------------------------------------------------------------------------

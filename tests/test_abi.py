@@ -56,13 +56,13 @@ def test_option_and_flag_constants_match_header(built, tmp_path):
     """The ctypes glue repeats the header's option numbers and feature / material flag bits: keep them in step."""
     from raytracert_b200 import binding
     src = tmp_path / "opt.c"
-    src.write_text('#include <stdio.h>\n#include "rt_b200.h"\nint main(void){printf("%d %d %d %d %d %d %d %d\\n",'
-                   "RT_OPT_TILE_CULLING,RT_OPT_PENCIL,RT_OPT_PENCIL_ANY,RT_OPT_GRAPH,RT_OPT_PENCIL_REFLECT,RT_OPT_SMALL_TRACE,RT_MAX_LIGHTS,"
+    src.write_text('#include <stdio.h>\n#include "rt_b200.h"\nint main(void){printf("%d %d %d %d %d %d %d %d %d\\n",'
+                   "RT_OPT_TILE_CULLING,RT_OPT_PENCIL,RT_OPT_PENCIL_ANY,RT_OPT_GRAPH,RT_OPT_PENCIL_REFLECT,RT_OPT_SMALL_TRACE,RT_OPT_PENCIL_THREAD,RT_MAX_LIGHTS,"
                    "RT_AMBIENT|RT_DIFFUSE|RT_SPECULAR|RT_REFLECTION|RT_SHADOWS|RT_REFRACTION);return 0;}\n")
     exe = tmp_path / "opt"
     subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert got == [binding.RT_OPT_TILE_CULLING, binding.RT_OPT_PENCIL, binding.RT_OPT_PENCIL_ANY, binding.RT_OPT_GRAPH, binding.RT_OPT_PENCIL_REFLECT, binding.RT_OPT_SMALL_TRACE, binding.RT_MAX_LIGHTS, binding.RT_ALL_FEATURES]
+    assert got == [binding.RT_OPT_TILE_CULLING, binding.RT_OPT_PENCIL, binding.RT_OPT_PENCIL_ANY, binding.RT_OPT_GRAPH, binding.RT_OPT_PENCIL_REFLECT, binding.RT_OPT_SMALL_TRACE, binding.RT_OPT_PENCIL_THREAD, binding.RT_MAX_LIGHTS, binding.RT_ALL_FEATURES]
 
 
 def test_header_is_plain_c(built, tmp_path):

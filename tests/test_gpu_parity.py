@@ -841,3 +841,53 @@ def test_small_trace_batches_take_one_launch(gpu, port):
     finally:
         gpu.set_option(binding.RT_OPT_SMALL_TRACE, 1)
         port.L.orc_set_spheres(0, None)
+
+
+def test_thread_pencils_are_invisible(gpu, port):
+    """RT_OPT_PENCIL_THREAD: level-1 continuation rays grouped by the triangle their primary ray hit, scanned with per-thread pencil
+    weights around that triangle's mirror image of the eye (rt_tpencil.h).  The frame -- ids, float RGB bits, ray counts -- must
+    equal the option-off frame and the oracle, with and without the plane-group mirror pencils; rt_stats must report the rays."""
+    from raytracert_b200 import binding, host, scenes
+    big = scenes.balls_standin()
+    cases = [
+        ("balls", big, host.Camera(200, 160, (0.0, 2.6, 5.2), (0.0, 0.55, 0.0)), 2, 3, [(2.5, 4.0, 3.0)], True),
+        ("balls_low", big, host.Camera(160, 100, (0.2, 0.75, 4.6), (0.0, 0.62, 0.0)), 3, 3, [(2.5, 4.0, 3.0)], True),
+        ("sphere", scenes.tessellated_sphere(slices=200, stacks=101, ground=True), host.Camera(120, 120, (1.2, 0.9, 2.6), (0.0, 0.0, 0.0)), 3, 2, [(1.2, 3.0, 2.6)], True),
+        ("room", scenes.mirror_room(n=16), host.Camera(96, 72, (0.3, 1.6, 4.2), (0, 0.8, 0)), 3, 6, [(1.5, 2.8, 2.5)], True),
+        ("cube", load_scene("cube"), host.Camera(96, 96, (2.6, 2.4, 3.0), (.5, .5, .5)), 3, 10, [(3.0, 5.0, 4.0)], None),
+        ("dodge", load_scene("dodge"), host.Camera(96, 54, (.75, .55, 1.1), (.07, 0, .23)), 3, 10, [(.75, .55, 1.1)], None),
+    ]
+    try:
+        for name, s, cam, pf, lvl, lights, expect in cases:
+            lights = np.asarray(lights, np.float32)
+            c = dict(corners=cam.corners, W=cam.W, H=cam.H, pfx=pf, pfy=pf, max_lvl=lvl, features=63, eye=cam.eye, lights=lights)
+            gpu.set_option(binding.RT_OPT_PENCIL_THREAD, 0)
+            rgb0, prim0 = gpu_render(gpu, s, c)
+            st0 = gpu.stats()
+            assert not (st0["variant"] & 64) and st0["thread_pencil_rays"] == 0, name
+            for reflect in (1, 0):
+                gpu.set_option(binding.RT_OPT_PENCIL_REFLECT, reflect)
+                gpu.set_option(binding.RT_OPT_PENCIL_THREAD, 1)
+                rgb1, prim1 = gpu_render(gpu, s, c)
+                st1 = gpu.stats()
+                if expect:
+                    assert (st1["variant"] & 64) and st1["thread_pencil_rays"] > 0, (name, reflect, st1["variant"], st1["thread_pencil_rays"])
+                assert np.array_equal(prim0, prim1), (name, reflect)
+                assert np.array_equal(bits(rgb0), bits(rgb1)), f"{name} reflect={reflect}: {np.count_nonzero(bits(rgb0) != bits(rgb1))} framebuffer words differ"
+                for k in ("primary_rays", "shadow_rays", "bounce_rays"):
+                    assert st0[k] == st1[k], (name, reflect, k, st0[k], st1[k])
+            gpu.set_option(binding.RT_OPT_PENCIL_REFLECT, 1)
+            port.set_scene(s); port.configure(cam.eye, lights, 63, lvl); port.reset_counts()
+            rgb_o, _, prim_o = port.render(cam.corners, cam.W, cam.H, pf, pf, want_samples=True)
+            assert np.array_equal(prim1, prim_o), name
+            assert np.abs(rgb1 - rgb_o).max() <= RGB_TOL, name
+            assert (st1["primary_rays"], st1["shadow_rays"], st1["bounce_rays"]) == port.ray_counts(), name
+        # headline scene: most of the level-1 rays that do not leave the water are served
+        gpu.set_option(binding.RT_OPT_PENCIL_THREAD, 1)
+        c = dict(corners=cases[0][2].corners, W=200, H=160, pfx=4, pfy=4, max_lvl=3, features=63, eye=cases[0][2].eye, lights=np.asarray([(2.5, 4.0, 3.0)], np.float32))
+        gpu_render(gpu, big, c)
+        st = gpu.stats()
+        assert st["thread_pencil_rays"] + st["mirror_rays"] > 0.5 * st["bounce_rays"], (st["thread_pencil_rays"], st["mirror_rays"], st["bounce_rays"])
+    finally:
+        gpu.set_option(binding.RT_OPT_PENCIL_THREAD, 0)
+        gpu.set_option(binding.RT_OPT_PENCIL_REFLECT, 1)
