@@ -391,8 +391,9 @@ def main():
     ms_e2e = float(np.mean(e2e_steps))
     ms_cull = float(np.mean(cull_steps))
     parts = [float(np.mean(e2e_parts[k])) for k in ("upload_ms", "render_ms", "download_ms")]
-    counts = np.array([st["primary_rays"], st["shadow_rays"], st["bounce_rays"], st["exact_evals"], st["mirror_rays"]], np.float64)
-    kinds = np.array([st["ms_trace"], st["ms_shadow"], st["ms_shade"], st["ms_resolve"], st["ms_gather"], st["ms_trace_primary"], st["ms_trace_mirror"]], np.float64)
+    counts = np.array([st["primary_rays"], st["shadow_rays"], st["bounce_rays"], st["exact_evals"], st["mirror_rays"], st["thread_pencil_rays"]], np.float64)
+    kinds = np.array([st["ms_trace"], st["ms_shadow"], st["ms_shade"], st["ms_resolve"], st["ms_gather"], st["ms_trace_primary"], st["ms_trace_mirror"],
+                      st["ms_trace_thread"]], np.float64)
     if multi_rank:
         import torch.distributed as td
         t = torch.tensor([ms_dev, ms_e2e, ms_cull] + parts + list(kinds), dtype=torch.float64, device=f"cuda:{local}")
@@ -418,47 +419,56 @@ def main():
         pencil_primary, pencil_shadow = bool(variant & 2), bool(variant & 4)
         ms_primary = float(kinds[5])
         ms_mirror = float(kinds[6])
-        ms_bounce = float(kinds[0] - kinds[5] - kinds[6])     # generic scans of the bounce levels
+        ms_thread = float(kinds[7])
+        ms_bounce = float(kinds[0] - kinds[5] - kinds[6] - kinds[7])     # generic scans of the bounce levels
 
         def kernel_row(key, name, rays_gpu, ms, executed):
-            a = FLOPS_PER_TEST * rays_gpu * ntri / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            alg = FLOPS_PER_TEST * rays_gpu * ntri / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            ex = alg * executed / FLOPS_PER_TEST
             m = ncu.get(key, {})
-            return {"kernel": name, "ms": ms, "tests_per_s": rays_gpu * ntri / (ms * 1e-3) if ms > 0 else 0.0, "achieved": a,
-                    "algorithmic_ratio": a / fp32_peak,   # algorithmic flops / peak: NOT a pipe utilisation (the pencil kernels do a test in 12 flop; any-hit rays stop early)
-                    "hot_loop_flops_per_test": executed, "executed_frac_from_hot_loop": a * executed / FLOPS_PER_TEST / fp32_peak,
+            return {"kernel": name, "ms": ms, "tests_per_s": rays_gpu * ntri / (ms * 1e-3) if ms > 0 else 0.0,
+                    "executed_flops_per_test": executed, "achieved": ex, "frac": ex / fp32_peak,          # executed at the FMA pipe
+                    "algorithmic_achieved": alg, "algorithmic_ratio": alg / fp32_peak,                   # 42 flop per test; NOT a utilisation (can exceed 1)
                     "fma_pipe_active_ncu": m.get("fma_pipe_cycles_active_pct"), "issue_active_ncu": m.get("issue_active_pct"),
                     "dram_bytes_ncu": m.get("dram_bytes"), "ncu_launch": m.get("launch")}
+        # executed flops per (ray, triangle) test in the hot loops (SASS: profiles/r2_sass_hot_loops.txt):
+        #   generic filter 11 FFMA2 + 3 FMUL2 + 2 FADD2 per ray pair = 27; pencil filters 6 FFMA2 per ray pair = 12;
+        #   thread pencils 9 FFMA per ray + (21 FFMA + 3 FADD) per triangle and thread of 8 rays = 23.6
         rows = [kernel_row("primary", "k_trace primary (%s filter)" % ("pencil" if pencil_primary else "generic"), counts[0] / world, ms_primary, 12 if pencil_primary else 27),
-                kernel_row("bounce", "k_trace bounce levels (generic filter)", (counts[2] - counts[4]) / world, ms_bounce, 27),
+                kernel_row("bounce", "k_trace bounce levels (generic filter)", (counts[2] - counts[4] - counts[5]) / world, ms_bounce, 27),
+                kernel_row("thread", "k_trace_tp level-1 rays grouped by reflector (thread pencils)", counts[5] / world, ms_thread, 23.6),
                 kernel_row("mirror", "k_trace level-1 rays of plane groups (mirror pencil)", counts[4] / world, ms_mirror, 12),
                 kernel_row("shadow", "k_shadow any-hit (%s filter)" % ("pencil" if pencil_shadow else "generic"), counts[1] / world, float(kinds[1]), 12 if pencil_shadow else 27)]
         dom = max(rows, key=lambda r: r["ms"])
-        ach = dom["achieved"]
-        roof = {"bound": "fp32", "kernel": dom["kernel"] + " -- the launch kind with the largest share of the frame", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ach / fp32_peak,
-                # executed at the pipe: the hot loop's instruction mix x the measured test rate, and ncu's own FMA-pipe counter
-                "executed_frac": dom["executed_frac_from_hot_loop"], "fma_pipe_active_ncu": dom["fma_pipe_active_ncu"],
+        roof = {"bound": "fp32", "kernel": dom["kernel"] + " -- the launch kind with the largest share of the frame",
+                # achieved = FP32 flops the kernel EXECUTES (hot-loop instruction mix x measured test rate) / its device time; frac = achieved / peak
+                "achieved": dom["achieved"], "peak": fp32_peak, "unit": "TFLOP/s", "frac": dom["frac"],
+                "executed_flops_per_test": dom["executed_flops_per_test"], "fma_pipe_active_ncu": dom["fma_pipe_active_ncu"],
+                # the same launches counted with SURVEY 8d's 42 algorithmic flop per test (general-ray form): what the reference's arithmetic would need
+                "algorithmic_achieved": dom["algorithmic_achieved"], "algorithmic_ratio": dom["algorithmic_ratio"],
                 # rt_probe_fp32_peak(): what a register-resident FFMA/FFMA2 loop sustains on this device right now (TFLOP/s)
-                "peak_fma_loop_measured": fp32_probe, "frac_of_measured_fma_loop": ach / fp32_probe if fp32_probe > 0 else None,
+                "peak_fma_loop_measured": fp32_probe, "frac_of_measured_fma_loop": dom["achieved"] / fp32_probe if fp32_probe > 0 else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of that kind, from an ncu capture of this workload
                 # (not measured in this run); null when there is no capture for the workload / GPU count
                 "traffic": dom["dram_bytes_ncu"] if world == 1 else None, "traffic_source": ncu_src, "traffic_launch": dom["ncu_launch"],
                 "peak_source": f"{sms} SMs x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock; no FP32 entry there, so the nominal figure at the measured max clock)",
-                "frac_at_measured_clock": (ach / (fp32_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])) if clocks.get("sm_mhz") else None,
+                "frac_at_measured_clock": (dom["achieved"] / (fp32_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])) if clocks.get("sm_mhz") else None,
+                "frame_executed_frac": sum(r["achieved"] * r["ms"] for r in rows) / max(sum(r["ms"] for r in rows), 1e-9) / fp32_peak,
                 "by_kernel": rows,
-                "note": "achieved/frac count 42 algorithmic flop per test (general-ray form, SURVEY 8d) for the dominant launch kind. by_kernel[].algorithmic_ratio is the same "
-                        "quotient per kind and is not a utilisation: the pencil kernels do a test in 12 executed flop (rays through a common point need no origin arithmetic), "
-                        "any-hit rays stop at their first occluder. The pipe-level figures are executed_frac_from_hot_loop and fma_pipe_active_ncu.",
-                "ms_by_kernel": dict(zip(["k_trace", "k_shadow", "k_shade", "k_resolve", "gather", "k_trace_primary", "k_trace_mirror"], [float(x) for x in kinds]))}
+                "note": "achieved/frac are EXECUTED FP32 flops at the FMA pipe (hot-loop instruction mix x measured test rate), fma_pipe_active_ncu is ncu's own pipe counter for "
+                        "the largest launch of the kind. algorithmic_* count 42 flop per test (SURVEY 8d, general-ray form): every kernel performs every (ray, triangle) test of the "
+                        "reference, the pencil kernels in 12 executed flop (rays through a common point need no origin arithmetic), so that quotient can exceed 1 and is not a utilisation.",
+                "ms_by_kernel": dict(zip(["k_trace", "k_shadow", "k_shade", "k_resolve", "gather", "k_trace_primary", "k_trace_mirror", "k_trace_thread"], [float(x) for x in kinds]))}
         line = {"metric": METRIC, "value": rays / ms_dev / 1e3, "unit": "Mrays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_for(args.workload, desc, scene, W, H, pf, lvl, len(lights), world),
                 "run": {"mode": "single process, rt_init(N)" if single else "one process per GPU (torchrun), rt_init_rank", "rays_per_frame": rays,
-                        "primary": counts[0], "shadow": counts[1], "bounce": counts[2], "bounce_served_by_mirror_pencils": counts[4], "exact_reevaluations": counts[3],
+                        "primary": counts[0], "shadow": counts[1], "bounce": counts[2], "bounce_served_by_mirror_pencils": counts[4],
+                        "bounce_served_by_thread_pencils": counts[5], "exact_reevaluations": counts[3],
                         "primary_mrays_per_s": counts[0] / ms_dev / 1e3,
                         "filter": {"primary": "pencil" if variant & 2 else "generic", "shadow": "pencil" if variant & 4 else "generic",
-                                   "bounce": "generic + mirror pencils" if variant & 32 else "generic",
+                                   "bounce": "generic" + (" + mirror pencils" if variant & 32 else "") + (" + thread pencils" if variant & 64 else ""),
                                    "clause_free": bool(variant & 1), "pencil_without_premise": bool(variant & 8), "graph_replay": bool(variant & 16)},
                         "l2": "flushed between timed iterations (256 MiB write per device)", "wall_s_timed_region": t_wall},
                 "clocks": clocks,

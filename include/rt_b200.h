@@ -188,7 +188,7 @@ int rt_trace(const rt_params* params, int n, const float* origins, const float* 
  * launch has a fixed grid: persistent CTAs read their ray counts from device counters); rt_stats.variant bit 4.
  * 0 = never, 1 = always.  A replayed frame reports no per-kernel times (rt_stats.ms_trace .. ms_resolve are 0). */
 #define RT_OPT_GRAPH 4
-/* RT_OPT_PENCIL_THREAD (default 0): the level-1 continuation rays of the primary hits on ANY triangle leave that triangle's own
+/* RT_OPT_PENCIL_THREAD (default 1 = auto: frames of more than 4e9 sample-triangle pairs; 2 = always; 0 = never): the level-1 continuation rays of the primary hits on ANY triangle leave that triangle's own
  * mirror image of the eye; grouped by reflector (8 rays per thread), they are scanned with per-thread pencil weights built on
  * the fly from an E-independent record (rt_tpencil.h) instead of the generic filter.  Every ray is checked against its
  * pencil when it is spawned; rays that do not fill a group take the generic scan.  rt_stats.variant bit 6,

@@ -28,6 +28,7 @@ using namespace rt;
 // The pencil kernels keep 6 registers per ray pair instead of 14, so they have their own shapes (RT_B200_PTUNE="rp,j,minb").
 #define RT_PENCIL_CONFIGS(X) X(2, 8, 2) X(1, 16, 4) X(4, 4, 2) X(3, 4, 2)   // rp >= 3: scalar hot loop (rt_kernels.cuh: pencil_ray_hot), cold state in dynamic shared memory
 struct ScanConfig { int rp, j, minb; };
+constexpr double kGraphMaxTests = 4e9;     // samples x triangles below which RT_OPT_GRAPH = auto captures the frame (and thread pencils stay off)
 constexpr uint32_t kMaxChunkSamples = 1u << 23;  // 8 Mi samples per wavefront chunk (84 B of state each)
 
 // ---- NCCL through dlopen (no link-time dependency; inside python the already-loaded torch copy is reused)
@@ -148,7 +149,7 @@ struct Global {
     ScanConfig pscan = {2, 8, 2};    // shape of the pencil kernels
     bool tile_culling = false;       // RT_OPT_TILE_CULLING
     bool pencil = true;              // RT_OPT_PENCIL: common-point filter for primary / shadow rays where it applies
-    bool pencil_thread = false;      // RT_OPT_PENCIL_THREAD: per-thread pencils for the level-1 continuation rays of every other triangle
+    int pencil_thread = 1;           // RT_OPT_PENCIL_THREAD (0 never, 1 auto: frames that are not launch-bound, 2 always): per-thread pencils for the level-1 continuation rays of every other triangle
     bool pencil_reflect = true;      // RT_OPT_PENCIL_REFLECT: mirror pencils for the level-1 continuation rays of planar reflectors
     struct PlaneGroup { double n[3], d; uint32_t count; };
     std::vector<PlaneGroup> planes;  // the (at most kMaxMirrors) largest groups of coplanar triangles of the scene; group id = index
@@ -367,7 +368,7 @@ void read_tuning_env() {
     if (const char* c = getenv("RT_B200_PENCIL_ANY")) g.pencil_any = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_ANY, ..)
     if (const char* c = getenv("RT_B200_PENCIL_REFLECT")) g.pencil_reflect = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_REFLECT, ..)
     if (const char* c = getenv("RT_B200_SMALL_TRACE")) g.small_trace = atoi(c) != 0;
-    if (const char* c = getenv("RT_B200_PENCIL_THREAD")) g.pencil_thread = atoi(c) != 0;   // same as rt_set_option(RT_OPT_PENCIL_THREAD, ..)
+    if (const char* c = getenv("RT_B200_PENCIL_THREAD")) g.pencil_thread = std::min(2, std::max(0, atoi(c)));   // same as rt_set_option(RT_OPT_PENCIL_THREAD, ..)
     if (const char* c = getenv("RT_B200_GRAPH")) g.graph_mode = atoi(c) < 0 ? -1 : (atoi(c) != 0);   // same as rt_set_option(RT_OPT_GRAPH, ..)
     if (const char* pe = getenv("RT_B200_PTUNE")) {
         ScanConfig c = g.pscan;
@@ -628,7 +629,9 @@ int plan_pencil(RtDevice& d, const rt_params& rp, bool cull, PencilPlan& plan) {
         }
         plan.n_mirrors = any ? (int)std::min(g.planes.size(), (size_t)kMaxMirrors) : 0;
     }
-    if (plan.cam && g.pencil_thread && (rp.features & RT_REFLECTION) && rp.max_lvl > 0)
+    // (not for launch-bound frames: grouping adds four launches and two memsets per chunk -- cube.obj 800x800 went 0.23 -> 0.36 ms)
+    const double frame_tests = (double)rp.width * rp.height * rp.pixelfactor_x * rp.pixelfactor_y / (double)std::max(g.world, 1) * (double)std::max(d.ntri, 1);
+    if (plan.cam && g.pencil_thread && (rp.features & RT_REFLECTION) && rp.max_lvl > 0 && (frame_tests > kGraphMaxTests || g.pencil_thread == 2))
         plan.tp = tp_setup(plan.cam_setup.E, plan.cam_setup.delta, (double)d.M_built, d.box_lo, d.box_hi, plan.tp_setup);
     int rc = ensure(d.prec, d.cap_prec, plan.slot_vec * (size_t)(plan.mirror_slot0 + plan.n_mirrors));
     if (rc) return rc;
@@ -834,7 +837,6 @@ struct KeyWriter {
 // counters), so the whole wavefront -- all chunks, all levels, the resolve -- is capturable as it is.
 constexpr int kSmallTraceRays = 32;        // rt_trace batches up to this size ...
 constexpr double kSmallTraceTests = 1e5;   // ... and this many (ray, triangle) pairs per level take the single-launch path (measured: tools/trace_latency.py)
-constexpr double kGraphMaxTests = 4e9;   // samples x triangles below which RT_OPT_GRAPH = auto captures the frame
 
 int render_enqueue_impl(const rt_params* rp) {
     int rc = check_ready();
@@ -1098,7 +1100,7 @@ void rt_shutdown(void) {
     g.pencil = true;
     g.pencil_any = true;
     g.pencil_reflect = true;
-    g.pencil_thread = false;
+    g.pencil_thread = 1;
     g.small_trace = true;
     g.graph_mode = -1;
 }
@@ -1633,7 +1635,7 @@ int rt_set_option(int option, int value) {
     if (option == RT_OPT_PENCIL_REFLECT) { g.pencil_reflect = value != 0; return RT_OK; }
     if (option == RT_OPT_PENCIL_REFLECT) { g.pencil_reflect = value != 0; return RT_OK; }
     if (option == RT_OPT_SMALL_TRACE) { g.small_trace = value != 0; return RT_OK; }
-    if (option == RT_OPT_PENCIL_THREAD) { g.pencil_thread = value != 0; return RT_OK; }
+    if (option == RT_OPT_PENCIL_THREAD) { g.pencil_thread = value < 0 ? 0 : (value > 2 ? 2 : value); return RT_OK; }
     if (option == RT_OPT_GRAPH) { g.graph_mode = value < 0 ? -1 : (value != 0); return RT_OK; }
     return fail(RT_ERR_INVALID, "unknown option %d", option);
 }

@@ -1601,7 +1601,7 @@ __global__ void k_build_trec(const float4* __restrict__ triv, const float4* __re
 }
 
 // One CTA: hist[t] accepted rays of reflector t -> groups of kTpR; exclusive scan of the group counts -> off[t];
-// group_tri[off[t] + g] = t; counters[kCntTpGroups] = number of groups.  (hist keeps the ray counts for k_tp_scatter.)
+// counters[kCntTpGroups] = number of groups.  (hist keeps the ray counts for k_tp_scatter, which also names each group's reflector.)
 __global__ void __launch_bounds__(1024) k_tp_offsets(const __grid_constant__ FrameParams P) {
     __shared__ uint32_t part[1024];
     const int tid = threadIdx.x, T = blockDim.x;
@@ -1619,10 +1619,8 @@ __global__ void __launch_bounds__(1024) k_tp_offsets(const __grid_constant__ Fra
     __syncthreads();
     uint32_t run = part[tid];
     for (int t = t0; t < t1; ++t) {
-        const uint32_t g = P.tp_hist[t] / (uint32_t)kTpR;
         P.tp_off[t] = run;
-        for (uint32_t k = 0; k < g; ++k) P.tp_group_tri[run + k] = (uint32_t)t;
-        run += g;
+        run += P.tp_hist[t] / (uint32_t)kTpR;
     }
 }
 
@@ -1640,8 +1638,10 @@ __global__ void __launch_bounds__(256) k_tp_scatter(const __grid_constant__ Fram
             const uint32_t t = __float_as_uint(P.hit[s].w);   // the level-0 hit record is still in place: the reflector
             const uint32_t pos = atomicAdd(&P.tp_cursor[t], 1u);
             const uint32_t lim = (P.tp_hist[t] / (uint32_t)kTpR) * (uint32_t)kTpR;
-            if (pos < lim) P.q_tp[(size_t)P.tp_off[t] * kTpR + pos] = s;
-            else spill = true;
+            if (pos < lim) {
+                P.q_tp[(size_t)P.tp_off[t] * kTpR + pos] = s;
+                if ((pos % (uint32_t)kTpR) == 0) P.tp_group_tri[P.tp_off[t] + pos / (uint32_t)kTpR] = t;   // the group's first ray names its reflector
+            } else spill = true;
         }
         warp_append(spill, s, P.q_ray, &P.counters[kCntRay + 1]);
     }

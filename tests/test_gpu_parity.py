@@ -867,7 +867,7 @@ def test_thread_pencils_are_invisible(gpu, port):
             assert not (st0["variant"] & 64) and st0["thread_pencil_rays"] == 0, name
             for reflect in (1, 0):
                 gpu.set_option(binding.RT_OPT_PENCIL_REFLECT, reflect)
-                gpu.set_option(binding.RT_OPT_PENCIL_THREAD, 1)
+                gpu.set_option(binding.RT_OPT_PENCIL_THREAD, 2)          # 2 = also for small frames (1 = auto skips launch-bound frames)
                 rgb1, prim1 = gpu_render(gpu, s, c)
                 st1 = gpu.stats()
                 if expect:
@@ -882,12 +882,16 @@ def test_thread_pencils_are_invisible(gpu, port):
             assert np.array_equal(prim1, prim_o), name
             assert np.abs(rgb1 - rgb_o).max() <= RGB_TOL, name
             assert (st1["primary_rays"], st1["shadow_rays"], st1["bounce_rays"]) == port.ray_counts(), name
-        # headline scene: most of the level-1 rays that do not leave the water are served
+        # headline scene, default mode: most of the level-1 rays that do not leave the water are served
         gpu.set_option(binding.RT_OPT_PENCIL_THREAD, 1)
         c = dict(corners=cases[0][2].corners, W=200, H=160, pfx=4, pfy=4, max_lvl=3, features=63, eye=cases[0][2].eye, lights=np.asarray([(2.5, 4.0, 3.0)], np.float32))
         gpu_render(gpu, big, c)
         st = gpu.stats()
         assert st["thread_pencil_rays"] + st["mirror_rays"] > 0.5 * st["bounce_rays"], (st["thread_pencil_rays"], st["mirror_rays"], st["bounce_rays"])
+        # ... and a launch-bound frame stays off them in auto mode
+        c = load_case("cube_default_64")
+        gpu_render(gpu, load_scene("cube"), c)
+        assert gpu.stats()["thread_pencil_rays"] == 0
     finally:
-        gpu.set_option(binding.RT_OPT_PENCIL_THREAD, 0)
+        gpu.set_option(binding.RT_OPT_PENCIL_THREAD, 1)
         gpu.set_option(binding.RT_OPT_PENCIL_REFLECT, 1)

@@ -237,7 +237,7 @@ def test_pencil_sound_on_the_balls_standin(checker, port):
 
 def test_pencil_sound_on_a_tessellated_sphere(checker, port):
     from raytracert_b200 import host, scenes
-    s = scenes.tessellated_sphere(slices=96, stacks=49, ground=True)
+    s = scenes.tessellated_sphere(slices=96, stacks=49)
     cam = host.Camera(48, 48, (1.2, 0.9, 2.6), (0.0, 0.0, 0.0))
     total, nl = check_frame(checker, port, s, cam, 48, 48, 2, [tuple(cam.eye), (0.0, 3.0, 0.0)], step=2)
     assert total["ref_hits"] > 1000 and nl == 2

@@ -36,12 +36,14 @@ for cfg, f in (("C1 cube.obj 800² 1 spp", "C1_bench_n{n}.json"), ("C2 Balls sta
         if not b:
             continue
         e = b["e2e"]; r = b["roofline"]; par = b.get("parity") or {}
-        ex = sum(k["executed_frac_from_hot_loop"] * k["ms"] for k in r["by_kernel"]) / max(sum(k["ms"] for k in r["by_kernel"]), 1e-9)
+        ex = r.get("frame_executed_frac")
+        if ex is None:
+            ex = sum(k.get("executed_frac_from_hot_loop", k.get("frac", 0.0)) * k["ms"] for k in r["by_kernel"]) / max(sum(k["ms"] for k in r["by_kernel"]), 1e-9)
         ptxt = "—" if not par.get("against") else f"{par['rows_checked']} rows: {par['id_mismatches']} id mismatches, {par['u8_off_by_more_than_1']} u8 off by > 1"
         cb = b.get("cpu_baseline")
         ctxt = "—" if not cb else f"{cb['value']:.4g} Mrays/s on {cb['cores']} cores ({cb['one_thread']['value']:.3g} on 1 thread)"
         print(f"| {cfg} | {n} | {b['ms_per_step']:.3f} | {b['value']:.1f} | {e['ms_per_step']:.2f} ({e['upload_ms']:.2f} / {e['render_ms']:.2f} / {e['download_ms']:.2f}) | "
-              f"{ex:.3f} | {r['frac']:.2f} ({r['kernel'][:22]}…) | {ptxt} | {ctxt} |")
+              f"{ex:.3f} | {r.get('algorithmic_ratio', r['frac']):.2f} ({r['kernel'][:22]}…) | {ptxt} | {ctxt} |")
 
 print()
 print("| C4 1 M-triangle sphere 3840×2160 16 spp | GPUs | brute force ms | Mrays/s | executed FP32 frac | primary / bounce / shadow ms | tile culling ms | culled == brute bits | oracle lattice | CPU reference |")

@@ -57,17 +57,19 @@ for mode, cull in (("brute_force", 0), ("tile_culling", 1)):
     if not cull:
         # executed FP32 at the pipe: hot-loop flops per test (12 pencil / 27 generic) x this rank's tests of each launch kind
         v = st["variant"]
-        cnt = np.array([st["primary_rays"], st["bounce_rays"], st["shadow_rays"]], np.float64)
+        cnt = np.array([st["primary_rays"], st["bounce_rays"], st["shadow_rays"], st["mirror_rays"], st["thread_pencil_rays"]], np.float64)
         kinds = np.array([st["ms_trace_primary"], st["ms_trace"] - st["ms_trace_primary"], st["ms_shadow"]], np.float64)
         if world > 1:
             c = torch.tensor(cnt, dtype=torch.float64, device="cuda"); td.all_reduce(c, op=td.ReduceOp.SUM); cnt = c.cpu().numpy()
             k_ = torch.tensor(kinds, dtype=torch.float64, device="cuda"); td.all_reduce(k_, op=td.ReduceOp.MAX); kinds = k_.cpu().numpy()
         peak = 148 * 128 * 2 * 1.965e9 / 1e12
         alg = 42 * rays * scene.n_triangles / (m * 1e-3) / 1e12 / world
-        ex = ((12 if v & 2 else 27) * cnt[0] + 27 * cnt[1] + (12 if v & 4 else 27) * cnt[2]) * scene.n_triangles / (m * 1e-3) / 1e12 / world
+        # (bounce rays: generic 27, served by a mirror pencil 12, by thread pencils 23.6)
+        ex = ((12 if v & 2 else 27) * cnt[0] + 27 * (cnt[1] - cnt[3] - cnt[4]) + 12 * cnt[3] + 23.6 * cnt[4] + (12 if v & 4 else 27) * cnt[2]) \
+            * scene.n_triangles / (m * 1e-3) / 1e12 / world
         out[mode].update({"fp32_algorithmic_tflops_per_gpu": alg, "algorithmic_ratio": alg / peak, "fp32_executed_tflops_per_gpu": ex,
                           "executed_frac_of_fp32_peak": ex / peak, "ms_primary_bounce_shadow": [float(x) for x in kinds],
-                          "rays_primary_bounce_shadow": [float(x) for x in cnt]})
+                          "rays_primary_bounce_shadow_mirror_thread": [float(x) for x in cnt]})
 if rank == 0:
     a = frames[modes[0]]
     rgb = a[0] if world == 1 else a

@@ -49,7 +49,7 @@ for W in [int(x) for x in args.sizes.split(",")]:
             st = R.stats()
             rays = float(st["primary_rays"] + st["shadow_rays"] + st["bounce_rays"]); m = float(np.min(ms))
             kinds = [st["ms_trace_primary"], st["ms_trace"] - st["ms_trace_primary"], st["ms_shadow"]]
-            cnt = [float(st["primary_rays"]), float(st["bounce_rays"]), float(st["shadow_rays"])]
+            cnt = [float(st["primary_rays"]), float(st["bounce_rays"]), float(st["shadow_rays"]), float(st["mirror_rays"]), float(st["thread_pencil_rays"])]
             if world > 1:
                 import torch, torch.distributed as td
                 t = torch.tensor([m] + kinds, dtype=torch.float64, device="cuda"); td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -60,7 +60,9 @@ for W in [int(x) for x in args.sizes.split(",")]:
             if not cull:
                 # executed FP32 at the pipe: hot-loop flops per test (12 pencil / 27 generic) x tests of each launch kind
                 pencil_p, pencil_s = bool(st["variant"] & 2), bool(st["variant"] & 4)
-                ex = ((12 if pencil_p else 27) * cnt[0] + 27 * cnt[1] + (12 if pencil_s else 27) * cnt[2]) * scene.n_triangles / (m * 1e-3) / 1e12 / world
+                # (bounce rays: generic 27, served by a mirror pencil 12, by thread pencils 23.6)
+                ex = ((12 if pencil_p else 27) * cnt[0] + 27 * (cnt[1] - cnt[3] - cnt[4]) + 12 * cnt[3] + 23.6 * cnt[4] + (12 if pencil_s else 27) * cnt[2]) \
+                    * scene.n_triangles / (m * 1e-3) / 1e12 / world
                 row[mode].update({"fp32_algorithmic_tflops_per_gpu": alg, "algorithmic_ratio": alg / PEAK, "fp32_executed_tflops_per_gpu": ex,
                                   "executed_frac_of_fp32_peak": ex / PEAK, "ms_primary_bounce_shadow": kinds})
         if rank == 0:
