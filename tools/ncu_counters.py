@@ -19,12 +19,14 @@ OUT = os.path.join(ROOT, "profiles", "r2_kernel_counters.json")
 
 
 def kind_of(name):
-    m = re.match(r"(?:void )?(k_trace|k_shadow)<([^>]*)>", name)
+    m = re.match(r"(?:void )?(?:rt::)?(k_trace_tp|k_trace|k_shadow)<([^>]*)>", name)
     if not m:
         return None
     args = [a.strip() for a in m.group(2).split(",")]
     if m.group(1) == "k_shadow":
         return "shadow"
+    if m.group(1) == "k_trace_tp":
+        return "thread"
     if args[3] in ("1", "true"):
         return "primary"
     return "mirror" if len(args) > 6 and args[6] in ("1", "true") else "bounce"   # queued rays through the pencil filter: a plane group's mirror pencil
