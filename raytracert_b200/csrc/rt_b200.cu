@@ -1276,7 +1276,10 @@ int rt_upload_scene(const rt_scene* sc) {
     };
     {
         std::vector<std::thread> pool;
-        for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+        for (int t = 1; t < nthreads; ++t) {
+            try { pool.emplace_back(work, t); }
+            catch (...) { work(t); }   // no thread to be had (resource limits): do that range here -- nothing is thrown across the C ABI
+        }
         work(0);
         for (std::thread& th : pool) th.join();
     }
