@@ -511,6 +511,46 @@ def test_thread_pencils_are_sound(checker, port, case):
     assert res.candidates <= 40 * acc and res.grazing_skipped <= 6 * acc
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_thread_pencils_sound_on_random_soups(checker, port, seed):
+    """Random triangle soups -- small and large triangles, slivers (seed % 4 == 1), a soup far from the world origin (seed 3), a
+    camera inside the soup (seed % 3 == 0) -- through the thread-pencil replay: primary rays hit whatever they hit, the
+    continuation rays are grouped by reflector.  Every pair the reference accepts must survive; rays the check refuses only cost
+    speed."""
+    from raytracert_b200 import host
+    rng = np.random.default_rng(9100 + seed)
+    n = int(rng.integers(60, 350))
+    ctr = rng.uniform(-1.5, 1.5, (n, 1, 3))
+    tri = ctr + rng.choice([0.05, 0.3, 0.9]) * rng.normal(size=(n, 3, 3))
+    if seed % 4 == 1:      # slivers: the third vertex almost on the line of the first two
+        t = rng.uniform(-0.2, 1.2, (n, 1))
+        tri[:, 2] = tri[:, 0] + t * (tri[:, 1] - tri[:, 0]) + 1e-4 * rng.normal(size=(n, 3))
+    if seed == 3:
+        tri += np.array([40.0, -25.0, 10.0])
+    v = tri.reshape(-1, 3).astype(np.float32)
+    idx = np.arange(len(v), dtype=np.uint32).reshape(-1, 3)
+    s = host.Scene(v, idx, np.zeros(n, np.uint32), host.face_normals(v, idx), np.zeros((1, 16), np.float32))
+    centre = v.mean(axis=0)
+    eye = centre + (rng.uniform(-1, 1, 3) + np.array([0, 0, 5.0]) if seed % 3 else rng.uniform(-0.5, 0.5, 3))
+    cam = host.Camera(40, 32, tuple(eye), tuple(centre + rng.uniform(-0.5, 0.5, 3)))
+    tris = tri_array(s)
+    M = magnitude_bound(s, cam.corners)
+    rays = primary_rays(cam.corners, 40, 32, 3, 1)
+    port.set_scene(s)
+    port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
+    _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+    ok = prim >= 0
+    if ok.sum() < 20:
+        pytest.skip("the camera sees almost nothing")
+    brays = reflected_rays(rays[ok], hit[ok], s.normals[prim[ok]])
+    t3 = tris.reshape(-1, 3)
+    res = checker.thread_pencil(np.asarray(cam.eye, np.float64), 1e-5, M, t3.min(axis=0) - 0.01, t3.max(axis=0) + 0.01, tris, brays, prim[ok])
+    if not res.setup_ok:
+        pytest.skip("no thread-pencil set-up for this scene (the library keeps the generic scan)")
+    assert res.violations == 0, f"seed {seed}: {res.violations} accepted pairs filtered out (ray {res.first_bad_ray}, triangle {res.first_bad_tri})"
+    assert res.pairs > 0 or res.unsafe_rays == len(brays)
+
+
 def bounce_like_rays(tris, rng, n):
     """Continuation-ray shaped rays (raytracing.cpp:266-285): origin = P + 0.01 * dir, dest = P + dir, P on a surface; half of
     them aimed at an edge / vertex point of another triangle."""
