@@ -540,13 +540,15 @@ def test_thread_pencils_sound_on_random_soups(checker, port, seed):
     port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
     _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
     ok = prim >= 0
-    if ok.sum() < 20:
-        pytest.skip("the camera sees almost nothing")
+    if ok.sum() == 0:      # (slivers are hard to see; use a denser frame for them below)
+        rays = primary_rays(cam.corners, 40, 32, 9, 1)
+        _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+        ok = prim >= 0
+    assert ok.sum() > 0
     brays = reflected_rays(rays[ok], hit[ok], s.normals[prim[ok]])
     t3 = tris.reshape(-1, 3)
     res = checker.thread_pencil(np.asarray(cam.eye, np.float64), 1e-5, M, t3.min(axis=0) - 0.01, t3.max(axis=0) + 0.01, tris, brays, prim[ok])
-    if not res.setup_ok:
-        pytest.skip("no thread-pencil set-up for this scene (the library keeps the generic scan)")
+    assert res.setup_ok
     assert res.violations == 0, f"seed {seed}: {res.violations} accepted pairs filtered out (ray {res.first_bad_ray}, triangle {res.first_bad_tri})"
     assert res.pairs > 0 or res.unsafe_rays == len(brays)
 
