@@ -202,7 +202,6 @@ PinnedStage<uint32_t> g_stage_perm;
 PinnedStage<uint8_t> g_stage_group;
 PinnedStage<rt_material> g_stage_mat;
 PinnedStage<float4> g_stage_rays, g_stage_out;   // rt_trace: rays in (origin, dest), results out (colour, level-0 hit)
-cudaEvent_t g_stage_event = nullptr;             // recorded after the last H2D copy out of the staging buffers
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -1089,7 +1088,6 @@ static void release_all() {
     g.devs.clear();
     g.world = 0;
     g.scene_ready = g.frame_ready = g.stats_ready = false;
-    if (g_stage_event) { cudaEventDestroy(g_stage_event); g_stage_event = nullptr; }
     g_stage_triv.release(); g_stage_nm.release(); g_stage_sph.release(); g_stage_perm.release(); g_stage_mat.release();
     g_stage_rays.release(); g_stage_out.release(); g_stage_group.release();
 }

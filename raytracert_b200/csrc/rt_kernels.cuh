@@ -38,7 +38,6 @@ constexpr int kRecVec = 4;         // float4 per filter record (64 B)
 constexpr int kStages = 4;         // TMA ring depth
 constexpr int kWarps = 8;          // all warps are consumers; the last warp to finish a stage refills it
 constexpr int kThreads = kWarps * 32;
-constexpr uint32_t kTileBytes = kTile * kRecVec * sizeof(float4);
 constexpr int kMaxParts = 64;      // a launch with few rays splits the triangle range into <= kMaxParts parts per ray chunk
 constexpr uint32_t kItemsPerCta = 24;   // load-balance target of make_split
 constexpr uint32_t kMinPartTiles = 8;   // >= 1024 triangles per part unless the launch is tiny
