@@ -11,6 +11,13 @@
 //   k_shadow          -- isShadow raytracing.cpp:241-261 (PENCIL: any-hit rays of one light through the common-point filter)
 //   k_shade           -- shade/diffuseOnly/blinnPhongSpecularOnly/reflection/refraction/addOffset/trace
 //                        raytracing.cpp:197-232, 266-330, 335-406
+//   k_trace<..,!PRIMARY,PENCIL> -- the same scan for the level-1 continuation rays of a plane group around the mirrored eye
+//                        (reflection(), raytracing.cpp:277-285, mirrors a pencil; rt_pencil.h: pencil_mirror_setup)
+//   k_build_trec / k_tp_offsets / k_tp_scatter / k_trace_tp -- thread pencils (rt_tpencil.h): level-1 continuation rays grouped by the
+//                        triangle their primary ray hit, 8 per thread, weights built on the fly around that triangle's mirror
+//                        image of the eye
+//   k_trace_small     -- performRayTracing raytracing.cpp:410-416 for a handful of rays: the whole recursion in one launch
+//   k_init_trace      -- rt_trace: unpacks the uploaded (origin, dest) pairs
 //   k_resolve         -- main.cpp:391-393 + RGBValue clamp main.cpp:24-42
 //   k_deinterleave / k_place_rows / k_quantise -- row gather after the all-gather; Image::writeImage's quantiser main.cpp:117
 //
