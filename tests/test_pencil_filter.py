@@ -554,6 +554,45 @@ def test_thread_pencils_sound_on_random_soups(checker, port, seed):
     assert res.pairs > 0 or res.unsafe_rays == len(brays)
 
 
+def test_thread_pencil_replay_detects_a_broken_filter(checker, port, tmp_path):
+    """The replay must be able to fail: the same harness built from a header in which tp_orient() no longer orients the weight
+    vectors by the side of the plane the common point lies on reports thousands of filtered-out accepted pairs."""
+    from raytracert_b200 import host, scenes
+    src = open(HDR2).read()
+    assert "    m &= 0x80000000u;" in src
+    mut = tmp_path / "raytracert_b200" / "csrc"
+    mut.mkdir(parents=True)
+    (mut / "rt_tpencil.h").write_text(src.replace("    m &= 0x80000000u;", "    m = 0u;"))
+    (mut / "rt_pencil.h").write_text(open(HDR).read())
+    (tmp_path / "tests").mkdir()
+    (tmp_path / "tests" / "pencil_check.cpp").write_text(open(SRC).read())
+    so = str(tmp_path / "pc_mut.so")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", so, str(tmp_path / "tests" / "pencil_check.cpp")], check=True)
+    L = C.CDLL(so)
+    L.tpencil_check.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_void_p, C.POINTER(Result)]
+    s = scenes.mirror_room(n=12)
+    cam = host.Camera(40, 30, (0.3, 1.6, 4.2), (0, 0.8, 0))
+    tris = np.ascontiguousarray(tri_array(s), np.float32).reshape(-1, 9)
+    M = magnitude_bound(s, cam.corners)
+    rays = primary_rays(cam.corners, 40, 30, 3, 1)
+    port.set_scene(s)
+    port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
+    _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+    ok = prim >= 0
+    brays = np.ascontiguousarray(reflected_rays(rays[ok], hit[ok], s.normals[prim[ok]]), np.float32)
+    refl = np.ascontiguousarray(prim[ok], np.int32)
+    t3 = tris.reshape(-1, 3)
+    lo = (t3.min(axis=0) - 0.01).astype(np.float32); hi = (t3.max(axis=0) + 0.01).astype(np.float32)
+    eye = np.ascontiguousarray(cam.eye, np.float64)
+    r = Result()
+    L.tpencil_check(eye.ctypes.data, 6e-6, float(M), lo.ctypes.data, hi.ctypes.data, len(tris), tris.ctypes.data, len(brays), brays.ctypes.data, refl.ctypes.data, 8,
+                    C.cast(port.L.orc_ray_triangle, C.c_void_p), C.byref(r))
+    good = checker.thread_pencil(eye, 6e-6, M, lo, hi, tris, brays, refl)
+    assert good.violations == 0 and good.ref_hits > 1000
+    assert r.violations > 0.5 * good.ref_hits, (r.violations, good.ref_hits)
+
+
 def bounce_like_rays(tris, rng, n):
     """Continuation-ray shaped rays (raytracing.cpp:266-285): origin = P + 0.01 * dir, dest = P + dir, P on a surface; half of
     them aimed at an edge / vertex point of another triangle."""
