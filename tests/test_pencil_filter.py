@@ -593,6 +593,55 @@ def test_thread_pencil_replay_detects_a_broken_filter(checker, port, tmp_path):
     assert r.violations > 0.5 * good.ref_hits, (r.violations, good.ref_hits)
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RT_MIRROR_SEEDS", "6"))))
+def test_mirror_pencil_on_random_tilted_planes(checker, port, seed):
+    """A tilted planar patch (float32 vertices: coplanar only up to rounding -- the group's plane is its first triangle's, as in
+    rt_upload_scene) under random blobs, random cameras.  Continuation rays of the primary hits anywhere go through the mirror
+    pencil of that plane: whatever the runtime check accepts must keep every pair the reference accepts; most rays off the
+    patch must be accepted."""
+    from raytracert_b200 import host
+    rng = np.random.default_rng(4200 + seed)
+    nq = int(rng.integers(6, 20))
+    a, b, c = rng.uniform(-0.6, 0.6), rng.uniform(-0.6, 0.6), rng.uniform(-0.5, 0.5)
+    u = np.linspace(-2.0, 2.0, nq + 1)
+    X, Z = np.meshgrid(u, u)
+    P = np.stack([X, a * X + b * Z + c, Z], axis=-1).reshape(-1, 3).astype(np.float32)
+    ii, jj = np.meshgrid(np.arange(nq), np.arange(nq))
+    q = (jj * (nq + 1) + ii).ravel()
+    patch = np.concatenate([np.stack([q, q + nq + 1, q + 1], 1), np.stack([q + 1, q + nq + 1, q + nq + 2], 1)])
+    nb = int(rng.integers(30, 150))
+    ctr = rng.uniform(-1.5, 1.5, (nb, 1, 3)) + np.array([0, 1.2, 0])
+    blobs = (ctr + 0.15 * rng.normal(size=(nb, 3, 3))).reshape(-1, 3).astype(np.float32)
+    v = np.concatenate([P, blobs])
+    idx = np.concatenate([patch, len(P) + np.arange(3 * nb).reshape(-1, 3)]).astype(np.uint32)
+    s = host.Scene(v, idx, np.zeros(len(idx), np.uint32), host.face_normals(v, idx), np.zeros((1, 16), np.float32))
+    eye = np.array([rng.uniform(-1, 1), rng.uniform(1.5, 3.5), rng.uniform(3.0, 5.0)])
+    cam = host.Camera(48, 36, tuple(eye), (rng.uniform(-0.5, 0.5), rng.uniform(0.0, 0.6), rng.uniform(-0.5, 0.5)))
+    tris = tri_array(s)
+    M = magnitude_bound(s, cam.corners)
+    rays = primary_rays(cam.corners, 48, 36, 2, 1)
+    port.set_scene(s)
+    port.configure(cam.eye, np.zeros((0, 3), np.float32), 0, 0)
+    _, prim, hit = port.trace(rays[:, :3], rays[:, 3:])
+    ok = prim >= 0
+    brays = reflected_rays(rays[ok], hit[ok], s.normals[prim[ok]])
+    on_patch = prim[ok] < len(patch)
+    # the group's plane: its first triangle's, in double (rt_upload_scene)
+    t0 = tris.reshape(-1, 3, 3)[0].astype(np.float64)
+    n = np.cross(t0[1] - t0[0], t0[2] - t0[0]); n /= np.linalg.norm(n)
+    checker.set_plane(n, float(n @ t0[0]))
+    try:
+        res = checker(3, cam.corners, M, tris, brays, 1.0, premise=False)
+        if not res.setup_ok:
+            return         # eye too close to the plane / frame too wide: the library serves no mirror pencil either
+        assert res.violations == 0, f"seed {seed}: {res.violations} accepted pairs filtered out (ray {res.first_bad_ray}, triangle {res.first_bad_tri})"
+        if on_patch.sum() > 100:
+            r_on = checker(3, cam.corners, M, tris, brays[on_patch], 1.0, premise=False)
+            assert r_on.unsafe_rays <= 0.1 * on_patch.sum(), f"seed {seed}: {r_on.unsafe_rays} of {on_patch.sum()} rays off the patch refused"
+    finally:
+        checker.set_plane((0, 1, 0), 0)
+
+
 def bounce_like_rays(tris, rng, n):
     """Continuation-ray shaped rays (raytracing.cpp:266-285): origin = P + 0.01 * dir, dest = P + dir, P on a surface; half of
     them aimed at an edge / vertex point of another triangle."""
